@@ -1,0 +1,270 @@
+"""ctypes front-end of the CPU oracle (oracle/*.c) -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  It is the checker, never the product path.  PARITY UNPINNED: see ora.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+LS_TYPE_CG, LS_TYPE_GMRES, LS_TYPE_NS, LS_TYPE_BICGS = 798, 797, 796, 795
+PRECOND_FSILS, PRECOND_RCS = 701, 709
+BC_TYPE_Dir, BC_TYPE_Neu = 0, 1
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+class FluidPar(C.Structure):
+    _fields_ = [("rho", C.c_double), ("mu", C.c_double), ("f", C.c_double * 3),
+                ("dt", C.c_double), ("af", C.c_double), ("am", C.c_double), ("gam", C.c_double)]
+
+
+class HeatPar(C.Structure):
+    _fields_ = [("nu", C.c_double), ("s", C.c_double), ("rho", C.c_double),
+                ("dt", C.c_double), ("af", C.c_double), ("am", C.c_double), ("gam", C.c_double)]
+
+
+class SubLs(C.Structure):
+    _fields_ = [("suc", C.c_int), ("mItr", C.c_int), ("sD", C.c_int), ("itr", C.c_int),
+                ("absTol", C.c_double), ("relTol", C.c_double), ("iNorm", C.c_double),
+                ("fNorm", C.c_double), ("dB", C.c_double), ("callD", C.c_double)]
+
+
+class Ls(C.Structure):
+    _fields_ = [("LS_type", C.c_int), ("Resm", C.c_int), ("Resc", C.c_int),
+                ("GM", SubLs), ("CG", SubLs), ("RI", SubLs)]
+
+
+def build(native: bool = False, force: bool = False) -> str:
+    name = "libsvfsi_oracle_native.so" if native else "libsvfsi_oracle.so"
+    path = os.path.join(_HERE, name)
+    srcs = [os.path.join(_HERE, f) for f in ("ora_elem.c", "ora_fsils.c", "ora.h")]
+    stale = (not os.path.exists(path)) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, name], stdout=subprocess.DEVNULL)
+    return path
+
+
+_libs = {}
+
+
+def lib(native: bool = False):
+    if native not in _libs:
+        L = C.CDLL(build(native))
+        L.ora_wtime.restype = C.c_double
+        L.ora_dotv.restype = C.c_double
+        L.ora_normv.restype = C.c_double
+        L.ora_world_create.restype = C.c_void_p
+        _libs[native] = L
+    return _libs[native]
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip)
+
+
+def _pp(arrs):
+    """array of per-rank pointers"""
+    return (C.c_void_p * len(arrs))(*[a.ctypes.data if a is not None else None for a in arrs])
+
+
+def fluid_par(rho, mu, f, dt, af, am, gam):
+    return FluidPar(rho, mu, (C.c_double * 3)(*f), dt, af, am, gam)
+
+
+def heat_par(nu, s, rho, dt, af, am, gam):
+    return HeatPar(nu, s, rho, dt, af, am, gam)
+
+
+# ------------------------------------------------------------------------------------------
+def tet4_tables():
+    w = np.zeros(4); N = np.zeros((4, 4)); Nxi = np.zeros((4, 3))
+    lib().ora_tet4_tables(_d(w), _d(N), _d(Nxi))
+    return w, N, Nxi
+
+
+def fluid_element(par, xl, al, yl, bfl):
+    """lR[a][i], lK[b][a][16] for one element (S/FLUID.f:84-168)."""
+    xl = np.ascontiguousarray(xl, dtype=np.float64); al = np.ascontiguousarray(al, dtype=np.float64)
+    yl = np.ascontiguousarray(yl, dtype=np.float64); bfl = np.ascontiguousarray(bfl, dtype=np.float64)
+    lR = np.zeros((4, 4)); lK = np.zeros((4, 4, 16)); flag = C.c_int(0)
+    lib().ora_fluid_element(C.byref(par), _d(xl), _d(al), _d(yl), _d(bfl), _d(lR), _d(lK), C.byref(flag))
+    return lR, lK, flag.value
+
+
+def heat_element(par, xl, al, yl):
+    xl = np.ascontiguousarray(xl, dtype=np.float64)
+    al = np.ascontiguousarray(al, dtype=np.float64); yl = np.ascontiguousarray(yl, dtype=np.float64)
+    lR = np.zeros(4); lK = np.zeros((4, 4)); flag = C.c_int(0)
+    lib().ora_heat_element(C.byref(par), _d(xl), _d(al), _d(yl), _d(lR), _d(lK), C.byref(flag))
+    return lR, lK, flag.value
+
+
+def lhsa(tnNo, IEN):
+    """(rowPtr[tnNo+1], colPtr[nnz]) 1-based, S/LHSA.f:38-262."""
+    IEN = np.ascontiguousarray(IEN, dtype=np.int32)
+    rp = _ip(); cp = _ip(); nnz = C.c_int(0)
+    iso = lib().ora_lhsa(int(tnNo), int(IEN.shape[0]), _i(IEN), C.byref(rp), C.byref(cp), C.byref(nnz))
+    rowPtr = np.ctypeslib.as_array(rp, shape=(tnNo + 1,)).copy()
+    colPtr = np.ctypeslib.as_array(cp, shape=(max(nnz.value, 1),))[: nnz.value].copy()
+    lib().ora_free(rp); lib().ora_free(cp)
+    if iso:
+        raise RuntimeError(f"Node {iso} is isolated")
+    return rowPtr, colPtr
+
+
+def construct_fluid(par, IEN, x, Ag, Yg, Bf, rowPtr, colPtr, faithful=False, native=False):
+    IEN = np.ascontiguousarray(IEN, dtype=np.int32)
+    tnNo = x.shape[0]; nnz = colPtr.shape[0]
+    R = np.zeros((tnNo, 4)); Val = np.zeros((nnz, 16))
+    nbad = lib(native).ora_construct_fluid(
+        C.byref(par), int(IEN.shape[0]), _i(IEN), _d(np.ascontiguousarray(x)),
+        _d(np.ascontiguousarray(Ag)), _d(np.ascontiguousarray(Yg)), _d(np.ascontiguousarray(Bf)),
+        _i(rowPtr), _i(colPtr), _d(R), _d(Val), int(faithful))
+    if nbad:
+        raise RuntimeError(f"Jac < 0 @ {nbad} elements")
+    return R, Val
+
+
+def construct_heats(par, IEN, x, Ag, Yg, rowPtr, colPtr, native=False):
+    IEN = np.ascontiguousarray(IEN, dtype=np.int32)
+    tnNo = x.shape[0]; nnz = colPtr.shape[0]
+    R = np.zeros(tnNo); Val = np.zeros(nnz)
+    nbad = lib(native).ora_construct_heats(
+        C.byref(par), int(IEN.shape[0]), _i(IEN), _d(np.ascontiguousarray(x)),
+        _d(np.ascontiguousarray(Ag)), _d(np.ascontiguousarray(Yg)), _i(rowPtr), _i(colPtr), _d(R), _d(Val))
+    if nbad:
+        raise RuntimeError(f"Jac < 0 @ {nbad} elements")
+    return R, Val
+
+
+# ------------------------------------------------------------------------------------------
+class World:
+    """nTasks simulated FSILS ranks (FSILS_LHS_CREATE on each, L/LHS.f:51-293)."""
+
+    def __init__(self, gnNo, ltg_list, rowPtr_list, colPtr_list, nFaces, native=False):
+        self.L = lib(native)
+        self.n = len(ltg_list)
+        self.ltg = [np.ascontiguousarray(a, dtype=np.int32) for a in ltg_list]
+        self.rowPtr = [np.ascontiguousarray(a, dtype=np.int32) for a in rowPtr_list]
+        self.colPtr = [np.ascontiguousarray(a, dtype=np.int32) for a in colPtr_list]
+        self.nNo = np.array([a.size for a in self.ltg], dtype=np.int32)
+        self.nnz = np.array([a.size for a in self.colPtr], dtype=np.int32)
+        self.nFaces = nFaces
+        self.h = C.c_void_p(self.L.ora_world_create(
+            self.n, int(gnNo), _i(self.nNo), _i(self.nnz), _pp(self.ltg), _pp(self.rowPtr),
+            _pp(self.colPtr), int(nFaces)))
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.ora_world_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def info(self, r):
+        a = C.c_int(); b = C.c_int(); c = C.c_int()
+        self.L.ora_world_info(self.h, r, C.byref(a), C.byref(b), C.byref(c))
+        return dict(mynNo=a.value, shnNo=b.value, nReq=c.value)
+
+    def map(self, r):
+        m = np.zeros(self.nNo[r], dtype=np.int32)
+        self.L.ora_world_map(self.h, r, _i(m))
+        return m
+
+    def rowptr(self, r):
+        rp = np.zeros((self.nNo[r], 2), dtype=np.int32); cp = np.zeros(self.nnz[r], dtype=np.int32)
+        dp = np.zeros(self.nNo[r], dtype=np.int32)
+        self.L.ora_world_rowptr(self.h, r, _i(rp), _i(cp), _i(dp))
+        return rp, cp, dp
+
+    def cs(self, r):
+        out = []
+        for i in range(self.info(r)["nReq"]):
+            iP = C.c_int(); n = C.c_int()
+            self.L.ora_world_cs(self.h, r, i, C.byref(iP), C.byref(n), None)
+            ptr = np.zeros(n.value, dtype=np.int32)
+            self.L.ora_world_cs(self.h, r, i, C.byref(iP), C.byref(n), _i(ptr))
+            out.append((iP.value, ptr))
+        return out
+
+    def bc_create(self, faIn, gNodes_list, dof, BC_type, val_list=None):
+        gN = [np.ascontiguousarray(g, dtype=np.int32) for g in gNodes_list]
+        nNo = np.array([g.size for g in gN], dtype=np.int32)
+        if val_list is None:
+            vp = None
+        else:
+            vals = [np.ascontiguousarray(v, dtype=np.float64) for v in val_list]
+            vp = _pp(vals)
+        self.L.ora_bc_create(self.h, int(faIn), _i(nNo), int(dof), int(BC_type), _pp(gN), vp)
+
+    def commuv(self, dof, R_list):
+        self.L.ora_commuv(self.h, int(dof), _pp(R_list))
+
+    def sparmul_vv(self, dof, K_list, U_list):
+        KU = [np.zeros_like(u) for u in U_list]
+        self.L.ora_sparmul_vv(self.h, int(dof), _pp(K_list), _pp(U_list), _pp(KU))
+        return KU
+
+    def sparmul_ss(self, K_list, U_list):
+        KU = [np.zeros_like(u) for u in U_list]
+        self.L.ora_sparmul_ss(self.h, _pp(K_list), _pp(U_list), _pp(KU))
+        return KU
+
+    def sparmul_vs(self, dof, K_list, U_list):
+        KU = [np.zeros(u.shape[0]) for u in U_list]
+        self.L.ora_sparmul_vs(self.h, int(dof), _pp(K_list), _pp(U_list), _pp(KU))
+        return KU
+
+    def sparmul_sv(self, dof, K_list, U_list):
+        KU = [np.zeros((u.shape[0], dof)) for u in U_list]
+        self.L.ora_sparmul_sv(self.h, int(dof), _pp(K_list), _pp(U_list), _pp(KU))
+        return KU
+
+    def dotv(self, dof, U_list, V_list):
+        return self.L.ora_dotv(self.h, int(dof), _pp(U_list), _pp(V_list))
+
+    def solve(self, ls: Ls, dof, Ri_list, Val_list, prec=PRECOND_FSILS, incL=None, res=None):
+        """FSILS_SOLVE (L/SOLVE.f:51-143): Ri_list/Val_list are modified in place."""
+        incp = _i(np.ascontiguousarray(incL, dtype=np.int32)) if incL is not None else None
+        resp = _d(np.ascontiguousarray(res, dtype=np.float64)) if res is not None else None
+        self.L.ora_fsils_solve(self.h, C.byref(ls), int(dof), _pp(Ri_list), _pp(Val_list),
+                               int(prec), incp, resp)
+        return ls
+
+
+def ls_create(LS_type, relTol=None, absTol=None, maxItr=None, dimKry=None,
+              relTolIn=None, absTolIn=None, maxItrIn=None) -> Ls:
+    """FSILS_LS_CREATE with the optional overrides of L/LS.f:97-116."""
+    ls = Ls()
+    lib().ora_ls_create(C.byref(ls), int(LS_type))
+    if relTol is not None: ls.RI.relTol = relTol
+    if absTol is not None: ls.RI.absTol = absTol
+    if maxItr is not None: ls.RI.mItr = maxItr
+    if dimKry is not None:
+        ls.RI.sD = dimKry; ls.GM.sD = dimKry
+    if relTolIn is not None:
+        ls.GM.relTol, ls.CG.relTol = relTolIn
+    if absTolIn is not None:
+        ls.GM.absTol, ls.CG.absTol = absTolIn
+    if maxItrIn is not None:
+        ls.GM.mItr, ls.CG.mItr = maxItrIn
+    return ls
+
+
+def ge(A, B):
+    A = np.asfortranarray(A, dtype=np.float64); B = np.array(B, dtype=np.float64)
+    ok = lib().ora_ge(A.shape[0], B.size, _d(A), _d(B))
+    return bool(ok), B

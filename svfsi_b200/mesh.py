@@ -1,0 +1,252 @@
+"""Synthetic tet-cylinder problems for the svFSI fluid hot path (host-side input generator).
+
+Produces exactly the arrays svFSI holds after READFILES/DISTRIBUTE/INITIALIZE for a one-mesh,
+one-domain TET4 case (reference: Code/Source/svFSI):
+
+* ``x(nsd,tnNo)``, ``IEN(eNoN,nEl)`` 1-based with svFSI's orientation (positive Jacobian, i.e.
+  ``((x2-x1) x (x3-x2)).(x4-x3) < 0``, READMSH.f:1133-1149),
+* faces inlet / outlet / wall as global node lists (+ boundary triangles), like ``msh%fa(:)%gN``,
+* a k-way element partition with per-rank first-touch local numbering and ``ltg`` exactly as
+  DISTRIBUTE.f:1455-1529 builds them (elements disjoint, cut nodes replicated, no ghosts),
+* generalised-alpha constants (INITIALIZE.f:78-139) and a Poiseuille + perturbation state.
+
+The lattice is Kuhn's 6-tet subdivision of a structured (nx, ny, nz) grid whose square cross
+section is mapped radially onto a disc.  The subdivision is mirrored per quadrant so that the
+cube diagonal always passes through the outer corner of the four corner columns (keeps the
+corner tets well shaped); nx and ny must be even.
+"""
+from __future__ import annotations
+
+import itertools
+from dataclasses import dataclass, field
+
+import numpy as np
+
+SEED = 1234  # seed for numpy default_rng
+
+
+@dataclass
+class Face:
+    name: str
+    gN: np.ndarray            # global node ids (1-based, int32, ascending)
+    tri: np.ndarray           # (nTri, 3) global node ids (1-based) of boundary triangles
+    parent: np.ndarray        # (nTri,) 0-based parent element id
+
+
+@dataclass
+class Mesh:
+    x: np.ndarray             # (nNo, 3) float64
+    IEN: np.ndarray           # (nEl, 4) int32, 1-based
+    faces: dict = field(default_factory=dict)
+    cell_k: np.ndarray | None = None   # (nEl,) axial cell index of every element (for slabs)
+    dims: tuple = (0, 0, 0)
+    R: float = 1.0
+    L: float = 1.0
+
+    @property
+    def nNo(self):
+        return self.x.shape[0]
+
+    @property
+    def nEl(self):
+        return self.IEN.shape[0]
+
+
+def _kuhn_paths():
+    """Six monotone lattice paths (0,0,0)->(1,1,1); each is one tet of the Kuhn subdivision."""
+    tets = []
+    for perm in itertools.permutations(range(3)):
+        v = np.zeros(3, dtype=np.int64)
+        verts = [v.copy()]
+        for ax in perm:
+            v[ax] += 1
+            verts.append(v.copy())
+        tets.append(np.array(verts))
+    return np.array(tets)  # (6, 4, 3)
+
+
+def make_cylinder(nx: int, ny: int, nz: int, R: float = 2.0, L: float = 30.0) -> Mesh:
+    """Kuhn-lattice tet cylinder with 6*nx*ny*nz elements and (nx+1)(ny+1)(nz+1) nodes."""
+    if nx % 2 or ny % 2:
+        raise ValueError("nx and ny must be even (quadrant-mirrored Kuhn subdivision)")
+    gx = np.linspace(-1.0, 1.0, nx + 1)
+    gy = np.linspace(-1.0, 1.0, ny + 1)
+    gz = np.linspace(0.0, L, nz + 1)
+    X, Y, Z = np.meshgrid(gx, gy, gz, indexing="ij")
+    rad = np.sqrt(X * X + Y * Y)
+    cheb = np.maximum(np.abs(X), np.abs(Y))
+    scale = np.where(rad > 0, cheb / np.where(rad > 0, rad, 1.0), 1.0)
+    x = np.stack([R * X * scale, R * Y * scale, Z], axis=-1).reshape(-1, 3)
+
+    def nid(i, j, k):
+        return (i * (ny + 1) + j) * (nz + 1) + k
+
+    ci, cj, ck = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    ci = ci.ravel(); cj = cj.ravel(); ck = ck.ravel()
+    fx = ci < nx // 2           # mirror in x on the -x half
+    fy = cj < ny // 2
+    paths = _kuhn_paths()
+    ien = np.empty((ci.size, 6, 4), dtype=np.int64)
+    for t in range(6):
+        for v in range(4):
+            dx, dy, dz = paths[t, v]
+            ii = ci + np.where(fx, 1 - dx, dx)
+            jj = cj + np.where(fy, 1 - dy, dy)
+            kk = ck + dz
+            ien[:, t, v] = nid(ii, jj, kk)
+    cell_k = np.repeat(ck, 6)
+    ien = ien.reshape(-1, 4)
+    # svFSI orientation: swap nodes 1,2 where the Jacobian is negative (READMSH.f:1133-1149)
+    a = x[ien[:, 0]] - x[ien[:, 3]]
+    b = x[ien[:, 1]] - x[ien[:, 3]]
+    c = x[ien[:, 2]] - x[ien[:, 3]]
+    jac = np.einsum("ij,ij->i", np.cross(a, b), c)
+    neg = jac < 0
+    ien[neg, 0], ien[neg, 1] = ien[neg, 1].copy(), ien[neg, 0].copy()
+    m = Mesh(x=np.ascontiguousarray(x), IEN=(ien + 1).astype(np.int32), cell_k=cell_k,
+             dims=(nx, ny, nz), R=R, L=L)
+    _make_faces(m, nx, ny, nz)
+    return m
+
+
+def _make_faces(m: Mesh, nx, ny, nz):
+    """Boundary triangles = tet faces whose three nodes lie on the same boundary surface."""
+    idx = np.arange(m.nNo)
+    k = idx % (nz + 1)
+    j = (idx // (nz + 1)) % (ny + 1)
+    i = idx // ((nz + 1) * (ny + 1))
+    on = {
+        "inlet": k == 0,
+        "outlet": k == nz,
+        "wall": (i == 0) | (i == nx) | (j == 0) | (j == ny),
+    }
+    ien0 = m.IEN.astype(np.int64) - 1
+    local_faces = [(0, 1, 2), (0, 1, 3), (0, 2, 3), (1, 2, 3)]
+    for name, mask in on.items():
+        tris, parents = [], []
+        for lf in local_faces:
+            f = ien0[:, lf]
+            sel = mask[f].all(axis=1)
+            if name == "wall":
+                # all three on the lateral surface AND on the same side plane
+                ii, jj = i[f], j[f]
+                same = ((ii == 0).all(1) | (ii == nx).all(1) | (jj == 0).all(1) | (jj == ny).all(1))
+                sel &= same
+            tris.append(f[sel])
+            parents.append(np.nonzero(sel)[0])
+        tri = np.concatenate(tris)
+        par = np.concatenate(parents)
+        gN = np.nonzero(mask)[0]
+        m.faces[name] = Face(name, (gN + 1).astype(np.int32), (tri + 1).astype(np.int32), par)
+
+
+def face_normal_integrals(m: Mesh, face: Face, node_ids: np.ndarray, tri_sel=None):
+    """sV(:,Ac) = sum_e sum_g N(a,g) w(g) n  over the face's triangles (BAFINI.f:515-529), with n the
+    outward area-weighted normal of GNNB (NN.f:1974-1991).  For TRI3 (3 Gauss points, w=1/6,
+    NN.f:416-422) this is (area-normal)/3 per node.  Returns val(len(node_ids), 3) for the given
+    1-based global node ids; ``tri_sel`` restricts to a subset of triangles (one rank's share)."""
+    tri = face.tri if tri_sel is None else face.tri[tri_sel]
+    par = face.parent if tri_sel is None else face.parent[tri_sel]
+    p = m.x[tri.astype(np.int64) - 1]                     # (nTri, 3, 3)
+    nrm = np.cross(p[:, 1] - p[:, 0], p[:, 2] - p[:, 0])  # 2*area*n
+    cen_el = m.x[m.IEN[par].astype(np.int64) - 1].mean(axis=1)
+    flip = np.einsum("ij,ij->i", nrm, p.mean(axis=1) - cen_el) < 0
+    nrm[flip] *= -1.0
+    # sum_g N(a,g)*w(g) = 1/6 for every node of TRI3; |n| from GNNB = 2*area
+    contrib = nrm / 6.0
+    sV = np.zeros((m.nNo, 3))
+    for v in range(3):
+        np.add.at(sV, tri[:, v].astype(np.int64) - 1, contrib)
+    return sV[node_ids.astype(np.int64) - 1]
+
+
+# ----------------------------------------------------------------------------------------------
+def gen_alpha(rho_inf: float = 0.2):
+    """First-order generalised-alpha constants, INITIALIZE.f:78-79,136-139."""
+    am = 0.5 * (3.0 - rho_inf) / (1.0 + rho_inf)
+    af = 1.0 / (1.0 + rho_inf)
+    gam = 0.5 + am - af
+    beta = 0.25 * (1.0 + am - af) ** 2
+    return dict(am=am, af=af, gam=gam, beta=beta)
+
+
+def poiseuille_state(m: Mesh, umax: float = 10.0, dpdz: float = -1.0, pert: float = 0.01,
+                     seed: int = SEED, acc: float = 0.0):
+    """Yg(tnNo,4) = Poiseuille (u,v,w,p) + `pert`*umax uniform noise on velocity; Ag(tnNo,4)."""
+    rng = np.random.default_rng(seed)
+    r2 = (m.x[:, 0] ** 2 + m.x[:, 1] ** 2) / (m.R ** 2)
+    Yg = np.zeros((m.nNo, 4))
+    Yg[:, 2] = umax * np.clip(1.0 - r2, 0.0, None)
+    Yg[:, :3] += pert * umax * rng.uniform(-1.0, 1.0, size=(m.nNo, 3))
+    Yg[:, 3] = dpdz * (m.x[:, 2] - m.L)
+    Ag = np.zeros((m.nNo, 4))
+    if acc:
+        Ag[:, :3] = acc * rng.uniform(-1.0, 1.0, size=(m.nNo, 3))
+    return Ag, Yg
+
+
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class RankMesh:
+    """One rank's share, numbered like DISTRIBUTE.f:1455-1529 (first-touch local ids)."""
+    rank: int
+    ltg: np.ndarray           # (nNo_local,) global node id (1-based)
+    IEN: np.ndarray           # (nEl_local, 4) local node ids (1-based)
+    x: np.ndarray             # (nNo_local, 3)
+    elems: np.ndarray         # global 0-based element ids owned by the rank (ascending)
+    faces: dict = field(default_factory=dict)   # name -> dict(gN local ids, gN_global, tri_sel)
+
+    @property
+    def nNo(self):
+        return self.ltg.shape[0]
+
+    @property
+    def nEl(self):
+        return self.IEN.shape[0]
+
+
+def partition_slabs(m: Mesh, nparts: int) -> np.ndarray:
+    """Element -> rank by axial slab with (nearly) equal element counts (stand-in for ParMETIS
+    PartMeshKway, SPLIT.c:114; any element-disjoint partition is valid)."""
+    nz = m.dims[2]
+    bounds = np.linspace(0, nz, nparts + 1).round().astype(np.int64)
+    part = np.searchsorted(bounds, m.cell_k, side="right") - 1
+    return np.clip(part, 0, nparts - 1).astype(np.int32)
+
+
+def first_touch_unique(ien_flat: np.ndarray):
+    """Unique values of `ien_flat` in order of first appearance, and the inverse map."""
+    uniq, first, inv = np.unique(ien_flat, return_index=True, return_inverse=True)
+    order = np.argsort(first, kind="stable")
+    rank_of = np.empty_like(order)
+    rank_of[order] = np.arange(order.size)
+    return uniq[order], rank_of[inv]
+
+
+def split_mesh(m: Mesh, part: np.ndarray, nparts: int):
+    out = []
+    for p in range(nparts):
+        elems = np.nonzero(part == p)[0]
+        ien_g = m.IEN[elems].astype(np.int64)
+        ltg, inv = first_touch_unique(ien_g.ravel())
+        ien_l = (inv.reshape(-1, 4) + 1).astype(np.int32)
+        rm = RankMesh(rank=p, ltg=ltg.astype(np.int32), IEN=ien_l,
+                      x=np.ascontiguousarray(m.x[ltg - 1]), elems=elems)
+        gtl = np.zeros(m.nNo + 1, dtype=np.int64)
+        gtl[ltg] = np.arange(1, ltg.size + 1)
+        owned = np.zeros(m.nEl, dtype=bool)
+        owned[elems] = True
+        for name, fa in m.faces.items():
+            # PARTFACE (DISTRIBUTE.f:1679-1698): triangles whose parent tet is local; node list =
+            # every global face node present on this rank.
+            loc = gtl[fa.gN]
+            keep = loc != 0
+            rm.faces[name] = dict(gN=loc[keep].astype(np.int32), gN_global=fa.gN[keep],
+                                  tri_sel=owned[fa.parent])
+        out.append(rm)
+    return out
+
+
+def scatter_nodal(rm: RankMesh, U: np.ndarray) -> np.ndarray:
+    """LOCAL(): a rank's copy of a global nodal array (DISTRIBUTE.f:221-231)."""
+    return np.ascontiguousarray(U[rm.ltg.astype(np.int64) - 1])

@@ -1,0 +1,551 @@
+// asm_kernels.cu -- element loops of svFSI on sm_100a: CONSTRUCT_FLUID
+// (S/FLUID.f:40-190 with FLUID3D_M :192-560 and FLUID3D_C :813-1084) and
+// CONSTRUCT_HEATS (S/HEATS.f:39-159) for linear tetrahedra, fused with the
+// DOASSEM scatter (S/LHSA.f:266-298) into the dof x dof block-CSR matrix.
+//
+// B200 design (not a transcription of the Fortran loop):
+//  * For TET4 the shape-function gradients, metric tensor, velocity gradient and
+//    every product of them are element constants; only N_a(g)-weighted
+//    quantities change between the four Gauss points (S/NN.f:268-275,654-671).
+//    The kernel therefore reduces the four Gauss points to ~40 per-element
+//    scalars (phase 1, one thread per element) and expands them into the sixteen
+//    4x4 tangent blocks only at scatter time (phase 2).  Identically-zero terms
+//    of the reference (second derivatives, viscosity gradient)
+//    are dropped.  ~2 kflop/element instead of ~15 kflop: the kernel is bound by
+//    the 2 KB/element scatter, not by FP64 issue.
+//  * Phase 2 is warp-cooperative: 8 consecutive lanes own one 128-byte tangent
+//    block (16 bytes per lane), so every warp-level store/atomic instruction
+//    covers four whole 128-byte lines of Val.
+//  * Two scatter variants: FP64 atomics (RED.ADD.F64, any element order) and a
+//    plain read-modify-write used with the greedy element colouring (no two
+//    elements of a colour share a node: deterministic).
+#include <cuda_runtime.h>
+#include <float.h>
+
+#include "ctx.h"
+#include "kernels.h"
+
+namespace svfsi {
+
+static constexpr int NE = 128;       // elements per CTA
+static constexpr int NEP = NE + 1;   // padded field stride in shared memory (bank spread)
+
+// field ids of the per-element compact record in shared memory
+enum {
+  F_NX = 0,     // 12: Nx(i,a) at F_NX + a*3 + i
+  F_D = 12,     // 16: 4 mu NxNx_ab + A_ab at F_D + a*4 + b
+  F_C2 = 28,    // 4 : rho sum_g tauM uaNx_a
+  F_R2 = 32,    // 4 : rho sum_g tauM (uNx_b + amd N_b)
+  F_STC = 36,   // sum_g tauC
+  F_STM = 37,   // sum_g tauM
+  F_WL = 38,    // wl = w * af*gam*dt
+  F_LR = 39,    // 16: lR(i,a) at F_LR + a*4 + i
+  F_COUNT = 55
+};
+
+// S/UTIL.f:879-903 ISZERO(x) with one argument
+__device__ __forceinline__ bool iszero1(double x) {
+  const double a = fabs(x);
+  const double nrm = a > DBL_EPSILON ? a : DBL_EPSILON;
+  return a / nrm < 10.0 * DBL_EPSILON;
+}
+
+struct Tet4Tab {
+  double N[4][4];  // N[g][a]
+  double sN[4];    // sum_g N[g][a]
+};
+
+__device__ __forceinline__ void tet4_tab(Tet4Tab &t) {
+  // S/NN.f:268-275 (GETGIP) and :654-658 (GETGNN); N4 = 1 - xi1 - xi2 - xi3 as computed
+  const double s = (5.0 + 3.0 * sqrt(5.0)) / 20.0;
+  const double q = (5.0 - sqrt(5.0)) / 20.0;
+#pragma unroll
+  for (int g = 0; g < 4; g++) {
+    const double x0 = (g == 0) ? s : q, x1 = (g == 1) ? s : q, x2 = (g == 2) ? s : q;
+    t.N[g][0] = x0;
+    t.N[g][1] = x1;
+    t.N[g][2] = x2;
+    t.N[g][3] = 1.0 - x0 - x1 - x2;
+  }
+#pragma unroll
+  for (int a = 0; a < 4; a++) t.sN[a] = t.N[0][a] + t.N[1][a] + t.N[2][a] + t.N[3][a];
+}
+
+// GNN for TET4, S/NN.f:1515-1561: Jacobian, inverse, metric ks, Nx
+__device__ __forceinline__ void gnn_tet4(const double xl[4][3], double Nx[4][3], double &Jac,
+                                         double ks[3][3]) {
+  double X[3][3], XI[3][3];
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) X[r][c] = xl[c][r] - xl[3][r];
+  Jac = X[0][0] * X[1][1] * X[2][2] + X[0][1] * X[1][2] * X[2][0] + X[0][2] * X[1][0] * X[2][1] -
+        X[0][0] * X[1][2] * X[2][1] - X[0][1] * X[1][0] * X[2][2] - X[0][2] * X[1][1] * X[2][0];
+  XI[0][0] = (X[1][1] * X[2][2] - X[1][2] * X[2][1]) / Jac;
+  XI[0][1] = (X[2][1] * X[0][2] - X[2][2] * X[0][1]) / Jac;
+  XI[0][2] = (X[0][1] * X[1][2] - X[0][2] * X[1][1]) / Jac;
+  XI[1][0] = (X[1][2] * X[2][0] - X[1][0] * X[2][2]) / Jac;
+  XI[1][1] = (X[2][2] * X[0][0] - X[2][0] * X[0][2]) / Jac;
+  XI[1][2] = (X[0][2] * X[1][0] - X[0][0] * X[1][2]) / Jac;
+  XI[2][0] = (X[1][0] * X[2][1] - X[1][1] * X[2][0]) / Jac;
+  XI[2][1] = (X[2][0] * X[0][1] - X[2][1] * X[0][0]) / Jac;
+  XI[2][2] = (X[0][0] * X[1][1] - X[0][1] * X[1][0]) / Jac;
+  ks[0][0] = XI[0][0] * XI[0][0] + XI[1][0] * XI[1][0] + XI[2][0] * XI[2][0];
+  ks[0][1] = XI[0][1] * XI[0][0] + XI[1][1] * XI[1][0] + XI[2][1] * XI[2][0];
+  ks[0][2] = XI[0][2] * XI[0][0] + XI[1][2] * XI[1][0] + XI[2][2] * XI[2][0];
+  ks[1][1] = XI[0][1] * XI[0][1] + XI[1][1] * XI[1][1] + XI[2][1] * XI[2][1];
+  ks[1][2] = XI[0][1] * XI[0][2] + XI[1][1] * XI[1][2] + XI[2][1] * XI[2][2];
+  ks[2][2] = XI[0][2] * XI[0][2] + XI[1][2] * XI[1][2] + XI[2][2] * XI[2][2];
+  ks[1][0] = ks[0][1];
+  ks[2][0] = ks[0][2];
+  ks[2][1] = ks[1][2];
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    Nx[0][c] = XI[0][c];
+    Nx[1][c] = XI[1][c];
+    Nx[2][c] = XI[2][c];
+    Nx[3][c] = -XI[0][c] - XI[1][c] - XI[2][c];
+  }
+}
+
+__device__ __forceinline__ void red_add(double *p, double v) { atomicAdd(p, v); }
+
+// ---------------------------------------------------------------------------
+template <bool ATOMIC>
+__global__ void __launch_bounds__(NE) fluid_asm_kernel(FluidPar par, int n, int e0,
+                                                       const int *__restrict__ elems,
+                                                       const int *__restrict__ ien,
+                                                       const int *__restrict__ edest,
+                                                       const double *__restrict__ x,
+                                                       const double *__restrict__ Ag,
+                                                       const double *__restrict__ Yg,
+                                                       const double *__restrict__ Bf,
+                                                       double *__restrict__ R,
+                                                       double *__restrict__ Val,
+                                                       int *__restrict__ badJac) {
+  extern __shared__ double sm[];      // [F_COUNT][NEP]
+  __shared__ int sEl[NE];             // element id per slot (-1 = none)
+  __shared__ int sNode[NE * 4];
+
+  const int slot = threadIdx.x;
+  const int idx = blockIdx.x * NE + slot;
+  int e = -1;
+  if (idx < n) e = elems ? elems[e0 + idx] : e0 + idx;
+  sEl[slot] = e;
+
+  // ---------------- phase 1: one thread per element ----------------
+  if (e >= 0) {
+    Tet4Tab tab;
+    tet4_tab(tab);
+    int nd[4];
+    {
+      const int4 v = __ldg((const int4 *)ien + e);
+      nd[0] = v.x; nd[1] = v.y; nd[2] = v.z; nd[3] = v.w;
+    }
+    double xl[4][3], al[4][3], yl[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      sNode[slot * 4 + a] = nd[a];
+      const double *xp = x + (size_t)nd[a] * 3;
+      xl[a][0] = __ldg(xp); xl[a][1] = __ldg(xp + 1); xl[a][2] = __ldg(xp + 2);
+      const double2 *ap = (const double2 *)(Ag + (size_t)nd[a] * 4);
+      const double2 a01 = __ldg(ap), a23 = __ldg(ap + 1);
+      al[a][0] = a01.x; al[a][1] = a01.y; al[a][2] = a23.x;
+      const double2 *yp = (const double2 *)(Yg + (size_t)nd[a] * 4);
+      const double2 y01 = __ldg(yp), y23 = __ldg(yp + 1);
+      yl[a][0] = y01.x; yl[a][1] = y01.y; yl[a][2] = y23.x; yl[a][3] = y23.y;
+      if (Bf) {  // ud uses al - bfl (S/FLUID.f:236-238)
+        const double *bp = Bf + (size_t)nd[a] * 3;
+        al[a][0] = al[a][0] - __ldg(bp);
+        al[a][1] = al[a][1] - __ldg(bp + 1);
+        al[a][2] = al[a][2] - __ldg(bp + 2);
+      }
+    }
+    double Nx[4][3], Jac, ks[3][3];
+    gnn_tet4(xl, Nx, Jac, ks);
+    if (iszero1(Jac)) atomicAdd(badJac, 1);
+
+    const double rho = par.rho, mu = par.mu;
+    const double T1c = par.af * par.gam * par.dt;
+    const double amd = par.am / T1c;
+    const double w = (1.0 / 24.0) * Jac;
+    const double wl = w * T1c;
+    const double wr = w * rho;
+
+    // element constants: velocity gradient ux(j,i) = d u_i / d x_j, pressure gradient
+    double ux[3][3], px[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      px[j] = 0.0;
+#pragma unroll
+      for (int i = 0; i < 3; i++) ux[j][i] = 0.0;
+    }
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        px[j] = px[j] + Nx[a][j] * yl[a][3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) ux[j][i] = ux[j][i] + Nx[a][j] * yl[a][i];
+      }
+    }
+    const double divU = ux[0][0] + ux[1][1] + ux[2][2];
+    double es[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+      for (int i = 0; i < 3; i++) es[j][i] = ux[j][i] + ux[i][j];
+
+    double tq = 1.0 / par.dt;
+    const double kT = 4.0 * (tq * tq);
+    double kS = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) kS = kS + ks[j][i] * ks[j][i];
+    tq = mu / rho;
+    kS = 36.0 * kS * (tq * tq);
+    const double trks = ks[0][0] + ks[1][1] + ks[2][2];
+
+    // accumulators over the Gauss points
+    double A[4][4], c2[4], r2[4], sTC = 0.0, sTM = 0.0;
+    double sRM[3][3], sNrV[4][3], lR4[4];
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      c2[a] = 0.0; r2[a] = 0.0; lR4[a] = 0.0;
+#pragma unroll
+      for (int b = 0; b < 4; b++) A[a][b] = 0.0;
+#pragma unroll
+      for (int i = 0; i < 3; i++) sNrV[a][i] = 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+      for (int i = 0; i < 3; i++) sRM[j][i] = 0.0;
+
+#pragma unroll 1
+    for (int g = 0; g < 4; g++) {
+      double Ng[4];
+#pragma unroll
+      for (int a = 0; a < 4; a++) Ng[a] = tab.N[g][a];
+      double ud[3], u[3], p = 0.0;
+#pragma unroll
+      for (int i = 0; i < 3; i++) { ud[i] = -par.f[i]; u[i] = 0.0; }
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          ud[i] = ud[i] + Ng[a] * al[a][i];
+          u[i] = u[i] + Ng[a] * yl[a][i];
+        }
+        p = p + Ng[a] * yl[a][3];
+      }
+      double kU = 0.0;
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) kU = kU + u[j] * u[i] * ks[j][i];
+      const double tauM = 1.0 / (rho * sqrt(kT + kU + kS));
+      double rV[3], up[3], ua[3];
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        rV[i] = ud[i] + u[0] * ux[0][i] + u[1] * ux[1][i] + u[2] * ux[2][i];
+        up[i] = -tauM * (rho * rV[i] + px[i]);
+      }
+      const double tauC = 1.0 / (tauM * trks);
+      double tauB = 0.0;
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) tauB = tauB + up[j] * up[i] * ks[j][i];
+      if (iszero1(tauB)) tauB = DBL_EPSILON;
+      tauB = rho / sqrt(tauB);
+#pragma unroll
+      for (int i = 0; i < 3; i++) ua[i] = u[i] + up[i];
+      const double pa = p - tauC * divU;
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+        rV[i] = tauB * (up[0] * ux[0][i] + up[1] * ux[1][i] + up[2] * ux[2][i]);
+      // rM(j,i), S/FLUID.f:427-439, summed over g
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          double v = mu * es[j][i] - rho * up[i] * ua[j] + rV[i] * up[j];
+          if (i == j) v = v - pa;
+          sRM[j][i] = sRM[j][i] + v;
+        }
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+        rV[i] = ud[i] + ua[0] * ux[0][i] + ua[1] * ux[1][i] + ua[2] * ux[2][i];
+
+      double uNx[4], upNx[4], uaNx[4];
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+        uNx[a] = u[0] * Nx[a][0] + u[1] * Nx[a][1] + u[2] * Nx[a][2];
+        upNx[a] = up[0] * Nx[a][0] + up[1] * Nx[a][1] + up[2] * Nx[a][2];
+        uaNx[a] = uNx[a] + upNx[a];
+#pragma unroll
+        for (int i = 0; i < 3; i++) sNrV[a][i] = sNrV[a][i] + Ng[a] * rV[i];
+        // continuity residual, S/FLUID.f:1046-1049
+        lR4[a] = lR4[a] + (Ng[a] * divU - upNx[a]);
+        c2[a] = c2[a] + tauM * uaNx[a];
+        r2[a] = r2[a] + tauM * (uNx[a] + amd * Ng[a]);
+      }
+      sTC = sTC + tauC;
+      sTM = sTM + tauM;
+      // diagonal-term scalar of the momentum tangent (S/FLUID.f:497-498 plus the
+      // -rho tauM uaNx_a updu(i,i,b) part with updu(i,i,b) = -rho uNx_b)
+#pragma unroll
+      for (int b = 0; b < 4; b++)
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+          A[a][b] = A[a][b] + (rho * amd * Ng[b] * (Ng[a] + rho * tauM * uaNx[a]) +
+                               rho * Ng[a] * (uNx[b] + upNx[b]) + tauB * upNx[a] * upNx[b] +
+                               rho * tauM * uaNx[a] * (rho * uNx[b]));
+    }
+
+    // store the compact record
+    double *rec = sm + slot;
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+#pragma unroll
+      for (int i = 0; i < 3; i++) rec[(F_NX + a * 3 + i) * NEP] = Nx[a][i];
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        const double nn = Nx[a][0] * Nx[b][0] + Nx[a][1] * Nx[b][1] + Nx[a][2] * Nx[b][2];
+        rec[(F_D + a * 4 + b) * NEP] = 4.0 * (mu * nn) + A[a][b];
+      }
+      rec[(F_C2 + a) * NEP] = rho * c2[a];
+      rec[(F_R2 + a) * NEP] = rho * r2[a];
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+        rec[(F_LR + a * 4 + i) * NEP] =
+            wr * sNrV[a][i] +
+            w * (Nx[a][0] * sRM[0][i] + Nx[a][1] * sRM[1][i] + Nx[a][2] * sRM[2][i]);
+      rec[(F_LR + a * 4 + 3) * NEP] = w * lR4[a];
+    }
+    rec[F_STC * NEP] = sTC;
+    rec[F_STM * NEP] = sTM;
+    rec[F_WL * NEP] = wl;
+  }
+  __syncthreads();
+
+  // ---------------- phase 2a: residual scatter, R(:,Ac) += lR(:,a) ----------------
+  for (int it = threadIdx.x; it < NE * 16; it += NE) {
+    const int s = it >> 4, r = it & 15;
+    if (sEl[s] < 0) continue;
+    const double v = sm[(F_LR + r) * NEP + s];
+    double *dst = R + (size_t)sNode[s * 4 + (r >> 2)] * 4 + (r & 3);
+    if (ATOMIC) red_add(dst, v);
+    else *dst += v;
+  }
+
+  // ---------------- phase 2b: tangent scatter, 8 lanes per 4x4 block ----------------
+  Tet4Tab tab2;
+  tet4_tab(tab2);
+  const double mu4 = 4.0 * par.mu;
+  for (int it = threadIdx.x; it < NE * 128; it += NE) {
+    const int s = it >> 7;
+    const int el = sEl[s];
+    if (el < 0) continue;
+    const int blk = (it >> 3) & 15, q = it & 7;
+    const int a = blk >> 2, b = blk & 3;
+    const int i = q >> 1, j0 = (q & 1) * 2;
+    const double *rec = sm + s;
+    const double wl = rec[F_WL * NEP];
+    double v0, v1;
+    if (i < 3) {
+      const double nai = rec[(F_NX + a * 3 + i) * NEP];
+      const double nbi = rec[(F_NX + b * 3 + i) * NEP];
+      if (j0 == 0) {
+        // columns 0,1
+        const double sTC = rec[F_STC * NEP];
+        const double na0 = rec[(F_NX + a * 3 + 0) * NEP], na1 = rec[(F_NX + a * 3 + 1) * NEP];
+        const double nb0 = rec[(F_NX + b * 3 + 0) * NEP], nb1 = rec[(F_NX + b * 3 + 1) * NEP];
+        v0 = mu4 * (na0 * nbi) + sTC * (nai * nb0);
+        v1 = mu4 * (na1 * nbi) + sTC * (nai * nb1);
+        const double d = rec[(F_D + a * 4 + b) * NEP];
+        if (i == 0) v0 += d;
+        if (i == 1) v1 += d;
+        v0 *= wl;
+        v1 *= wl;
+      } else {
+        // column 2 and the pressure column 3 (S/FLUID.f:547-557)
+        const double sTC = rec[F_STC * NEP];
+        const double na2 = rec[(F_NX + a * 3 + 2) * NEP], nb2 = rec[(F_NX + b * 3 + 2) * NEP];
+        v0 = mu4 * (na2 * nbi) + sTC * (nai * nb2);
+        if (i == 2) v0 += rec[(F_D + a * 4 + b) * NEP];
+        v0 *= wl;
+        v1 = -wl * (nai * tab2.sN[b] - nbi * rec[(F_C2 + a) * NEP]);
+      }
+    } else {
+      // continuity row (S/FLUID.f:1052-1081)
+      const double sNa = tab2.sN[a];
+      const double r2b = rec[(F_R2 + b) * NEP];
+      if (j0 == 0) {
+        v0 = wl * (sNa * rec[(F_NX + b * 3 + 0) * NEP] + rec[(F_NX + a * 3 + 0) * NEP] * r2b);
+        v1 = wl * (sNa * rec[(F_NX + b * 3 + 1) * NEP] + rec[(F_NX + a * 3 + 1) * NEP] * r2b);
+      } else {
+        v0 = wl * (sNa * rec[(F_NX + b * 3 + 2) * NEP] + rec[(F_NX + a * 3 + 2) * NEP] * r2b);
+        const double nn = rec[(F_NX + a * 3 + 0) * NEP] * rec[(F_NX + b * 3 + 0) * NEP] +
+                          rec[(F_NX + a * 3 + 1) * NEP] * rec[(F_NX + b * 3 + 1) * NEP] +
+                          rec[(F_NX + a * 3 + 2) * NEP] * rec[(F_NX + b * 3 + 2) * NEP];
+        v1 = wl * (rec[F_STM * NEP] * nn);
+      }
+    }
+    const int p = __ldg(edest + (size_t)el * 16 + blk);
+    double *dst = Val + (size_t)p * 16 + q * 2;
+    if (ATOMIC) {
+      red_add(dst, v0);
+      red_add(dst + 1, v1);
+    } else {
+      double2 cur = *(double2 *)dst;
+      cur.x += v0;
+      cur.y += v1;
+      *(double2 *)dst = cur;
+    }
+  }
+}
+
+void launch_fluid_asm(cudaStream_t st, const FluidPar &par, int n, int e0, const int *elems,
+                      const int *ien, const int *edest, const double *x, const double *Ag,
+                      const double *Yg, const double *Bf, double *R, double *Val, int atomic,
+                      int *badJac) {
+  if (n <= 0) return;
+  count_launch();
+  const size_t smem = (size_t)F_COUNT * NEP * sizeof(double);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(fluid_asm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)smem);
+    cudaFuncSetAttribute(fluid_asm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)smem);
+    attr = true;
+  }
+  const int blocks = (n + NE - 1) / NE;
+  if (atomic)
+    fluid_asm_kernel<true><<<blocks, NE, smem, st>>>(par, n, e0, elems, ien, edest, x, Ag, Yg, Bf,
+                                                     R, Val, badJac);
+  else
+    fluid_asm_kernel<false><<<blocks, NE, smem, st>>>(par, n, e0, elems, ien, edest, x, Ag, Yg, Bf,
+                                                      R, Val, badJac);
+}
+
+// ---------------------------------------------------------------------------
+// CONSTRUCT_HEATS / HEATS3D, S/HEATS.f:60-108,116-159 (dof = 1): one thread per
+// element; lK(a,b) = wl (amd sum_g N_a N_b + 4 nu Nx_a.Nx_b)
+template <bool ATOMIC>
+__global__ void __launch_bounds__(128) heat_asm_kernel(HeatPar par, int n, int e0,
+                                                       const int *__restrict__ elems,
+                                                       const int *__restrict__ ien,
+                                                       const int *__restrict__ edest,
+                                                       const double *__restrict__ x,
+                                                       const double *__restrict__ Ag,
+                                                       const double *__restrict__ Yg,
+                                                       double *__restrict__ R,
+                                                       double *__restrict__ Val,
+                                                       int *__restrict__ badJac) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int e = elems ? elems[e0 + idx] : e0 + idx;
+  Tet4Tab tab;
+  tet4_tab(tab);
+  int nd[4];
+  {
+    const int4 v = __ldg((const int4 *)ien + e);
+    nd[0] = v.x; nd[1] = v.y; nd[2] = v.z; nd[3] = v.w;
+  }
+  double xl[4][3], al[4], yl[4];
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    const double *xp = x + (size_t)nd[a] * 3;
+    xl[a][0] = __ldg(xp); xl[a][1] = __ldg(xp + 1); xl[a][2] = __ldg(xp + 2);
+    al[a] = __ldg(Ag + nd[a]);
+    yl[a] = __ldg(Yg + nd[a]);
+  }
+  double Nx[4][3], Jac, ks[3][3];
+  gnn_tet4(xl, Nx, Jac, ks);
+  if (iszero1(Jac)) atomicAdd(badJac, 1);
+  const double T1 = par.af * par.gam * par.dt;
+  const double amd = par.am * par.rho / T1;
+  const double w = (1.0 / 24.0) * Jac;
+  const double wl = w * T1;
+  double Tx[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int i = 0; i < 3; i++) Tx[i] = Tx[i] + Nx[a][i] * yl[a];
+  double lR[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int g = 0; g < 4; g++) {
+    double Td = -par.s;
+#pragma unroll
+    for (int a = 0; a < 4; a++) Td = Td + tab.N[g][a] * al[a];
+    Td = Td * par.rho;
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+      lR[a] = lR[a] + w * (tab.N[g][a] * Td +
+                           (Nx[a][0] * Tx[0] + Nx[a][1] * Tx[1] + Nx[a][2] * Tx[2]) * par.nu);
+  }
+  const int4 *dp = (const int4 *)(edest + (size_t)e * 16);
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    if (ATOMIC) red_add(R + nd[a], lR[a]);
+    else R[nd[a]] += lR[a];
+    const int4 d4 = __ldg(dp + a);
+    const int dst[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      double v = 0.0;
+#pragma unroll
+      for (int g = 0; g < 4; g++)
+        v = v + wl * (tab.N[g][a] * tab.N[g][b] * amd +
+                      par.nu * (Nx[a][0] * Nx[b][0] + Nx[a][1] * Nx[b][1] + Nx[a][2] * Nx[b][2]));
+      if (ATOMIC) red_add(Val + dst[b], v);
+      else Val[dst[b]] += v;
+    }
+  }
+}
+
+void launch_heat_asm(cudaStream_t st, const HeatPar &par, int n, int e0, const int *elems,
+                     const int *ien, const int *edest, const double *x, const double *Ag,
+                     const double *Yg, double *R, double *Val, int atomic, int *badJac) {
+  if (n <= 0) return;
+  count_launch();
+  const int blocks = (n + 127) / 128;
+  if (atomic)
+    heat_asm_kernel<true><<<blocks, 128, 0, st>>>(par, n, e0, elems, ien, edest, x, Ag, Yg, R, Val,
+                                                  badJac);
+  else
+    heat_asm_kernel<false><<<blocks, 128, 0, st>>>(par, n, e0, elems, ien, edest, x, Ag, Yg, R,
+                                                   Val, badJac);
+}
+
+// ---------------------------------------------------------------------------
+// per-element scatter map: one binary search per (a,b) done ONCE at setup instead
+// of per assembly (S/LHSA.f:282-292).  Rows keep svFSI's ascending ORIGINAL column
+// order, which is not ascending in reordered ids, so the search runs on a key
+// array `colKey` (original ids) -- here col holds reordered ids and the rows are
+// short (<= ~30), so a linear scan is used.
+__global__ void build_edest_kernel(int nEl, const int *__restrict__ ien,
+                                   const int *__restrict__ rowPtr, const int *__restrict__ col,
+                                   int *__restrict__ edest) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)nEl * 16) return;
+  const int e = (int)(t >> 4), a = (int)((t >> 2) & 3), b = (int)(t & 3);
+  const int row = ien[(size_t)e * 4 + a], c = ien[(size_t)e * 4 + b];
+  int p = -1;
+  for (int j = rowPtr[row]; j < rowPtr[row + 1]; j++)
+    if (col[j] == c) { p = j; break; }
+  edest[t] = p;
+}
+void launch_build_edest(cudaStream_t st, int nEl, const int *ien, const int *rowPtr,
+                        const int *col, int *edest) {
+  if (nEl <= 0) return;
+  count_launch();
+  size_t tot = (size_t)nEl * 16;
+  build_edest_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(nEl, ien, rowPtr, col, edest);
+}
+
+}  // namespace svfsi

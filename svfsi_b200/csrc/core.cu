@@ -1,0 +1,309 @@
+// core.cu -- context, NCCL plumbing (dlopen'd so a 1-GPU run never needs it), the
+// FSILS halo sum (L/INCOMMU.f) and all-reduce (L/BCAST.f) on the library stream,
+// layout permutations and event-based profiling.
+#include "core.h"
+
+#include <dlfcn.h>
+#include <nccl.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace svfsi {
+
+Ctx &ctx() {
+  static Ctx c;
+  return c;
+}
+
+int fail(int code, const std::string &msg) {
+  ctx().err = msg;
+  fprintf(stderr, "svfsi_b200: error %d: %s\n", code, msg.c_str());
+  return code;
+}
+
+void count_launch(int n) { ctx().launches += n; }
+
+// ------------------------------------------------------------------ NCCL
+namespace {
+struct NcclApi {
+  void *h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                            cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t,
+                            cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+} g_nccl;
+
+#define NCCL_TRY(expr)                                                                    \
+  do {                                                                                    \
+    ncclResult_t _r = (expr);                                                             \
+    if (_r != ncclSuccess)                                                                \
+      return fail(SVFSI_ERR_COMM, std::string(#expr) + ": " +                             \
+                                      (g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "?")); \
+  } while (0)
+}  // namespace
+
+int nccl_load() {
+  if (g_nccl.h) return 0;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *n : names) {
+    g_nccl.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.h) break;
+  }
+  if (!g_nccl.h) return fail(SVFSI_ERR_COMM, std::string("dlopen(libnccl.so.2): ") + dlerror());
+#define SYM(field, name)                                                    \
+  *(void **)(&g_nccl.field) = dlsym(g_nccl.h, name);                         \
+  if (!g_nccl.field) return fail(SVFSI_ERR_COMM, std::string("dlsym ") + name)
+  SYM(GetUniqueId, "ncclGetUniqueId");
+  SYM(CommInitRank, "ncclCommInitRank");
+  SYM(CommDestroy, "ncclCommDestroy");
+  SYM(AllReduce, "ncclAllReduce");
+  SYM(AllGather, "ncclAllGather");
+  SYM(Send, "ncclSend");
+  SYM(Recv, "ncclRecv");
+  SYM(GroupStart, "ncclGroupStart");
+  SYM(GroupEnd, "ncclGroupEnd");
+  SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+  return 0;
+}
+
+int nccl_unique_id(void *uid128) {
+  if (int rc = nccl_load()) return rc;
+  ncclUniqueId id;
+  NCCL_TRY(g_nccl.GetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(uid128, &id, 128);
+  return 0;
+}
+
+int nccl_init_rank(const void *uid128, int nranks, int rank) {
+  if (int rc = nccl_load()) return rc;
+  ncclUniqueId id;
+  memcpy(&id, uid128, 128);
+  ncclComm_t comm;
+  NCCL_TRY(g_nccl.CommInitRank(&comm, nranks, id, rank));
+  ctx().nccl = (void *)comm;
+  return 0;
+}
+
+void nccl_destroy() {
+  if (ctx().nccl && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)ctx().nccl);
+  ctx().nccl = nullptr;
+}
+
+int nccl_allreduce_sum(double *buf, size_t n, cudaStream_t st) {
+  NCCL_TRY(g_nccl.AllReduce(buf, buf, n, ncclFloat64, ncclSum, (ncclComm_t)ctx().nccl, st));
+  return 0;
+}
+
+int nccl_allgather_i32(const int32_t *send, int32_t n, int32_t *recv, cudaStream_t st) {
+  NCCL_TRY(g_nccl.AllGather(send, recv, (size_t)n, ncclInt32, (ncclComm_t)ctx().nccl, st));
+  return 0;
+}
+
+int nccl_sendrecv(const double *sbuf, double *rbuf, const std::vector<Neighbor> &nbr, int dof,
+                  cudaStream_t st) {
+  ncclComm_t comm = (ncclComm_t)ctx().nccl;
+  NCCL_TRY(g_nccl.GroupStart());
+  for (const Neighbor &nb : nbr) {
+    NCCL_TRY(g_nccl.Send(sbuf + (size_t)nb.off * dof, (size_t)nb.n * dof, ncclFloat64, nb.iP, comm, st));
+    NCCL_TRY(g_nccl.Recv(rbuf + (size_t)nb.off * dof, (size_t)nb.n * dof, ncclFloat64, nb.iP, comm, st));
+  }
+  NCCL_TRY(g_nccl.GroupEnd());
+  return 0;
+}
+
+// ------------------------------------------------------------------ collectives
+int halo_sum(double *R, int dof, const int *done) {
+  Ctx &c = ctx();
+  if (c.nranks == 1 || c.nbr.empty()) return 0;
+  ProfScope ps(PROF_HALO);
+  launch_pack(c.stream, dof, c.nShared, c.d_packIdx, R, c.d_sbuf, done);
+  if (int rc = nccl_sendrecv(c.d_sbuf, c.d_rbuf, c.nbr, dof, c.stream)) return rc;
+  launch_unpack_add(c.stream, dof, c.nUniq, c.d_uniqNode, c.d_uniqPtr, c.d_uniqSlot, c.d_rbuf, R,
+                    done);
+  return 0;
+}
+
+int allreduce_dev(double *buf, size_t n) {
+  Ctx &c = ctx();
+  if (c.nranks == 1) return 0;
+  ProfScope ps(PROF_ALLREDUCE);
+  return nccl_allreduce_sum(buf, n, c.stream);
+}
+
+int host_allgather_i32(const int32_t *send, int32_t n, int32_t *recv) {
+  Ctx &c = ctx();
+  if (c.nranks == 1) {
+    memcpy(recv, send, sizeof(int32_t) * (size_t)n);
+    return 0;
+  }
+  if (c.host_allgather) {
+    if (c.host_allgather(c.host_allgather_ctx, send, n, recv) != 0)
+      return fail(SVFSI_ERR_COMM, "host all-gather callback failed");
+    return 0;
+  }
+  if (!c.nccl) return fail(SVFSI_ERR_COMM, "no host all-gather registered and no NCCL communicator");
+  int32_t *ds = nullptr, *dr = nullptr;
+  CUDA_TRY(cudaMalloc(&ds, sizeof(int32_t) * (size_t)(n > 0 ? n : 1)));
+  CUDA_TRY(cudaMalloc(&dr, sizeof(int32_t) * (size_t)(n > 0 ? n : 1) * c.nranks));
+  CUDA_TRY(cudaMemcpyAsync(ds, send, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c.stream));
+  if (int rc = nccl_allgather_i32(ds, n, dr, c.stream)) return rc;
+  CUDA_TRY(cudaMemcpyAsync(recv, dr, sizeof(int32_t) * (size_t)n * c.nranks, cudaMemcpyDeviceToHost,
+                           c.stream));
+  CUDA_TRY(cudaStreamSynchronize(c.stream));
+  cudaFree(ds);
+  cudaFree(dr);
+  return 0;
+}
+
+int row_dof(int kind, int dof) { return (kind == 0 || kind == 2) ? dof : 1; }
+int col_dof(int kind, int dof) { return (kind == 0 || kind == 1) ? dof : 1; }
+
+int sparmul(int kind, int dof, const double *K, const double *U, double *KU, const int *done) {
+  Ctx &c = ctx();
+  if (kind == 3) dof = 1;
+  {
+    ProfScope ps(PROF_SPMV);
+    launch_spmv(c.stream, kind, dof, 0, c.nNo, c.d_rowPtr, c.d_col, K, U, KU, done);
+  }
+  return halo_sum(KU, row_dof(kind, dof), done);
+}
+
+// ------------------------------------------------------------------ memory
+int ensure_ws(size_t bytes) {
+  Ctx &c = ctx();
+  if (c.wsBytes >= bytes) return 0;
+  if (c.d_ws) cudaFree(c.d_ws);
+  c.d_ws = nullptr;
+  c.wsBytes = 0;
+  CUDA_TRY(cudaMalloc(&c.d_ws, bytes));
+  c.wsBytes = bytes;
+  return 0;
+}
+
+int ensure_stage(size_t bytes) {
+  Ctx &c = ctx();
+  if (c.stageBytes >= bytes) return 0;
+  if (c.d_stage) cudaFree(c.d_stage);
+  c.d_stage = nullptr;
+  c.stageBytes = 0;
+  CUDA_TRY(cudaMalloc(&c.d_stage, bytes));
+  c.stageBytes = bytes;
+  return 0;
+}
+
+static constexpr size_t kSmallDoubles = 1 << 17;  // 1 MB of scalars: Hessenberg up to sD ~ 340
+
+int ensure_small() {
+  Ctx &c = ctx();
+  if (c.d_small) return 0;
+  CUDA_TRY(cudaMalloc(&c.d_small, kSmallDoubles * sizeof(double)));
+  CUDA_TRY(cudaMemset(c.d_small, 0, kSmallDoubles * sizeof(double)));
+  CUDA_TRY(cudaMallocHost(&c.h_small, kSmallDoubles * sizeof(double)));
+  c.partialDoubles = (size_t)multidot_nblk() * 512;
+  CUDA_TRY(cudaMalloc(&c.d_partial, c.partialDoubles * sizeof(double)));
+  return 0;
+}
+
+// ------------------------------------------------------------------ layouts
+int upload_nodal(const double *host, int m, double *dev) {
+  Ctx &c = ctx();
+  const size_t bytes = sizeof(double) * (size_t)c.nNo * m;
+  if (c.nranks == 1) {  // map is the identity (L/LHS.f:89-111)
+    CUDA_TRY(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, c.stream));
+    return 0;
+  }
+  if (int rc = ensure_stage(bytes)) return rc;
+  CUDA_TRY(cudaMemcpyAsync(c.d_stage, host, bytes, cudaMemcpyHostToDevice, c.stream));
+  launch_perm_scatter(c.stream, c.nNo, m, c.d_perm, c.d_stage, dev);
+  return 0;
+}
+
+int download_nodal(const double *dev, int m, double *host) {
+  Ctx &c = ctx();
+  const size_t bytes = sizeof(double) * (size_t)c.nNo * m;
+  if (c.nranks == 1) {
+    CUDA_TRY(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c.stream));
+    CUDA_TRY(cudaStreamSynchronize(c.stream));
+    return 0;
+  }
+  if (int rc = ensure_stage(bytes)) return rc;
+  launch_perm_gather(c.stream, c.nNo, m, c.d_perm, dev, c.d_stage);
+  CUDA_TRY(cudaMemcpyAsync(host, c.d_stage, bytes, cudaMemcpyDeviceToHost, c.stream));
+  CUDA_TRY(cudaStreamSynchronize(c.stream));
+  return 0;
+}
+
+int upload_val(const double *host, int dd, double *dev) {
+  Ctx &c = ctx();
+  const size_t bytes = sizeof(double) * (size_t)c.nnz * dd;
+  if (c.nranks == 1) {
+    CUDA_TRY(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, c.stream));
+    return 0;
+  }
+  if (int rc = ensure_stage(bytes)) return rc;
+  CUDA_TRY(cudaMemcpyAsync(c.d_stage, host, bytes, cudaMemcpyHostToDevice, c.stream));
+  launch_perm_scatter(c.stream, c.nnz, dd, c.d_vperm, c.d_stage, dev);
+  return 0;
+}
+
+int download_val(const double *dev, int dd, double *host) {
+  Ctx &c = ctx();
+  const size_t bytes = sizeof(double) * (size_t)c.nnz * dd;
+  if (c.nranks == 1) {
+    CUDA_TRY(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c.stream));
+    CUDA_TRY(cudaStreamSynchronize(c.stream));
+    return 0;
+  }
+  if (int rc = ensure_stage(bytes)) return rc;
+  launch_perm_gather(c.stream, c.nnz, dd, c.d_vperm, dev, c.d_stage);
+  CUDA_TRY(cudaMemcpyAsync(host, c.d_stage, bytes, cudaMemcpyDeviceToHost, c.stream));
+  CUDA_TRY(cudaStreamSynchronize(c.stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------ profiling
+ProfScope::ProfScope(int s) : slot(s), on(ctx().prof), idx(0) {
+  if (!on) return;
+  Ctx &c = ctx();
+  if (c.evUsed == c.evPool.size()) {
+    EventPair ep;
+    cudaEventCreate(&ep.a);
+    cudaEventCreate(&ep.b);
+    ep.slot = slot;
+    c.evPool.push_back(ep);
+  }
+  idx = c.evUsed++;
+  c.evPool[idx].slot = slot;
+  cudaEventRecord(c.evPool[idx].a, c.stream);
+}
+ProfScope::~ProfScope() {
+  if (!on) return;
+  Ctx &c = ctx();
+  cudaEventRecord(c.evPool[idx].b, c.stream);
+}
+
+void prof_collect() {
+  Ctx &c = ctx();
+  if (c.evUsed == 0) return;
+  cudaStreamSynchronize(c.stream);
+  for (size_t i = 0; i < c.evUsed; i++) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c.evPool[i].a, c.evPool[i].b) == cudaSuccess) {
+      c.profMs[c.evPool[i].slot] += ms;
+      c.profN[c.evPool[i].slot] += 1;
+    }
+  }
+  c.evUsed = 0;
+}
+
+}  // namespace svfsi

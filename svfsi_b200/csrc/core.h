@@ -1,0 +1,57 @@
+// core.h -- internal host-side services: NCCL (dlopen'd), halo sum, all-reduce,
+// workspace, profiling events.
+#pragma once
+#include "ctx.h"
+#include "kernels.h"
+
+namespace svfsi {
+
+// ---- NCCL via dlopen (only touched when nranks > 1) ----
+int nccl_load();                                   // 0 ok
+int nccl_unique_id(void *uid128);
+int nccl_init_rank(const void *uid128, int nranks, int rank);
+void nccl_destroy();
+int nccl_allreduce_sum(double *buf, size_t n, cudaStream_t st);      // in place
+int nccl_allgather_i32(const int32_t *send, int32_t n, int32_t *recv, cudaStream_t st);  // device bufs
+int nccl_sendrecv(const double *sbuf, double *rbuf, const std::vector<Neighbor> &nbr, int dof,
+                  cudaStream_t st);
+
+// ---- collectives on the library stream ----
+// FSILS_COMMUV/S on a device vector in FSILS order (L/INCOMMU.f:56-151)
+int halo_sum(double *R, int dof, const int *done);
+// MPI_ALLREDUCE(SUM) of n doubles living on the device (L/BCAST.f, L/DOT.f, L/NORM.f)
+int allreduce_dev(double *buf, size_t n);
+// host-side all-gather of int32 for the setup phase
+int host_allgather_i32(const int32_t *send, int32_t n, int32_t *recv);
+
+// ---- full FSILS_SPARMUL*: kernel + halo sum ----
+int sparmul(int kind, int dof, const double *K, const double *U, double *KU, const int *done);
+int row_dof(int kind, int dof);  // dof of KU
+int col_dof(int kind, int dof);  // dof of U
+
+// ---- workspace ----
+int ensure_ws(size_t bytes);          // d_ws >= bytes (contents not preserved)
+int ensure_stage(size_t bytes);
+int ensure_small();
+
+// ---- profiling (CUDA events on the library stream) ----
+struct ProfScope {
+  int slot;
+  bool on;
+  size_t idx;
+  explicit ProfScope(int slot);
+  ~ProfScope();
+};
+void prof_collect();  // sync + fold event pairs into ctx.profMs
+
+// ---- solver (solver.cu) ----
+int fsils_solve_dev(svfsi_ls_t *ls, int dof, int prec, const int32_t *incL, const double *res);
+void ls_defaults(svfsi_ls_t *ls, int LS_type);
+
+// upload / download with permutation between svFSI and FSILS layouts
+int upload_nodal(const double *host, int m, double *dev);   // dev[perm[a]][m] = host[a][m]
+int download_nodal(const double *dev, int m, double *host);
+int upload_val(const double *host, int dd, double *dev);    // by block positions (vperm)
+int download_val(const double *dev, int dd, double *host);
+
+}  // namespace svfsi

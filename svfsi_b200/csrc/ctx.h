@@ -1,0 +1,138 @@
+// ctx.h -- process-wide device context of the svFSI hot path on one B200.
+//
+// Everything on the device lives in the FSILS (reordered) node numbering of
+// L/LHS.f:134-211: rows [0,shnNo) are shared with lower ranks, [shnNo,mynNo)
+// interior, [mynNo,nNo) shared with higher ranks.  The block-CSR rows are stored
+// in that order with each row's blocks kept in svFSI's original (ascending
+// original column id) order, so the SpMV sums in the reference's order.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/svfsi_b200.h"
+
+namespace svfsi {
+
+// timer slots of gpu_prof_get_
+enum ProfSlot {
+  PROF_ASM = 0,      // element loop kernels (fluid / heat)
+  PROF_SPMV = 1,     // block-CSR SpMV kernels (all shapes)
+  PROF_HALO = 2,     // pack + NCCL + unpack
+  PROF_DOT = 3,      // fused multi-dot / dot / norm kernels
+  PROF_AXPY = 4,     // fused multi-axpy / scale kernels
+  PROF_PRECOND = 5,  // Jacobi scaling
+  PROF_SMALL = 6,    // Hessenberg / Givens / scalar kernels
+  PROF_ALLREDUCE = 7,
+  PROF_SOLVE = 8,    // whole FSILS_SOLVE on the device
+  PROF_NSLOTS = SVFSI_NTIMERS
+};
+
+struct Face {
+  bool created = false;
+  bool coupled = false, shared = false, inc = true;
+  int nNo = 0, dof = 0, bGrp = SVFSI_BC_TYPE_DIR;
+  double nS = 0.0, res = 0.0;
+  int *d_glob = nullptr;     // [nNo] 0-based reordered node ids
+  double *d_val = nullptr;   // [nNo][dof]
+  double *d_valM = nullptr;  // [nNo][dof]
+  std::vector<int> glob;     // host copy, 0-based reordered
+};
+
+struct Neighbor {
+  int iP = 0;  // 0-based peer rank
+  int n = 0;
+  int off = 0;            // offset (in nodes) of this neighbour's slab in the pack buffers
+  std::vector<int> ptr;   // 0-based reordered node ids (host copy)
+};
+
+struct EventPair {
+  cudaEvent_t a, b;
+  int slot;
+};
+
+struct Ctx {
+  bool inited = false;
+  int device = 0, rank = 0, nranks = 1;
+  cudaStream_t stream = nullptr;
+  void *nccl = nullptr;  // ncclComm_t
+  svfsi_allgather_i32_fn host_allgather = nullptr;
+  void *host_allgather_ctx = nullptr;
+  std::string err;
+  int64_t launches = 0;
+
+  // ---- lhs (FSILS_lhsType) ----
+  bool lhs = false;
+  int gnNo = 0, nNo = 0, nnz = 0, nFaces = 0, mynNo = 0, shnNo = 0;
+  std::vector<int> map;       // [nNo] svFSI local id (0-based) -> reordered id (0-based)
+  std::vector<int> rowPtrDev; // host copy of device rowPtr (0-based, nNo+1)
+  std::vector<Neighbor> nbr;
+  std::vector<Face> face;
+  int *d_perm = nullptr;     // [nNo] = map
+  int *d_rowPtr = nullptr;   // [nNo+1] device-layout block offsets
+  int *d_col = nullptr;      // [nnz] reordered column ids, device layout
+  int *d_diag = nullptr;     // [nNo] block index of the diagonal
+  int *d_vperm = nullptr;    // [nnz] svFSI block position -> device block position
+  int *d_rowOf = nullptr;    // [nnz] row of each block (device layout)
+  // halo
+  int nShared = 0;           // total entries in pack buffers (sum of nbr.n)
+  int *d_packIdx = nullptr;  // [nShared] node id per pack slot
+  int nUniq = 0;             // unique shared nodes
+  int *d_uniqNode = nullptr; // [nUniq]
+  int *d_uniqPtr = nullptr;  // [nUniq+1] -> d_uniqSlot
+  int *d_uniqSlot = nullptr; // pack-slot ids in ascending neighbour order
+  double *d_sbuf = nullptr, *d_rbuf = nullptr;  // [nShared*4]
+
+  // ---- mesh ----
+  bool mesh = false;
+  int nEl = 0;
+  int *d_ien = nullptr;      // [nEl][4] 0-based reordered node ids
+  int *d_edest = nullptr;    // [nEl][16] device block index of (a,b)
+  double *d_x = nullptr;     // [nNo][3]
+  int ncolors = 0;
+  std::vector<int> colorOff; // [ncolors+1]
+  int *d_colorElems = nullptr;  // [nEl] element ids grouped by colour
+  // gather variant adjacency
+  int *d_blkAdjPtr = nullptr;   // [nnz+1]
+  int *d_blkAdj = nullptr;      // [16*nEl] (e<<4 | a<<2 | b)
+  int *d_nodeAdjPtr = nullptr;  // [nNo+1]
+  int *d_nodeAdj = nullptr;     // [4*nEl] (e<<2 | a)
+  double *d_elemP = nullptr;    // per-element compact data for the gather variant
+
+  // ---- system ----
+  int dof = 0;                // dof of the resident R/Val
+  double *d_R = nullptr;      // [nNo][4]
+  double *d_Val = nullptr;    // [nnz][16]
+  double *d_Ag = nullptr, *d_Yg = nullptr, *d_Bf = nullptr;  // [nNo][4],[nNo][4],[nNo][3]
+  double *d_stage = nullptr;  // staging for H2D/D2H permutes
+  size_t stageBytes = 0;
+  int *d_flag = nullptr;      // device int flags (e.g. bad Jacobian count)
+
+  // ---- solver workspace (grown on demand) ----
+  double *d_ws = nullptr;
+  size_t wsBytes = 0;
+  double *d_small = nullptr;  // small scalars: dots, Hessenberg, control block
+  double *h_small = nullptr;  // pinned mirror
+  double *d_partial = nullptr;
+  size_t partialDoubles = 0;
+
+  // ---- profiling ----
+  bool prof = false;
+  std::vector<EventPair> evPool;
+  size_t evUsed = 0;
+  double profMs[PROF_NSLOTS] = {0};
+  int64_t profN[PROF_NSLOTS] = {0};
+};
+
+Ctx &ctx();
+int fail(int code, const std::string &msg);
+
+#define CUDA_TRY(expr)                                                              \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess)                                                          \
+      return svfsi::fail(SVFSI_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+}  // namespace svfsi

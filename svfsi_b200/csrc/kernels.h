@@ -1,0 +1,134 @@
+// kernels.h -- launchers of the hand-written sm_100a kernels (la_kernels.cu,
+// asm_kernels.cu).  All launch on the given stream, return nothing, and bump the
+// context's launch counter.  `done` (may be NULL) is a device flag: when it is
+// non-zero the kernel returns immediately (used to run the Krylov loop ahead of
+// the host without a sync per iteration).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace svfsi {
+
+struct FluidPar {
+  double rho, mu, f[3], dt, af, am, gam;
+};
+struct HeatPar {
+  double nu, s, rho, dt, af, am, gam;
+};
+
+// Control block of one GMRES / CG solve, resident on the device.
+struct KrylovCtl {
+  int done;     // stop flag: later kernels of the current cycle become no-ops
+  int suc;      // ls%suc
+  int ilast;    // number of Krylov vectors built in the current cycle
+  int itr;      // ls%itr (SpMV count) accumulated on the device
+  double eps;   // absolute stopping threshold
+  double inv;   // 1/h(i+1,i) of the current column
+  double fNorm, iNorm, dBref;
+  double scal[8];  // scratch scalars (alpha, err, errO, ...)
+};
+
+// ---------------- block-CSR SpMV (L/SPARMUL.f) ----------------
+// rows [r0,r1) of KU = K*U.  kind: 0 VV (dof x dof blocks), 1 VS (1 x dof), 2 SV (dof x 1),
+// 3 SS.  dof in {1,2,3,4}.
+void launch_spmv(cudaStream_t st, int kind, int dof, int r0, int r1, const int *rowPtr,
+                 const int *col, const double *K, const double *U, double *KU, const int *done);
+
+// ---------------- halo (L/INCOMMU.f) ----------------
+void launch_pack(cudaStream_t st, int dof, int nShared, const int *packIdx, const double *R,
+                 double *sbuf, const int *done);
+void launch_unpack_add(cudaStream_t st, int dof, int nUniq, const int *uniqNode,
+                       const int *uniqPtr, const int *uniqSlot, const double *rbuf, double *R,
+                       const int *done);
+
+// ---------------- vectors ----------------
+// partial[j*nblk + b] = sum over block b of U_j . w, j < k; U_j = U + j*stride. n doubles.
+int multidot_nblk();
+void launch_multidot(cudaStream_t st, const double *U, size_t stride, const double *w, size_t n,
+                     int k, double *partial, const int *done);
+// out[j] = sum_b partial[j*nblk+b]
+void launch_reduce_partials(cudaStream_t st, const double *partial, int k, double *out,
+                            const int *done);
+// w = (w - sum_{j<k} coef[j]*U_j) * (*scale)   (coef, scale on device; scale may be NULL = 1)
+void launch_multi_axpy_scale(cudaStream_t st, const double *U, size_t stride, double *w, size_t n,
+                             int k, const double *coef, const double *scale, const int *done);
+// X += sum_{j<*kdev} y[j]*U_j   (k read from the device)
+void launch_multi_axpy_acc(cudaStream_t st, const double *U, size_t stride, double *X, size_t n,
+                           const int *kdev, int kmax, const double *y);
+// elementwise helpers: op codes
+enum VecOp {
+  VOP_COPY = 0,       // a = b
+  VOP_SUB_FROM = 1,   // a = b - a
+  VOP_SCALE_DEV = 2,  // a = a * (*s)            (s on device)
+  VOP_DIV_DEV = 3,    // a = a / (*s)
+  VOP_AXPY_DEV = 4,   // a = a + (*s) * b
+  VOP_AXMY_DEV = 5,   // a = a - (*s) * b
+  VOP_MUL = 6,        // a = a * b               (elementwise)
+  VOP_ZERO = 7,
+  VOP_AXPY = 8,       // a = a + sh * b          (host scalar)
+  VOP_SCALE = 9,      // a = sh * a
+  VOP_XPBY_DEV = 10,  // a = b + (*s) * a        (CG direction update)
+  VOP_SUB = 11        // a = b - c
+};
+void launch_vecop(cudaStream_t st, int op, double *a, const double *b, const double *c, size_t n,
+                  const double *sdev, double shost, const int *done);
+// interleave / de-interleave momentum and continuity parts (NSSOLVER Rm/Rc split)
+void launch_split_mc(cudaStream_t st, int nNo, int dof, const double *R, double *Rm, double *Rc);
+void launch_join_mc(cudaStream_t st, int nNo, int dof, const double *Rm, const double *Rc,
+                    double *R);
+
+// ---------------- permutation between svFSI and FSILS layouts ----------------
+// dst[perm[a]][m] = src[a][m]  (scatter) ; dst[a][m] = src[perm[a]][m] (gather)
+void launch_perm_scatter(cudaStream_t st, int n, int m, const int *perm, const double *src,
+                         double *dst);
+void launch_perm_gather(cudaStream_t st, int n, int m, const int *perm, const double *src,
+                        double *dst);
+
+// ---------------- Jacobi preconditioner (L/PRECOND.f:50-145) ----------------
+void launch_diag_extract(cudaStream_t st, int nNo, int dof, const int *diag, const double *Val,
+                         double *W);
+void launch_w_finalize(cudaStream_t st, size_t n, double *W);
+void launch_w_dirichlet(cudaStream_t st, int nFaceNo, int fdof, int dof, const int *glob,
+                        const double *val, double *W);
+void launch_scale_val(cudaStream_t st, int nnz, int dof, const int *rowOf, const int *col,
+                      const double *W, double *Val);
+void launch_face_valM(cudaStream_t st, int nFaceNo, int fdof, int dof, const int *glob,
+                      const double *val, const double *W, double *valM);
+// ADDBCMUL (L/ADDBCMUL.f): S = sum_a sum_i valM(i,a) X(i,glob(a)) over nodes with glob < ownedLimit
+void launch_face_dot(cudaStream_t st, int nFaceNo, int fdof, int dof, const int *glob,
+                     const double *valM, const double *X, int ownedLimit, double *S,
+                     const int *done);
+// Y(i,glob(a)) += valM(i,a) * coef * (*S)
+void launch_face_axpy(cudaStream_t st, int nFaceNo, int fdof, int dof, const int *glob,
+                      const double *valM, double coef, const double *S, double *Y,
+                      const int *done);
+// nS = sum valM^2 over nodes with glob < ownedLimit
+void launch_face_norm2(cudaStream_t st, int nFaceNo, int fdof, int nsd, const int *glob,
+                       const double *valM, int ownedLimit, double *S);
+
+// ---------------- Krylov scalar kernels ----------------
+void launch_gmres_column(cudaStream_t st, KrylovCtl *ctl, int i, int sD, const double *hcol,
+                         double *h, double *c, double *s, double *err, double *coef);
+void launch_gmres_backsub(cudaStream_t st, KrylovCtl *ctl, int sD, const double *h,
+                          const double *err, double *y);
+// DEPART (L/NSSOLVER.f:237-305)
+void launch_depart(cudaStream_t st, int nnz, int nsd, const double *Val, double *mK, double *mG,
+                   double *mD, double *mL);
+void launch_gt(cudaStream_t st, int nnz, int nsd, const int *tpos, const double *mG, double *Gt);
+
+// ---------------- element loops (S/FLUID.f, S/HEATS.f) ----------------
+// variant: SVFSI_ASM_ATOMIC / COLORED.  elems == NULL -> elements [e0, e0+n); else elems[e0..e0+n)
+void launch_fluid_asm(cudaStream_t st, const FluidPar &par, int n, int e0, const int *elems,
+                      const int *ien, const int *edest, const double *x, const double *Ag,
+                      const double *Yg, const double *Bf, double *R, double *Val, int atomic,
+                      int *badJac);
+void launch_heat_asm(cudaStream_t st, const HeatPar &par, int n, int e0, const int *elems,
+                     const int *ien, const int *edest, const double *x, const double *Ag,
+                     const double *Yg, double *R, double *Val, int atomic, int *badJac);
+// edest[e][a*4+b] = device block index of (row ien[e][a], col ien[e][b])
+void launch_build_edest(cudaStream_t st, int nEl, const int *ien, const int *rowPtr,
+                        const int *col, int *edest);
+
+void count_launch(int n = 1);
+
+}  // namespace svfsi

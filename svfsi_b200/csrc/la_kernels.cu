@@ -1,0 +1,712 @@
+// la_kernels.cu -- hand-written sm_100a kernels of the FSILS linear-algebra core:
+// block-CSR SpMV (L/SPARMUL.f), halo pack/unpack (L/INCOMMU.f), fused
+// multi-dot / multi-axpy for classical Gram-Schmidt (L/GMRES.f:337-349,
+// L/DOT.f, L/OMPLA.f), Jacobi scaling (L/PRECOND.f:50-145, 372-489), the
+// coupled-BC rank-1 update (L/ADDBCMUL.f) and the scalar Hessenberg/Givens step.
+//
+// All of these are HBM-bandwidth bound (no tensor cores: nothing here is a dense
+// contraction).  Design rules: 128-bit loads, every 32-byte sector fully used,
+// grids sized as multiples of the 148 SMs, reductions by warp shuffles, and no
+// host synchronisation inside the Krylov loop (kernels test a device flag).
+#include <cuda_runtime.h>
+
+#include "ctx.h"
+#include "kernels.h"
+
+namespace svfsi {
+
+static constexpr int kSMs = 148;
+
+#define DONE_GUARD(done) \
+  if ((done) != nullptr && *(volatile const int *)(done) != 0) return;
+
+__device__ __forceinline__ double2 ldg_stream2(const double2 *p) {
+  // streaming 128-bit load: matrix values are read exactly once per SpMV
+  return __ldcs(p);
+}
+
+// ---------------------------------------------------------------------------
+// SPARMULVV, dof = 4 (L/SPARMUL.f:98-113).  8 lanes own one block row: lane q
+// loads the q-th 16-byte piece of every 128-byte block (one LDG.128 per lane,
+// a warp instruction covers four whole 128-byte lines), multiplies by the
+// matching half of U(:,col) and the two halves are combined by one shuffle.
+// Column ids of 8 consecutive blocks are fetched by one coalesced load and
+// broadcast by shuffles, so the U gather does not wait on a dependent load per
+// block.
+__global__ void __launch_bounds__(256) spmv_vv4_kernel(int r0, int r1, const int *__restrict__ rowPtr,
+                                                        const int *__restrict__ col,
+                                                        const double2 *__restrict__ K,
+                                                        const double2 *__restrict__ U,
+                                                        double *__restrict__ KU,
+                                                        const int *done) {
+  DONE_GUARD(done);
+  const int lane = threadIdx.x & 31;
+  const int q = lane & 7;
+  const int h = q & 1;
+  const unsigned gmask = 0xFFu << (lane & 24);
+  int row = r0 + (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 3);
+  if (row >= r1) return;  // whole 8-lane groups leave together
+  const int s = __ldg(rowPtr + row), e = __ldg(rowPtr + row + 1);
+  double acc = 0.0;
+  for (int base = s; base < e; base += 8) {
+    const int mine = base + q;
+    const int cq = (mine < e) ? __ldg(col + mine) : 0;
+    const int cnt = min(8, e - base);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int c = __shfl_sync(gmask, cq, k, 8);
+      if (k < cnt) {
+        const double2 kv = ldg_stream2(K + (size_t)(base + k) * 8 + q);
+        const double2 uv = __ldg(U + (size_t)c * 2 + h);
+        acc = fma(kv.x, uv.x, acc);
+        acc = fma(kv.y, uv.y, acc);
+      }
+    }
+  }
+  acc += __shfl_xor_sync(gmask, acc, 1, 8);
+  if (h == 0) KU[(size_t)row * 4 + (q >> 1)] = acc;
+}
+
+// Generic shapes (VV dof<=3, VS, SV, SS): 4 lanes per row, each lane takes blocks
+// q, q+4, ... of the row; partial results combined by shuffles.  BR x BC is the
+// block shape: VV d: (d,d); VS d: (1,d); SV d: (d,1); SS: (1,1).
+template <int BR, int BC>
+__global__ void __launch_bounds__(256) spmv_generic_kernel(int r0, int r1, const int *__restrict__ rowPtr,
+                                                            const int *__restrict__ col,
+                                                            const double *__restrict__ K,
+                                                            const double *__restrict__ U,
+                                                            double *__restrict__ KU,
+                                                            const int *done) {
+  DONE_GUARD(done);
+  const int lane = threadIdx.x & 31;
+  const int q = lane & 3;
+  const unsigned gmask = 0xFu << (lane & 28);
+  int row = r0 + (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 2);
+  if (row >= r1) return;
+  const int s = __ldg(rowPtr + row), e = __ldg(rowPtr + row + 1);
+  double acc[BR];
+#pragma unroll
+  for (int l = 0; l < BR; l++) acc[l] = 0.0;
+  for (int j = s + q; j < e; j += 4) {
+    const int c = __ldg(col + j);
+    const double *k = K + (size_t)j * (BR * BC);
+    double u[BC];
+#pragma unroll
+    for (int m = 0; m < BC; m++) u[m] = __ldg(U + (size_t)c * BC + m);
+#pragma unroll
+    for (int l = 0; l < BR; l++)
+#pragma unroll
+      for (int m = 0; m < BC; m++) acc[l] = fma(__ldcs(k + l * BC + m), u[m], acc[l]);
+  }
+#pragma unroll
+  for (int l = 0; l < BR; l++) {
+    acc[l] += __shfl_xor_sync(gmask, acc[l], 1, 4);
+    acc[l] += __shfl_xor_sync(gmask, acc[l], 2, 4);
+  }
+  if (q == 0) {
+#pragma unroll
+    for (int l = 0; l < BR; l++) KU[(size_t)row * BR + l] = acc[l];
+  }
+}
+
+template <int BR, int BC>
+static void launch_generic(cudaStream_t st, int r0, int r1, const int *rowPtr, const int *col,
+                           const double *K, const double *U, double *KU, const int *done) {
+  const int rows = r1 - r0;
+  const int blocks = (rows * 4 + 255) / 256;
+  spmv_generic_kernel<BR, BC><<<blocks, 256, 0, st>>>(r0, r1, rowPtr, col, K, U, KU, done);
+}
+
+void launch_spmv(cudaStream_t st, int kind, int dof, int r0, int r1, const int *rowPtr,
+                 const int *col, const double *K, const double *U, double *KU, const int *done) {
+  if (r1 <= r0) return;
+  count_launch();
+  if (kind == 0 && dof == 4) {
+    const int rows = r1 - r0;
+    const int blocks = (int)(((size_t)rows * 8 + 255) / 256);
+    spmv_vv4_kernel<<<blocks, 256, 0, st>>>(r0, r1, rowPtr, col, (const double2 *)K,
+                                            (const double2 *)U, KU, done);
+    return;
+  }
+  if (kind == 3 || dof == 1) {
+    launch_generic<1, 1>(st, r0, r1, rowPtr, col, K, U, KU, done);
+  } else if (kind == 0) {
+    if (dof == 2) launch_generic<2, 2>(st, r0, r1, rowPtr, col, K, U, KU, done);
+    else launch_generic<3, 3>(st, r0, r1, rowPtr, col, K, U, KU, done);
+  } else if (kind == 1) {
+    if (dof == 2) launch_generic<1, 2>(st, r0, r1, rowPtr, col, K, U, KU, done);
+    else if (dof == 3) launch_generic<1, 3>(st, r0, r1, rowPtr, col, K, U, KU, done);
+    else launch_generic<1, 4>(st, r0, r1, rowPtr, col, K, U, KU, done);
+  } else {
+    if (dof == 2) launch_generic<2, 1>(st, r0, r1, rowPtr, col, K, U, KU, done);
+    else if (dof == 3) launch_generic<3, 1>(st, r0, r1, rowPtr, col, K, U, KU, done);
+    else launch_generic<4, 1>(st, r0, r1, rowPtr, col, K, U, KU, done);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// halo sum, L/INCOMMU.f:56-151
+__global__ void pack_kernel(int dof, int nShared, const int *__restrict__ packIdx,
+                            const double *__restrict__ R, double *__restrict__ sbuf,
+                            const int *done) {
+  DONE_GUARD(done);
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nShared * dof) return;
+  int s = t / dof, d = t - s * dof;
+  sbuf[t] = R[(size_t)packIdx[s] * dof + d];
+}
+
+// each unique shared node adds its neighbours' contributions in ascending
+// neighbour-rank order (L/INCOMMU.f:91-96) -- deterministic
+__global__ void unpack_add_kernel(int dof, int nUniq, const int *__restrict__ uniqNode,
+                                  const int *__restrict__ uniqPtr,
+                                  const int *__restrict__ uniqSlot,
+                                  const double *__restrict__ rbuf, double *__restrict__ R,
+                                  const int *done) {
+  DONE_GUARD(done);
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nUniq * dof) return;
+  int u = t / dof, d = t - u * dof;
+  size_t at = (size_t)uniqNode[u] * dof + d;
+  double v = R[at];
+  for (int k = uniqPtr[u]; k < uniqPtr[u + 1]; k++) v = v + rbuf[(size_t)uniqSlot[k] * dof + d];
+  R[at] = v;
+}
+
+void launch_pack(cudaStream_t st, int dof, int nShared, const int *packIdx, const double *R,
+                 double *sbuf, const int *done) {
+  if (nShared <= 0) return;
+  count_launch();
+  int n = nShared * dof;
+  pack_kernel<<<(n + 255) / 256, 256, 0, st>>>(dof, nShared, packIdx, R, sbuf, done);
+}
+void launch_unpack_add(cudaStream_t st, int dof, int nUniq, const int *uniqNode,
+                       const int *uniqPtr, const int *uniqSlot, const double *rbuf, double *R,
+                       const int *done) {
+  if (nUniq <= 0) return;
+  count_launch();
+  int n = nUniq * dof;
+  unpack_add_kernel<<<(n + 255) / 256, 256, 0, st>>>(dof, nUniq, uniqNode, uniqPtr, uniqSlot,
+                                                     rbuf, R, done);
+}
+
+// ---------------------------------------------------------------------------
+// fused multi-dot: one pass over w and k basis vectors (replaces the i+1 separate
+// FSILS_NCDOTV passes of L/GMRES.f:337-339).  Deterministic two-stage reduction.
+static constexpr int kDotBlocks = kSMs * 4;
+static constexpr int kDotThreads = 256;
+int multidot_nblk() { return kDotBlocks; }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int JT>
+__device__ __forceinline__ void multidot_tile(const double *__restrict__ U, size_t stride,
+                                              const double *__restrict__ w, size_t n, int j0,
+                                              double *__restrict__ partial, double *smem) {
+  double acc[JT];
+#pragma unroll
+  for (int jj = 0; jj < JT; jj++) acc[jj] = 0.0;
+  const size_t n2 = n >> 1;
+  const double2 *w2 = (const double2 *)w;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n2;
+       e += (size_t)gridDim.x * blockDim.x) {
+    const double2 wv = __ldg(w2 + e);
+#pragma unroll
+    for (int jj = 0; jj < JT; jj++) {
+      const double2 uv = __ldcs((const double2 *)(U + (size_t)(j0 + jj) * stride) + e);
+      acc[jj] = fma(uv.x, wv.x, acc[jj]);
+      acc[jj] = fma(uv.y, wv.y, acc[jj]);
+    }
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const double wv = w[n - 1];
+#pragma unroll
+    for (int jj = 0; jj < JT; jj++) acc[jj] = fma(U[(size_t)(j0 + jj) * stride + n - 1], wv, acc[jj]);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int jj = 0; jj < JT; jj++) {
+    double v = warp_sum(acc[jj]);
+    if (lane == 0) smem[wid * JT + jj] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < JT) {
+    double v = 0.0;
+    for (int wq = 0; wq < kDotThreads / 32; wq++) v += smem[wq * JT + threadIdx.x];
+    partial[(size_t)(j0 + threadIdx.x) * gridDim.x + blockIdx.x] = v;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kDotThreads) multidot_kernel(const double *__restrict__ U, size_t stride,
+                                                               const double *__restrict__ w, size_t n,
+                                                               int k, double *__restrict__ partial,
+                                                               const int *done) {
+  DONE_GUARD(done);
+  __shared__ double smem[(kDotThreads / 32) * 8];
+  int j0 = 0;
+  while (k - j0 >= 8) { multidot_tile<8>(U, stride, w, n, j0, partial, smem); j0 += 8; }
+  if (k - j0 >= 4) { multidot_tile<4>(U, stride, w, n, j0, partial, smem); j0 += 4; }
+  if (k - j0 >= 2) { multidot_tile<2>(U, stride, w, n, j0, partial, smem); j0 += 2; }
+  if (k - j0 >= 1) { multidot_tile<1>(U, stride, w, n, j0, partial, smem); j0 += 1; }
+}
+
+__global__ void reduce_partials_kernel(const double *__restrict__ partial, int nblk,
+                                       double *__restrict__ out, const int *done) {
+  DONE_GUARD(done);
+  __shared__ double smem[8];
+  const int j = blockIdx.x;
+  double v = 0.0;
+  for (int b = threadIdx.x; b < nblk; b += blockDim.x) v += partial[(size_t)j * nblk + b];
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int wq = 0; wq < (int)(blockDim.x >> 5); wq++) t += smem[wq];
+    out[j] = t;
+  }
+}
+
+void launch_multidot(cudaStream_t st, const double *U, size_t stride, const double *w, size_t n,
+                     int k, double *partial, const int *done) {
+  if (k <= 0) return;
+  count_launch();
+  multidot_kernel<<<kDotBlocks, kDotThreads, 0, st>>>(U, stride, w, n, k, partial, done);
+}
+void launch_reduce_partials(cudaStream_t st, const double *partial, int k, double *out,
+                            const int *done) {
+  if (k <= 0) return;
+  count_launch();
+  reduce_partials_kernel<<<k, 256, 0, st>>>(partial, kDotBlocks, out, done);
+}
+
+// fused multi-axpy + scale: w = (w - sum_j coef[j] U_j) * scale, the i OMPSUMV
+// passes and the OMPMULV of L/GMRES.f:342-349 in one pass, same j order.
+__global__ void __launch_bounds__(256) multi_axpy_scale_kernel(const double *__restrict__ U, size_t stride,
+                                                               double *__restrict__ w, size_t n, int k,
+                                                               const double *__restrict__ coef,
+                                                               const double *__restrict__ scale,
+                                                               const int *done) {
+  DONE_GUARD(done);
+  extern __shared__ double sc[];
+  for (int j = threadIdx.x; j < k; j += blockDim.x) sc[j] = coef[j];
+  __syncthreads();
+  const double s = scale ? *scale : 1.0;
+  const size_t n2 = n >> 1;
+  double2 *w2 = (double2 *)w;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n2;
+       e += (size_t)gridDim.x * blockDim.x) {
+    double2 v = w2[e];
+#pragma unroll 4
+    for (int j = 0; j < k; j++) {
+      const double2 uv = __ldcs((const double2 *)(U + (size_t)j * stride) + e);
+      v.x = fma(-sc[j], uv.x, v.x);
+      v.y = fma(-sc[j], uv.y, v.y);
+    }
+    v.x *= s;
+    v.y *= s;
+    w2[e] = v;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    double v = w[n - 1];
+    for (int j = 0; j < k; j++) v = fma(-sc[j], U[(size_t)j * stride + n - 1], v);
+    w[n - 1] = v * s;
+  }
+}
+
+void launch_multi_axpy_scale(cudaStream_t st, const double *U, size_t stride, double *w, size_t n,
+                             int k, const double *coef, const double *scale, const int *done) {
+  count_launch();
+  multi_axpy_scale_kernel<<<kSMs * 8, 256, (size_t)(k > 0 ? k : 1) * sizeof(double), st>>>(
+      U, stride, w, n, k, coef, scale, done);
+}
+
+// X += sum_{j<k} y[j] U_j with k read from the device (number of Krylov vectors
+// actually built), L/GMRES.f:377-380
+__global__ void __launch_bounds__(256) multi_axpy_acc_kernel(const double *__restrict__ U, size_t stride,
+                                                             double *__restrict__ X, size_t n,
+                                                             const int *__restrict__ kdev, int kmax,
+                                                             const double *__restrict__ y) {
+  extern __shared__ double sc[];
+  const int k = min(*kdev, kmax);
+  for (int j = threadIdx.x; j < k; j += blockDim.x) sc[j] = y[j];
+  __syncthreads();
+  const size_t n2 = n >> 1;
+  double2 *x2 = (double2 *)X;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n2;
+       e += (size_t)gridDim.x * blockDim.x) {
+    double2 v = x2[e];
+#pragma unroll 4
+    for (int j = 0; j < k; j++) {
+      const double2 uv = __ldcs((const double2 *)(U + (size_t)j * stride) + e);
+      v.x = fma(sc[j], uv.x, v.x);
+      v.y = fma(sc[j], uv.y, v.y);
+    }
+    x2[e] = v;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    double v = X[n - 1];
+    for (int j = 0; j < k; j++) v = fma(sc[j], U[(size_t)j * stride + n - 1], v);
+    X[n - 1] = v;
+  }
+}
+
+void launch_multi_axpy_acc(cudaStream_t st, const double *U, size_t stride, double *X, size_t n,
+                           const int *kdev, int kmax, const double *y) {
+  count_launch();
+  multi_axpy_acc_kernel<<<kSMs * 8, 256, (size_t)(kmax > 0 ? kmax : 1) * sizeof(double), st>>>(
+      U, stride, X, n, kdev, kmax, y);
+}
+
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) vecop_kernel(int op, double *__restrict__ a, const double *__restrict__ b,
+                                                    const double *__restrict__ c, size_t n,
+                                                    const double *__restrict__ sdev, double sh,
+                                                    const int *done) {
+  DONE_GUARD(done);
+  const double s = sdev ? *sdev : sh;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n;
+       e += (size_t)gridDim.x * blockDim.x) {
+    double v;
+    switch (op) {
+      case VOP_COPY: v = b[e]; break;
+      case VOP_SUB_FROM: v = b[e] - a[e]; break;
+      case VOP_SCALE_DEV: case VOP_SCALE: v = a[e] * s; break;
+      case VOP_DIV_DEV: v = a[e] / s; break;
+      case VOP_AXPY_DEV: case VOP_AXPY: v = a[e] + s * b[e]; break;
+      case VOP_AXMY_DEV: v = a[e] - s * b[e]; break;
+      case VOP_MUL: v = a[e] * b[e]; break;
+      case VOP_ZERO: v = 0.0; break;
+      case VOP_XPBY_DEV: v = b[e] + s * a[e]; break;
+      case VOP_SUB: v = b[e] - c[e]; break;
+      default: v = a[e];
+    }
+    a[e] = v;
+  }
+}
+
+void launch_vecop(cudaStream_t st, int op, double *a, const double *b, const double *c, size_t n,
+                  const double *sdev, double shost, const int *done) {
+  if (n == 0) return;
+  count_launch();
+  size_t want = (n + 255) / 256;
+  int blocks = (int)(want < (size_t)kSMs * 8 ? want : (size_t)kSMs * 8);
+  vecop_kernel<<<blocks, 256, 0, st>>>(op, a, b, c, n, sdev, shost, done);
+}
+
+__global__ void split_mc_kernel(int nNo, int dof, const double *__restrict__ R,
+                                double *__restrict__ Rm, double *__restrict__ Rc) {
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= nNo) return;
+  const int nsd = dof - 1;
+  for (int d = 0; d < nsd; d++) Rm[(size_t)a * nsd + d] = R[(size_t)a * dof + d];
+  Rc[a] = R[(size_t)a * dof + nsd];
+}
+__global__ void join_mc_kernel(int nNo, int dof, const double *__restrict__ Rm,
+                               const double *__restrict__ Rc, double *__restrict__ R) {
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= nNo) return;
+  const int nsd = dof - 1;
+  for (int d = 0; d < nsd; d++) R[(size_t)a * dof + d] = Rm[(size_t)a * nsd + d];
+  R[(size_t)a * dof + nsd] = Rc[a];
+}
+void launch_split_mc(cudaStream_t st, int nNo, int dof, const double *R, double *Rm, double *Rc) {
+  count_launch();
+  split_mc_kernel<<<(nNo + 255) / 256, 256, 0, st>>>(nNo, dof, R, Rm, Rc);
+}
+void launch_join_mc(cudaStream_t st, int nNo, int dof, const double *Rm, const double *Rc,
+                    double *R) {
+  count_launch();
+  join_mc_kernel<<<(nNo + 255) / 256, 256, 0, st>>>(nNo, dof, Rm, Rc, R);
+}
+
+// ---------------------------------------------------------------------------
+__global__ void perm_scatter_kernel(int n, int m, const int *__restrict__ perm,
+                                    const double *__restrict__ src, double *__restrict__ dst) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)n * m) return;
+  int a = (int)(t / m), d = (int)(t - (size_t)a * m);
+  dst[(size_t)perm[a] * m + d] = src[t];
+}
+__global__ void perm_gather_kernel(int n, int m, const int *__restrict__ perm,
+                                   const double *__restrict__ src, double *__restrict__ dst) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)n * m) return;
+  int a = (int)(t / m), d = (int)(t - (size_t)a * m);
+  dst[t] = src[(size_t)perm[a] * m + d];
+}
+void launch_perm_scatter(cudaStream_t st, int n, int m, const int *perm, const double *src,
+                         double *dst) {
+  if (n <= 0) return;
+  count_launch();
+  size_t tot = (size_t)n * m;
+  perm_scatter_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(n, m, perm, src, dst);
+}
+void launch_perm_gather(cudaStream_t st, int n, int m, const int *perm, const double *src,
+                        double *dst) {
+  if (n <= 0) return;
+  count_launch();
+  size_t tot = (size_t)n * m;
+  perm_gather_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(n, m, perm, src, dst);
+}
+
+// ---------------------------------------------------------------------------
+// PRECONDDIAG pieces, L/PRECOND.f:66-142
+__global__ void diag_extract_kernel(int nNo, int dof, const int *__restrict__ diag,
+                                    const double *__restrict__ Val, double *__restrict__ W) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nNo * dof) return;
+  int a = t / dof, i = t - a * dof;
+  W[t] = Val[(size_t)diag[a] * dof * dof + i * dof + i];
+}
+__global__ void w_finalize_kernel(size_t n, double *__restrict__ W) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  double w = W[t];
+  if (w == 0.0) w = 1.0;
+  W[t] = 1.0 / sqrt(fabs(w));
+}
+__global__ void w_dirichlet_kernel(int nFaceNo, int fdof, int dof, const int *__restrict__ glob,
+                                   const double *__restrict__ val, double *__restrict__ W) {
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= nFaceNo) return;
+  const int m = fdof < dof ? fdof : dof;
+  for (int i = 0; i < m; i++) W[(size_t)glob[a] * dof + i] *= val[(size_t)a * fdof + i];
+}
+// K = (W_row K) W_col fused (PREMUL then POSMUL, same multiplication order per entry)
+__global__ void __launch_bounds__(256) scale_val4_kernel(int nnz, const int *__restrict__ rowOf,
+                                                          const int *__restrict__ col,
+                                                          const double *__restrict__ W,
+                                                          double2 *__restrict__ Val) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)nnz * 8) return;
+  const int p = (int)(t >> 3), q = (int)(t & 7);
+  const int i = q >> 1, k0 = (q & 1) * 2;
+  const double wr = __ldg(W + (size_t)__ldg(rowOf + p) * 4 + i);
+  const double2 wc = __ldg((const double2 *)(W + (size_t)__ldg(col + p) * 4 + k0));
+  double2 v = Val[t];
+  v.x = (v.x * wr) * wc.x;
+  v.y = (v.y * wr) * wc.y;
+  Val[t] = v;
+}
+__global__ void scale_val_generic_kernel(int nnz, int dof, const int *__restrict__ rowOf,
+                                         const int *__restrict__ col,
+                                         const double *__restrict__ W, double *__restrict__ Val) {
+  const int dd = dof * dof;
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)nnz * dd) return;
+  const int p = (int)(t / dd), r = (int)(t - (size_t)p * dd);
+  const int i = r / dof, k = r - i * dof;
+  Val[t] = (Val[t] * W[(size_t)rowOf[p] * dof + i]) * W[(size_t)col[p] * dof + k];
+}
+__global__ void face_valM_kernel(int nFaceNo, int fdof, int dof, const int *__restrict__ glob,
+                                 const double *__restrict__ val, const double *__restrict__ W,
+                                 double *__restrict__ valM) {
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= nFaceNo) return;
+  const int m = fdof < dof ? fdof : dof;
+  for (int i = 0; i < m; i++)
+    valM[(size_t)a * fdof + i] = val[(size_t)a * fdof + i] * W[(size_t)glob[a] * dof + i];
+}
+
+void launch_diag_extract(cudaStream_t st, int nNo, int dof, const int *diag, const double *Val,
+                         double *W) {
+  count_launch();
+  diag_extract_kernel<<<(nNo * dof + 255) / 256, 256, 0, st>>>(nNo, dof, diag, Val, W);
+}
+void launch_w_finalize(cudaStream_t st, size_t n, double *W) {
+  count_launch();
+  w_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, W);
+}
+void launch_w_dirichlet(cudaStream_t st, int nFaceNo, int fdof, int dof, const int *glob,
+                        const double *val, double *W) {
+  if (nFaceNo <= 0) return;
+  count_launch();
+  w_dirichlet_kernel<<<(nFaceNo + 255) / 256, 256, 0, st>>>(nFaceNo, fdof, dof, glob, val, W);
+}
+void launch_scale_val(cudaStream_t st, int nnz, int dof, const int *rowOf, const int *col,
+                      const double *W, double *Val) {
+  count_launch();
+  if (dof == 4) {
+    size_t tot = (size_t)nnz * 8;
+    scale_val4_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(nnz, rowOf, col, W,
+                                                                     (double2 *)Val);
+  } else {
+    size_t tot = (size_t)nnz * dof * dof;
+    scale_val_generic_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(nnz, dof, rowOf, col,
+                                                                            W, Val);
+  }
+}
+void launch_face_valM(cudaStream_t st, int nFaceNo, int fdof, int dof, const int *glob,
+                      const double *val, const double *W, double *valM) {
+  if (nFaceNo <= 0) return;
+  count_launch();
+  face_valM_kernel<<<(nFaceNo + 255) / 256, 256, 0, st>>>(nFaceNo, fdof, dof, glob, val, W, valM);
+}
+
+// ---------------------------------------------------------------------------
+// ADDBCMUL, L/ADDBCMUL.f:53-114 -- a face has O(10^3..10^4) nodes: one block
+__global__ void __launch_bounds__(1024) face_dot_kernel(int nFaceNo, int fdof, int dof,
+                                                        const int *__restrict__ glob,
+                                                        const double *__restrict__ valM,
+                                                        const double *__restrict__ X, int ownedLimit,
+                                                        int square, double *__restrict__ S,
+                                                        const int *done) {
+  DONE_GUARD(done);
+  __shared__ double smem[32];
+  const int m = fdof < dof ? fdof : dof;
+  double v = 0.0;
+  for (int a = threadIdx.x; a < nFaceNo; a += blockDim.x) {
+    const int Ac = glob[a];
+    if (Ac >= ownedLimit) continue;
+    for (int i = 0; i < m; i++) {
+      const double vm = valM[(size_t)a * fdof + i];
+      v += square ? vm * vm : vm * X[(size_t)Ac * dof + i];
+    }
+  }
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int wq = 0; wq < (int)(blockDim.x >> 5); wq++) t += smem[wq];
+    *S = t;
+  }
+}
+__global__ void face_axpy_kernel(int nFaceNo, int fdof, int dof, const int *__restrict__ glob,
+                                 const double *__restrict__ valM, double coef,
+                                 const double *__restrict__ S, double *__restrict__ Y,
+                                 const int *done) {
+  DONE_GUARD(done);
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= nFaceNo) return;
+  const int m = fdof < dof ? fdof : dof;
+  const double s = coef * (*S);
+  for (int i = 0; i < m; i++) Y[(size_t)glob[a] * dof + i] += valM[(size_t)a * fdof + i] * s;
+}
+void launch_face_dot(cudaStream_t st, int nFaceNo, int fdof, int dof, const int *glob,
+                     const double *valM, const double *X, int ownedLimit, double *S,
+                     const int *done) {
+  count_launch();
+  face_dot_kernel<<<1, 1024, 0, st>>>(nFaceNo, fdof, dof, glob, valM, X, ownedLimit, 0, S, done);
+}
+void launch_face_norm2(cudaStream_t st, int nFaceNo, int fdof, int nsd, const int *glob,
+                       const double *valM, int ownedLimit, double *S) {
+  count_launch();
+  face_dot_kernel<<<1, 1024, 0, st>>>(nFaceNo, fdof, nsd, glob, valM, nullptr, ownedLimit, 1, S,
+                                      nullptr);
+}
+void launch_face_axpy(cudaStream_t st, int nFaceNo, int fdof, int dof, const int *glob,
+                      const double *valM, double coef, const double *S, double *Y,
+                      const int *done) {
+  if (nFaceNo <= 0) return;
+  count_launch();
+  face_axpy_kernel<<<(nFaceNo + 255) / 256, 256, 0, st>>>(nFaceNo, fdof, dof, glob, valM, coef, S,
+                                                          Y, done);
+}
+
+// ---------------------------------------------------------------------------
+// One column of the Arnoldi/Givens recurrence, L/GMRES.f:342-366 (scalar part).
+// hcol[0..i] = <u_j, u_{i+1}> (already all-reduced).  Column-major h(sD+1, sD).
+__global__ void gmres_column_kernel(KrylovCtl *ctl, int i, int sD, const double *__restrict__ hcol,
+                                    double *__restrict__ h, double *__restrict__ c,
+                                    double *__restrict__ s, double *__restrict__ err,
+                                    double *__restrict__ coef) {
+  if (ctl->done) return;
+  if (threadIdx.x != 0) return;
+  double *hc = h + (size_t)(i - 1) * (sD + 1);  // h(:,i), 0-based rows
+  double hh = hcol[i];
+  for (int j = 0; j < i; j++) {
+    const double v = hcol[j];
+    hc[j] = v;
+    coef[j] = v;
+    hh = hh - v * v;
+  }
+  hh = sqrt(fabs(hh));
+  ctl->inv = 1.0 / hh;
+  hc[i] = hh;
+  for (int j = 0; j < i - 1; j++) {
+    const double tmp = c[j] * hc[j] + s[j] * hc[j + 1];
+    hc[j + 1] = -s[j] * hc[j] + c[j] * hc[j + 1];
+    hc[j] = tmp;
+  }
+  const double tmp = sqrt(hc[i - 1] * hc[i - 1] + hc[i] * hc[i]);
+  c[i - 1] = hc[i - 1] / tmp;
+  s[i - 1] = hc[i] / tmp;
+  hc[i - 1] = tmp;
+  hc[i] = 0.0;
+  err[i] = -s[i - 1] * err[i - 1];
+  err[i - 1] = c[i - 1] * err[i - 1];
+  ctl->ilast = i;
+  ctl->itr += 1;
+  if (fabs(err[i]) < ctl->eps) {
+    ctl->suc = 1;
+    ctl->done = 1;
+  }
+}
+void launch_gmres_column(cudaStream_t st, KrylovCtl *ctl, int i, int sD, const double *hcol,
+                         double *h, double *c, double *s, double *err, double *coef) {
+  count_launch();
+  gmres_column_kernel<<<1, 32, 0, st>>>(ctl, i, sD, hcol, h, c, s, err, coef);
+}
+
+// back substitution, L/GMRES.f:370-376; fNorm = |err(i+1)| (:382)
+__global__ void gmres_backsub_kernel(KrylovCtl *ctl, int sD, const double *__restrict__ h,
+                                     const double *__restrict__ err, double *__restrict__ y) {
+  if (threadIdx.x != 0) return;
+  const int i = ctl->ilast;
+  for (int j = 0; j < i; j++) y[j] = err[j];
+  for (int j = i - 1; j >= 0; j--) {
+    for (int k = j + 1; k < i; k++) y[j] = y[j] - h[(size_t)k * (sD + 1) + j] * y[k];
+    y[j] = y[j] / h[(size_t)j * (sD + 1) + j];
+  }
+  ctl->fNorm = fabs(err[i]);
+}
+void launch_gmres_backsub(cudaStream_t st, KrylovCtl *ctl, int sD, const double *h,
+                          const double *err, double *y) {
+  count_launch();
+  gmres_backsub_kernel<<<1, 32, 0, st>>>(ctl, sD, h, err, y);
+}
+
+// ---------------------------------------------------------------------------
+// DEPART, L/NSSOLVER.f:237-290: split dof x dof blocks into K (nsd x nsd), G (nsd x 1),
+// D (1 x nsd), L (1 x 1)
+__global__ void depart_kernel(int nnz, int nsd, const double *__restrict__ Val,
+                              double *__restrict__ mK, double *__restrict__ mG,
+                              double *__restrict__ mD, double *__restrict__ mL) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nnz) return;
+  const int dof = nsd + 1;
+  const double *t = Val + (size_t)p * dof * dof;
+  for (int i = 0; i < nsd; i++) {
+    for (int j = 0; j < nsd; j++) mK[(size_t)p * nsd * nsd + i * nsd + j] = t[i * dof + j];
+    mG[(size_t)p * nsd + i] = t[i * dof + nsd];
+    mD[(size_t)p * nsd + i] = t[nsd * dof + i];
+  }
+  mL[p] = t[nsd * dof + nsd];
+}
+// Gt(:, tpos[p]) = -mG(:, p): tpos = position of the transposed block (L/NSSOLVER.f:292-302)
+__global__ void gt_kernel(int nnz, int nsd, const int *__restrict__ tpos,
+                          const double *__restrict__ mG, double *__restrict__ Gt) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nnz) return;
+  const int l = tpos[p];
+  if (l < 0) return;
+  for (int d = 0; d < nsd; d++) Gt[(size_t)l * nsd + d] = -mG[(size_t)p * nsd + d];
+}
+void launch_depart(cudaStream_t st, int nnz, int nsd, const double *Val, double *mK, double *mG,
+                   double *mD, double *mL) {
+  count_launch();
+  depart_kernel<<<(nnz + 255) / 256, 256, 0, st>>>(nnz, nsd, Val, mK, mG, mD, mL);
+}
+void launch_gt(cudaStream_t st, int nnz, int nsd, const int *tpos, const double *mG, double *Gt) {
+  count_launch();
+  gt_kernel<<<(nnz + 255) / 256, 256, 0, st>>>(nnz, nsd, tpos, mG, Gt);
+}
+
+}  // namespace svfsi

@@ -1,0 +1,570 @@
+// solver.cu -- host orchestration of FSILS_SOLVE on the device (L/SOLVE.f:51-143):
+// PRECONDDIAG (L/PRECOND.f:50-145), GMRESV/GMRESS (L/GMRES.f:171-431), GMRES
+// out-of-place (L/GMRES.f:51-169), CGRADS/CGRADV/CGRAD_SCHUR (L/CGRAD.f),
+// NSSOLVER (L/NSSOLVER.f:52-233) with GE (L/GE.f).
+//
+// The Krylov loops never synchronise with the host per iteration: all scalars
+// (Hessenberg column, Givens rotations, residual estimate, CG alpha/beta) live
+// in device memory, the convergence test sets a device flag that turns the
+// remaining queued kernels of the cycle into no-ops, and the host watches a
+// progress word in mapped pinned memory to stay a bounded number of iterations
+// ahead of the GPU.
+#include <float.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <chrono>
+
+#include "core.h"
+
+namespace svfsi {
+
+namespace {
+
+constexpr int kLookahead = 4;  // iterations the host may run ahead of the device
+
+struct HostMirror {  // mapped pinned words written by the device
+  volatile int progress;
+  volatile int done;
+};
+HostMirror *g_hm = nullptr;      // host pointer
+HostMirror *g_hm_dev = nullptr;  // device alias
+int g_seq = 0;
+
+int ensure_mirror() {
+  if (g_hm) return 0;
+  void *p = nullptr;
+  CUDA_TRY(cudaHostAlloc(&p, sizeof(HostMirror), cudaHostAllocMapped));
+  g_hm = (HostMirror *)p;
+  g_hm->progress = 0;
+  g_hm->done = 0;
+  void *d = nullptr;
+  CUDA_TRY(cudaHostGetDevicePointer(&d, p, 0));
+  g_hm_dev = (HostMirror *)d;
+  return 0;
+}
+
+// progress/done publication + small scalar steps
+__global__ void publish_kernel(HostMirror *hm, int seq, const KrylovCtl *ctl) {
+  hm->progress = seq;
+  if (ctl->done) hm->done = 1;
+  __threadfence_system();
+}
+
+__global__ void ctl_reset_kernel(KrylovCtl *ctl, int clear_all) {
+  ctl->done = 0;
+  ctl->ilast = 0;
+  if (clear_all) {
+    ctl->suc = 0;
+    ctl->itr = 0;
+  }
+}
+
+// eps / iNorm from the squared norm in *ss (L/GMRES.f:296-300)
+__global__ void gmres_init_kernel(KrylovCtl *ctl, const double *ss, double absTol, double relTol) {
+  const double nrm = sqrt(*ss);
+  ctl->iNorm = nrm;
+  ctl->fNorm = nrm;
+  const double e = relTol * nrm;
+  ctl->eps = absTol > e ? absTol : e;
+}
+
+// err(1) = ||u1|| (L/GMRES.f:324)
+__global__ void gmres_err0_kernel(const double *ss, double *err) { err[0] = sqrt(*ss); }
+
+// ------------------------------------------------------------------ CG scalars
+// scal[0] = err, scal[1] = errO, scal[2] = alpha, scal[3] = errO/err, scal[4] = err/errO
+__global__ void cg_init_kernel(KrylovCtl *ctl, const double *ss, double absTol, double relTol) {
+  const double nrm = sqrt(*ss);
+  ctl->iNorm = nrm;
+  const double e0 = relTol * nrm;
+  double eps = absTol > e0 ? absTol : e0;
+  eps = eps * eps;
+  ctl->eps = eps;
+  const double err = nrm * nrm;
+  ctl->scal[0] = err;
+  ctl->scal[1] = err;
+  ctl->done = 0;
+  ctl->suc = 0;
+  ctl->ilast = 0;
+  if (err < eps) {  // loop exits at i = 1 with suc (L/CGRAD.f:151-154)
+    ctl->suc = 1;
+    ctl->done = 1;
+  }
+}
+// alpha = errO / <P, KP>   (L/CGRAD.f:159)
+__global__ void cg_alpha_kernel(KrylovCtl *ctl, const double *pkp) {
+  if (ctl->done) return;
+  ctl->scal[1] = ctl->scal[0];  // errO = err
+  ctl->scal[2] = ctl->scal[1] / *pkp;
+}
+// err = ||R||^2, convergence test of the NEXT loop trip (L/CGRAD.f:151-154,164-165)
+__global__ void cg_err_kernel(KrylovCtl *ctl, const double *rr, int mItr) {
+  if (ctl->done) return;
+  double e = sqrt(*rr);
+  e = e * e;
+  ctl->scal[0] = e;
+  ctl->scal[3] = ctl->scal[1] / e;
+  ctl->scal[4] = e / ctl->scal[1];
+  ctl->ilast += 1;  // completed iterations
+  // the reference still updates P before leaving the loop at the next trip's test;
+  // P is dead after that, so stopping here gives the same X, R, err, itr
+  if (e < ctl->eps) {
+    ctl->suc = 1;
+    ctl->done = 1;
+  }
+  (void)mItr;
+}
+
+// X += alpha P ; R -= alpha KP ; partial sums of R.R over the owned range
+__global__ void __launch_bounds__(256) cg_update_kernel(const KrylovCtl *ctl, double *__restrict__ X,
+                                                        double *__restrict__ R,
+                                                        const double *__restrict__ P,
+                                                        const double *__restrict__ KP, size_t n,
+                                                        size_t nOwned, double *__restrict__ partial) {
+  if (ctl->done) return;
+  __shared__ double smem[8];
+  const double alpha = ctl->scal[2];
+  double acc = 0.0;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n;
+       e += (size_t)gridDim.x * blockDim.x) {
+    X[e] = X[e] + alpha * P[e];
+    const double r = R[e] + (-alpha) * KP[e];
+    R[e] = r;
+    if (e < nOwned) acc = fma(r, r, acc);
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; w++) t += smem[w];
+    partial[blockIdx.x] = t;
+  }
+}
+// P = (P + (errO/err) R) * (err/errO)   (L/CGRAD.f:166-167: OMPSUM then OMPMUL)
+__global__ void __launch_bounds__(256) cg_pupdate_kernel(const KrylovCtl *ctl, double *__restrict__ P,
+                                                         const double *__restrict__ R, size_t n) {
+  if (ctl->done) return;
+  const double s1 = ctl->scal[3], s2 = ctl->scal[4];
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n;
+       e += (size_t)gridDim.x * blockDim.x)
+    P[e] = (P[e] + s1 * R[e]) * s2;
+}
+
+struct Bump {
+  char *base;
+  size_t off = 0;
+  explicit Bump(void *b) : base((char *)b) {}
+  double *take(size_t nd) {
+    double *p = (double *)(base + off);
+    off += ((nd * sizeof(double) + 255) / 256) * 256;
+    return p;
+  }
+};
+size_t padded(size_t nd) { return ((nd * sizeof(double) + 255) / 256) * 256; }
+
+bool any_coupled() {
+  for (const Face &f : ctx().face)
+    if (f.created && f.coupled) return true;
+  return false;
+}
+
+// ADDBCMUL (L/ADDBCMUL.f:53-114).  sS = device scratch scalars (one per face).
+int addbcmul(int op, int dof, const double *X, double *Y, double *sS, const int *done) {
+  Ctx &c = ctx();
+  for (size_t fi = 0; fi < c.face.size(); fi++) {
+    Face &f = c.face[fi];
+    if (!f.created || !f.coupled) continue;
+    const double coef = (op == 0) ? f.res : -f.res / (1.0 + (f.res * f.nS));
+    double *S = sS + fi;
+    if (f.shared) {
+      launch_face_dot(c.stream, f.nNo, f.dof, dof, f.d_glob, f.d_valM, X, c.mynNo, S, done);
+      if (int rc = allreduce_dev(S, 1)) return rc;
+    } else {
+      launch_face_dot(c.stream, f.nNo, f.dof, dof, f.d_glob, f.d_valM, X, c.nNo, S, done);
+    }
+    launch_face_axpy(c.stream, f.nNo, f.dof, dof, f.d_glob, f.d_valM, coef, S, Y, done);
+  }
+  return 0;
+}
+
+// BCPRE (L/GMRES.f:393-429, L/NSSOLVER.f:307-341): nS = ||valM||^2
+int bcpre(int nsd, double *sS) {
+  Ctx &c = ctx();
+  bool any = false;
+  for (size_t fi = 0; fi < c.face.size(); fi++) {
+    Face &f = c.face[fi];
+    if (!f.created || !f.coupled) continue;
+    any = true;
+    launch_face_norm2(c.stream, f.nNo, f.dof, nsd, f.d_glob, f.d_valM,
+                      f.shared ? c.mynNo : c.nNo, sS + fi);
+    if (f.shared)
+      if (int rc = allreduce_dev(sS + fi, 1)) return rc;
+  }
+  if (!any) return 0;
+  CUDA_TRY(cudaMemcpyAsync(c.h_small, sS, sizeof(double) * c.face.size(), cudaMemcpyDeviceToHost,
+                           c.stream));
+  CUDA_TRY(cudaStreamSynchronize(c.stream));
+  for (size_t fi = 0; fi < c.face.size(); fi++) {
+    Face &f = c.face[fi];
+    if (!f.created || !f.coupled) continue;
+    double v = c.h_small[fi];
+    if (f.shared) {  // NORMV(...)**2: sqrt then square (L/GMRES.f:413-414)
+      v = sqrt(v);
+      v = v * v;
+    }
+    f.nS = v;
+  }
+  return 0;
+}
+
+// squared 2-norm / dot over owned entries -> *out (device), all-reduced
+int dot_dev(const double *U, const double *V, size_t nOwned, double *out, const int *done) {
+  Ctx &c = ctx();
+  {
+    ProfScope ps(PROF_DOT);
+    launch_multidot(c.stream, U, 0, V, nOwned, 1, c.d_partial, done);
+    launch_reduce_partials(c.stream, c.d_partial, 1, out, done);
+  }
+  return allreduce_dev(out, 1);
+}
+
+double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// layout of the scalar area used by GMRES
+struct GmresScal {
+  KrylovCtl *ctl;
+  double *hcol, *h, *cc, *ss, *err, *y, *coef, *faceS, *tmp;
+  size_t doubles;
+};
+GmresScal gmres_scal(double *base, int sD, int nFaces) {
+  GmresScal g;
+  size_t o = 0;
+  g.ctl = (KrylovCtl *)base;
+  o += 32;
+  g.hcol = base + o; o += sD + 2;
+  g.h = base + o; o += (size_t)(sD + 1) * sD;
+  g.cc = base + o; o += sD;
+  g.ss = base + o; o += sD;
+  g.err = base + o; o += sD + 1;
+  g.y = base + o; o += sD;
+  g.coef = base + o; o += sD + 1;
+  g.faceS = base + o; o += nFaces + 1;
+  g.tmp = base + o; o += 8;
+  g.doubles = o;
+  return g;
+}
+
+int ensure_small_n(size_t nd) {
+  Ctx &c = ctx();
+  if (int rc = ensure_small()) return rc;
+  static size_t cap = 1 << 17;
+  if (nd <= cap) return 0;
+  cudaFree(c.d_small);
+  cudaFreeHost(c.h_small);
+  c.d_small = nullptr;
+  c.h_small = nullptr;
+  cap = nd + 1024;
+  CUDA_TRY(cudaMalloc(&c.d_small, cap * sizeof(double)));
+  CUDA_TRY(cudaMemset(c.d_small, 0, cap * sizeof(double)));
+  CUDA_TRY(cudaMallocHost(&c.h_small, cap * sizeof(double)));
+  return 0;
+}
+
+// One Arnoldi cycle (L/GMRES.f:327-367 and the shared core of :106-152): u[0]
+// holds the normalised residual, err[0] its norm.  Enqueues up to sD columns and
+// stops enqueueing once the device reports convergence.
+int arnoldi_cycle(int kind, int dof, const double *Val, double *u, size_t stride, size_t n,
+                  size_t nOwned, int sD, GmresScal &g, bool pre, double *unCondU) {
+  Ctx &c = ctx();
+  const int *done = &g.ctl->done;
+  g_hm->done = 0;
+  const int seq0 = g_seq;
+  for (int i = 1; i <= sD; i++) {
+    if (g_hm->done) break;
+    while (g_seq - g_hm->progress > kLookahead && !g_hm->done) { /* spin: bounded run-ahead */ }
+    double *ui = u + (size_t)i * stride, *um = u + (size_t)(i - 1) * stride;
+    if (int rc = sparmul(kind, dof, Val, um, ui, done)) return rc;
+    if (kind == 0) {
+      if (int rc = addbcmul(0, dof, um, ui, g.faceS, done)) return rc;
+      if (pre && any_coupled()) {
+        launch_vecop(c.stream, VOP_COPY, unCondU, ui, nullptr, n, nullptr, 0.0, done);
+        if (int rc = addbcmul(1, dof, unCondU, ui, g.faceS, done)) return rc;
+      }
+    }
+    {
+      ProfScope ps(PROF_DOT);
+      launch_multidot(c.stream, u, stride, ui, nOwned, i + 1, c.d_partial, done);
+      launch_reduce_partials(c.stream, c.d_partial, i + 1, g.hcol, done);
+    }
+    if (int rc = allreduce_dev(g.hcol, (size_t)i + 1)) return rc;
+    {
+      ProfScope ps(PROF_SMALL);
+      launch_gmres_column(c.stream, g.ctl, i, sD, g.hcol, g.h, g.cc, g.ss, g.err, g.coef);
+    }
+    {
+      ProfScope ps(PROF_AXPY);
+      // the column kernel may have set `done`; the update of u(i+1) must still run
+      // for the column that converged?  No: after EXIT the reference never uses
+      // u(:,:,i+1) (L/GMRES.f:363-381 sums j = 1..i), so skipping is exact.
+      launch_multi_axpy_scale(c.stream, u, stride, ui, n, i, g.coef, &g.ctl->inv, done);
+    }
+    g_seq++;
+    publish_kernel<<<1, 1, 0, c.stream>>>(g_hm_dev, g_seq, g.ctl);
+    count_launch();
+  }
+  (void)seq0;
+  return 0;
+}
+
+// GMRESV / GMRESS in place (L/GMRES.f:273-431, :171-271)
+int gmres_inplace(svfsi_subls_t *ls, int dof, const double *Val, double *R, bool scalar) {
+  Ctx &c = ctx();
+  const int sD = ls->sD;
+  const size_t n = (size_t)c.nNo * dof, nOwned = (size_t)c.mynNo * dof;
+  const size_t stride = padded(n) / sizeof(double);
+  const int kind = scalar ? 3 : 0;
+  if (int rc = ensure_mirror()) return rc;
+  GmresScal g = gmres_scal(nullptr, sD, (int)c.face.size());
+  if (int rc = ensure_small_n(g.doubles)) return rc;
+  g = gmres_scal(c.d_small, sD, (int)c.face.size());
+  // workspace: u(sD+1), X
+  if (int rc = ensure_ws((size_t)(sD + 2) * stride * sizeof(double) + 4096)) return rc;
+  Bump b((char *)c.d_ws);
+  double *u = b.take((size_t)(sD + 1) * stride);
+  double *X = b.take(n);
+  const int *nodone = nullptr;
+
+  const double t0 = now_s();
+  ls->suc = 0;
+  ctl_reset_kernel<<<1, 1, 0, c.stream>>>(g.ctl, 1);
+  count_launch();
+  if (int rc = dot_dev(R, R, nOwned, g.tmp, nodone)) return rc;
+  gmres_init_kernel<<<1, 1, 0, c.stream>>>(g.ctl, g.tmp, ls->absTol, ls->relTol);
+  count_launch();
+  launch_vecop(c.stream, VOP_ZERO, X, nullptr, nullptr, n, nullptr, 0.0, nodone);
+  if (!scalar)
+    if (int rc = bcpre(dof - 1, g.faceS)) return rc;
+  KrylovCtl hc;
+  CUDA_TRY(cudaMemcpyAsync(&hc, g.ctl, sizeof(hc), cudaMemcpyDeviceToHost, c.stream));
+  CUDA_TRY(cudaStreamSynchronize(c.stream));
+  ls->iNorm = hc.iNorm;
+  ls->fNorm = hc.iNorm;
+  ls->itr = 0;
+  if (ls->iNorm <= ls->absTol) {
+    ls->callD = DBL_EPSILON;
+    ls->dB = 0.0;
+    return 0;
+  }
+  int itrHost = 0;
+  for (int l = 1; l <= ls->mItr; l++) {
+    ls->dB = ls->fNorm;
+    itrHost++;
+    ctl_reset_kernel<<<1, 1, 0, c.stream>>>(g.ctl, 0);
+    count_launch();
+    if (int rc = sparmul(kind, dof, Val, X, u, nodone)) return rc;
+    if (!scalar)
+      if (int rc = addbcmul(0, dof, X, u, g.faceS, nodone)) return rc;
+    launch_vecop(c.stream, VOP_SUB_FROM, u, R, nullptr, n, nullptr, 0.0, nodone);
+    if (int rc = dot_dev(u, u, nOwned, g.tmp, nodone)) return rc;
+    gmres_err0_kernel<<<1, 1, 0, c.stream>>>(g.tmp, g.err);
+    count_launch();
+    launch_vecop(c.stream, VOP_DIV_DEV, u, nullptr, nullptr, n, g.err, 0.0, nodone);
+    if (int rc = arnoldi_cycle(kind, dof, Val, u, stride, n, nOwned, sD, g, false, nullptr)) return rc;
+    {
+      ProfScope ps(PROF_SMALL);
+      launch_gmres_backsub(c.stream, g.ctl, sD, g.h, g.err, g.y);
+    }
+    {
+      ProfScope ps(PROF_AXPY);
+      launch_multi_axpy_acc(c.stream, u, stride, X, n, &g.ctl->ilast, sD, g.y);
+    }
+    CUDA_TRY(cudaMemcpyAsync(&hc, g.ctl, sizeof(hc), cudaMemcpyDeviceToHost, c.stream));
+    CUDA_TRY(cudaStreamSynchronize(c.stream));
+    ls->fNorm = hc.fNorm;
+    if (hc.suc) {
+      ls->suc = 1;
+      break;
+    }
+  }
+  ls->itr = itrHost + hc.itr;
+  launch_vecop(c.stream, VOP_COPY, R, X, nullptr, n, nullptr, 0.0, nodone);
+  CUDA_TRY(cudaStreamSynchronize(c.stream));
+  ls->callD = now_s() - t0;
+  ls->dB = 10.0 * log(ls->fNorm / ls->dB);
+  return 0;
+}
+
+// CGRADS / CGRADV (L/CGRAD.f:125-242)
+int cgrad(svfsi_subls_t *ls, int dof, const double *K, double *R) {
+  Ctx &c = ctx();
+  const size_t n = (size_t)c.nNo * dof, nOwned = (size_t)c.mynNo * dof;
+  const int kind = dof == 1 ? 3 : 0;
+  if (int rc = ensure_mirror()) return rc;
+  if (int rc = ensure_small_n(4096)) return rc;
+  KrylovCtl *ctl = (KrylovCtl *)c.d_small;
+  double *sc = c.d_small + 32;  // [0] = <P,KP> / R.R scratch
+  if (int rc = ensure_ws(3 * padded(n) + 4096)) return rc;
+  Bump b((char *)c.d_ws);
+  double *P = b.take(n), *KP = b.take(n), *X = b.take(n);
+  const int *done = &ctl->done;
+  const int nblk = multidot_nblk();
+
+  const double t0 = now_s();
+  if (int rc = dot_dev(R, R, nOwned, sc, nullptr)) return rc;
+  cg_init_kernel<<<1, 1, 0, c.stream>>>(ctl, sc, ls->absTol, ls->relTol);
+  count_launch();
+  launch_vecop(c.stream, VOP_COPY, P, R, nullptr, n, nullptr, 0.0, nullptr);
+  launch_vecop(c.stream, VOP_ZERO, X, nullptr, nullptr, n, nullptr, 0.0, nullptr);
+  g_hm->done = 0;
+  g_seq++;
+  publish_kernel<<<1, 1, 0, c.stream>>>(g_hm_dev, g_seq, ctl);
+  count_launch();
+  for (int i = 1; i <= ls->mItr; i++) {
+    if (g_hm->done) break;
+    while (g_seq - g_hm->progress > kLookahead && !g_hm->done) { /* bounded run-ahead */ }
+    if (int rc = sparmul(kind, dof, K, P, KP, done)) return rc;
+    if (int rc = dot_dev(P, KP, nOwned, sc, done)) return rc;
+    cg_alpha_kernel<<<1, 1, 0, c.stream>>>(ctl, sc);
+    {
+      ProfScope ps(PROF_AXPY);
+      cg_update_kernel<<<nblk, 256, 0, c.stream>>>(ctl, X, R, P, KP, n, nOwned, c.d_partial);
+      launch_reduce_partials(c.stream, c.d_partial, 1, sc + 1, done);
+    }
+    if (int rc = allreduce_dev(sc + 1, 1)) return rc;
+    cg_err_kernel<<<1, 1, 0, c.stream>>>(ctl, sc + 1, ls->mItr);
+    {
+      ProfScope ps(PROF_AXPY);
+      cg_pupdate_kernel<<<148 * 8, 256, 0, c.stream>>>(ctl, P, R, n);
+    }
+    g_seq++;
+    publish_kernel<<<1, 1, 0, c.stream>>>(g_hm_dev, g_seq, ctl);
+    count_launch(5);
+  }
+  launch_vecop(c.stream, VOP_COPY, R, X, nullptr, n, nullptr, 0.0, nullptr);
+  KrylovCtl hc;
+  CUDA_TRY(cudaMemcpyAsync(&hc, ctl, sizeof(hc), cudaMemcpyDeviceToHost, c.stream));
+  CUDA_TRY(cudaStreamSynchronize(c.stream));
+  ls->suc = hc.suc;
+  ls->iNorm = hc.iNorm;
+  ls->itr = hc.ilast;
+  const double err = hc.scal[0], errO = hc.scal[1];
+  ls->fNorm = sqrt(err);
+  ls->callD = now_s() - t0;
+  if (errO < DBL_EPSILON) ls->dB = 0.0;
+  else ls->dB = 5.0 * log(err / errO);
+  return 0;
+}
+
+// PRECONDDIAG (L/PRECOND.f:50-145); W receives the scaling (Wc of L/SOLVE.f:98-100)
+int preconddiag(int dof, double *Val, double *R, double *W) {
+  Ctx &c = ctx();
+  ProfScope ps(PROF_PRECOND);
+  launch_diag_extract(c.stream, c.nNo, dof, c.d_diag, Val, W);
+  if (int rc = halo_sum(W, dof, nullptr)) return rc;
+  launch_w_finalize(c.stream, (size_t)c.nNo * dof, W);
+  for (Face &f : c.face) {
+    if (!f.created || !f.inc) continue;
+    if (f.bGrp == SVFSI_BC_TYPE_DIR)
+      launch_w_dirichlet(c.stream, f.nNo, f.dof, dof, f.d_glob, f.d_val, W);
+  }
+  launch_scale_val(c.stream, c.nnz, dof, c.d_rowOf, c.d_col, W, Val);
+  launch_vecop(c.stream, VOP_MUL, R, W, nullptr, (size_t)c.nNo * dof, nullptr, 0.0, nullptr);
+  for (Face &f : c.face) {
+    if (!f.created || !f.coupled) continue;
+    launch_face_valM(c.stream, f.nNo, f.dof, dof, f.d_glob, f.d_val, W, f.d_valM);
+  }
+  return 0;
+}
+
+}  // namespace
+
+int nssolver_dev(svfsi_ls_t *ls, int dof, const double *Val, double *R);  // nssolver.cu
+
+void ls_defaults(svfsi_ls_t *ls, int LS_type) {
+  // FSILS_LS_CREATE, L/LS.f:69-95
+  memset(ls, 0, sizeof(*ls));
+  ls->LS_type = LS_type;
+  switch (LS_type) {
+    case SVFSI_LS_TYPE_NS:
+      ls->RI.relTol = 0.4; ls->GM.relTol = 1.e-2; ls->CG.relTol = 0.2;
+      ls->RI.mItr = 10; ls->GM.mItr = 2; ls->CG.mItr = 500;
+      ls->GM.sD = 100; ls->RI.sD = 100;
+      break;
+    case SVFSI_LS_TYPE_GMRES:
+      ls->RI.relTol = 0.1; ls->RI.mItr = 4; ls->RI.sD = 250;
+      break;
+    case SVFSI_LS_TYPE_CG:
+      ls->RI.relTol = 1.e-2; ls->RI.mItr = 1000;
+      break;
+    case SVFSI_LS_TYPE_BICGS:
+      ls->RI.relTol = 1.e-2; ls->RI.mItr = 500;
+      break;
+    default: break;
+  }
+  ls->RI.absTol = 1.e-10; ls->GM.absTol = 1.e-10; ls->CG.absTol = 1.e-10;
+}
+
+// exported to nssolver.cu
+int solver_addbcmul(int op, int dof, const double *X, double *Y, double *sS, const int *done) {
+  return addbcmul(op, dof, X, Y, sS, done);
+}
+int solver_bcpre(int nsd, double *sS) { return bcpre(nsd, sS); }
+bool solver_any_coupled() { return any_coupled(); }
+
+int fsils_solve_dev(svfsi_ls_t *ls, int dof, int prec, const int32_t *incL, const double *res) {
+  Ctx &c = ctx();
+  if (!c.lhs) return fail(SVFSI_ERR_STATE, "FSILS_SOLVE before FSILS_LHS_CREATE");
+  if (c.dof != dof || !c.d_R || !c.d_Val)
+    return fail(SVFSI_ERR_STATE, "no device-resident system of this dof");
+  // face flags, L/SOLVE.f:69-91
+  bool anyNeu = false;
+  for (size_t fi = 0; fi < c.face.size(); fi++) {
+    Face &f = c.face[fi];
+    f.inc = true;
+    if (incL && incL[fi] == 0) f.inc = false;
+    if (f.bGrp == SVFSI_BC_TYPE_NEU) anyNeu = true;
+  }
+  if (!res && anyNeu) return fail(SVFSI_ERR_ARG, "FSILS: res is required for Neu surfaces");
+  for (size_t fi = 0; fi < c.face.size(); fi++) {
+    Face &f = c.face[fi];
+    f.coupled = false;
+    if (!f.inc) continue;
+    if (f.bGrp == SVFSI_BC_TYPE_NEU && res[fi] != 0.0) {
+      f.res = res[fi];
+      f.coupled = true;
+    }
+  }
+  if (prec != SVFSI_PRECOND_FSILS)
+    return fail(SVFSI_ERR_UNSUPPORTED, "only PRECOND_FSILS (diagonal) is implemented");
+  if (int rc = ensure_small()) return rc;
+
+  ProfScope ps(PROF_SOLVE);
+  // the solvers may grow (reallocate) the workspace, so W lives in its own buffer
+  static double *d_W = nullptr;
+  static size_t wCap = 0;
+  const size_t wNeed = (size_t)c.nNo * dof * sizeof(double);
+  if (wCap < wNeed) {
+    if (d_W) cudaFree(d_W);
+    CUDA_TRY(cudaMalloc(&d_W, wNeed));
+    wCap = wNeed;
+  }
+  if (int rc = preconddiag(dof, c.d_Val, c.d_R, d_W)) return rc;
+
+  int rc = 0;
+  switch (ls->LS_type) {
+    case SVFSI_LS_TYPE_NS: rc = nssolver_dev(ls, dof, c.d_Val, c.d_R); break;
+    case SVFSI_LS_TYPE_GMRES: rc = gmres_inplace(&ls->RI, dof, c.d_Val, c.d_R, dof == 1); break;
+    case SVFSI_LS_TYPE_CG: rc = cgrad(&ls->RI, dof, c.d_Val, c.d_R); break;
+    default: rc = fail(SVFSI_ERR_UNSUPPORTED, "FSILS: LS_type not implemented on the device");
+  }
+  if (rc) return rc;
+  launch_vecop(c.stream, VOP_MUL, c.d_R, d_W, nullptr, (size_t)c.nNo * dof, nullptr, 0.0, nullptr);
+  return 0;
+}
+
+}  // namespace svfsi

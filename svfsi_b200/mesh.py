@@ -250,3 +250,65 @@ def split_mesh(m: Mesh, part: np.ndarray, nparts: int):
 def scatter_nodal(rm: RankMesh, U: np.ndarray) -> np.ndarray:
     """LOCAL(): a rank's copy of a global nodal array (DISTRIBUTE.f:221-231)."""
     return np.ascontiguousarray(U[rm.ltg.astype(np.int64) - 1])
+
+
+# ----------------------------------------------------------------------------------------------
+def csr_pattern(tnNo: int, IEN: np.ndarray):
+    """Node-graph CSR that svFSI's LHSA builds at setup (LHSA.f:38-262): row a lists every node
+    sharing an element with a (a itself included), ascending, 1-based ``rowPtr[tnNo+1]``,
+    ``colPtr[nnz]``.  Host/NumPy: this is setup the Fortran driver keeps; the synthetic harness
+    needs it to feed ``FSILS_LHS_CREATE``."""
+    ien = IEN.astype(np.int64) - 1
+    nEl = ien.shape[0]
+    keys = []
+    chunk = 2_000_000
+    for s in range(0, nEl, chunk):
+        e = ien[s:s + chunk]
+        k = (e[:, :, None] * tnNo + e[:, None, :]).reshape(-1)
+        keys.append(np.unique(k))
+    k = np.unique(np.concatenate(keys)) if len(keys) > 1 else keys[0]
+    rows = k // tnNo
+    cols = k - rows * tnNo
+    counts = np.bincount(rows, minlength=tnNo)
+    if (counts == 0).any():
+        raise RuntimeError(f"Node {int(np.argmin(counts > 0)) + 1} is isolated")
+    rowPtr = np.empty(tnNo + 1, dtype=np.int32)
+    rowPtr[0] = 1
+    rowPtr[1:] = 1 + np.cumsum(counts)
+    return rowPtr, (cols + 1).astype(np.int32)
+
+
+@dataclass
+class RankProblem:
+    """Everything one rank hands to the C-ABI: local mesh, CSR pattern, state, face lists."""
+    rm: RankMesh
+    rowPtr: np.ndarray
+    colPtr: np.ndarray
+    Ag: np.ndarray
+    Yg: np.ndarray
+    faces: dict           # name -> dict(gN local ids (1-based), val (n,3) or None, bc 'Dir'|'Neu')
+
+
+def build_problem(nx, ny, nz, nparts=1, R=2.0, L=30.0, umax=10.0, pert=0.01, acc=0.0,
+                  seed=SEED):
+    """Synthetic pipe problem: mesh, axial-slab partition, per-rank CSR and state, and the three
+    faces (inlet/wall Dirichlet with zero mask, outlet Neumann with val = int N n dGamma,
+    BAFINI.f:490-533)."""
+    m = make_cylinder(nx, ny, nz, R=R, L=L)
+    Ag, Yg = poiseuille_state(m, umax=umax, pert=pert, seed=seed, acc=acc)
+    part = partition_slabs(m, nparts)
+    rms = split_mesh(m, part, nparts)
+    out = []
+    for rm in rms:
+        rowPtr, colPtr = csr_pattern(rm.nNo, rm.IEN)
+        faces = {}
+        for name in ("inlet", "wall", "outlet"):
+            fa = rm.faces[name]
+            if name == "outlet":
+                val = face_normal_integrals(m, m.faces[name], fa["gN_global"], fa["tri_sel"])
+                faces[name] = dict(gN=fa["gN"], val=val, bc="Neu")
+            else:
+                faces[name] = dict(gN=fa["gN"], val=None, bc="Dir")
+        out.append(RankProblem(rm, rowPtr, colPtr, scatter_nodal(rm, Ag), scatter_nodal(rm, Yg),
+                               faces))
+    return m, out, (Ag, Yg)

@@ -1,0 +1,60 @@
+"""Shared helpers of the parity tests: run the CPU oracle (oracle/) end to end on the same
+synthetic problem the CUDA path gets.  Test infrastructure only."""
+import numpy as np
+
+from oracle import oracle as ora
+from svfsi_b200 import mesh
+
+RHO, MU, DT = 1.06, 0.04, 5e-3
+F = (0.0, 0.0, 0.0)
+GA = mesh.gen_alpha(0.2)
+FACE_ORDER = ("inlet", "wall", "outlet")     # faIn = 1, 2, 3
+
+
+def fluid_par():
+    return ora.fluid_par(RHO, MU, F, DT, GA["af"], GA["am"], GA["gam"])
+
+
+def rel_err(a, b):
+    """max|a-b| / max|b|  (SURVEY.md 8c parity metric)"""
+    den = np.abs(b).max()
+    return float(np.abs(a - b).max() / (den if den > 0 else 1.0))
+
+
+def block_class_errs(Val, Val_ref):
+    """per dof-block class of the 4x4 tangent: momentum 3x3, pressure column, continuity row, dC/dP"""
+    V = Val.reshape(-1, 4, 4); W = Val_ref.reshape(-1, 4, 4)
+    return dict(KK=rel_err(V[:, :3, :3], W[:, :3, :3]), G=rel_err(V[:, :3, 3], W[:, :3, 3]),
+                D=rel_err(V[:, 3, :3], W[:, 3, :3]), L=rel_err(V[:, 3, 3], W[:, 3, 3]))
+
+
+def oracle_world(probs, gnNo, nFaces=3, with_faces=True, native=False):
+    w = ora.World(gnNo, [p.rm.ltg for p in probs], [p.rowPtr for p in probs],
+                  [p.colPtr for p in probs], nFaces, native=native)
+    if with_faces:
+        for fi, name in enumerate(FACE_ORDER, start=1):
+            bc = ora.BC_TYPE_Neu if probs[0].faces[name]["bc"] == "Neu" else ora.BC_TYPE_Dir
+            vals = [p.faces[name]["val"] for p in probs]
+            w.bc_create(fi, [p.faces[name]["gN"] for p in probs], 3, bc,
+                        None if vals[0] is None else vals)
+    return w
+
+
+def oracle_assemble(probs, native=False):
+    par = fluid_par()
+    Rs, Vs = [], []
+    for p in probs:
+        R, V = ora.construct_fluid(par, p.rm.IEN, p.rm.x, p.Ag, p.Yg, np.zeros((p.rm.nNo, 3)),
+                                   p.rowPtr, p.colPtr, native=native)
+        Rs.append(R); Vs.append(V)
+    return Rs, Vs
+
+
+def oracle_commu(w, probs, Rs, dof=4):
+    """COMMU(R), S/ALLFUN.f:514-533: permute -> FSILS_COMMUV -> unpermute"""
+    maps = [w.map(r).astype(np.int64) - 1 for r in range(len(probs))]
+    tmp = []
+    for R, mp in zip(Rs, maps):
+        t = np.zeros_like(R); t[mp] = R; tmp.append(t)
+    w.commuv(dof, tmp)
+    return [t[mp].copy() for t, mp in zip(tmp, maps)]

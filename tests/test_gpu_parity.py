@@ -1,0 +1,177 @@
+"""-m gpu: the CUDA path (through the C-ABI, svfsi_b200.api) against the CPU oracle on the same
+seeded synthetic pipe.  Tolerances are the north_star's: assembled residual / tangent within
+1e-12 relative (max|diff|/max|ref| per array and per block class), GMRES iteration count
+(RI%itr = SpMV count, L/GMRES.f:315,328) within +-1, Newton-step solution within 1e-8 relative."""
+import numpy as np
+import pytest
+
+import common as cm
+from oracle import oracle as ora
+from svfsi_b200 import api, mesh
+
+pytestmark = pytest.mark.gpu
+
+TOL_ASM = 1e-12
+TOL_SOL = 1e-8
+
+
+@pytest.fixture(scope="module")
+def prob(gpu_lib):
+    m, probs, _ = mesh.build_problem(8, 8, 20, nparts=1, L=4.0)
+    p = probs[0]
+    api.FSILS_LHS_CREATE(m.nNo, p.rm.nNo, p.colPtr.size, p.rm.ltg, p.rowPtr, p.colPtr, 3)
+    for fi, name in enumerate(cm.FACE_ORDER, start=1):
+        fa = p.faces[name]
+        api.FSILS_BC_CREATE(fi, fa["gN"].size, 3,
+                            api.BC_TYPE_Neu if fa["bc"] == "Neu" else api.BC_TYPE_Dir, fa["gN"],
+                            fa["val"])
+    api.mesh_create(p.rm.IEN, p.rm.x)
+    yield m, p
+    api.FSILS_LHS_FREE()
+
+
+def gpu_assemble(p, variant):
+    api.CONSTRUCT_FLUID(p.Ag, p.Yg, None, cm.RHO, cm.MU, cm.F, cm.DT, cm.GA["af"], cm.GA["am"],
+                        cm.GA["gam"], variant)
+    return api.get_R(4), api.get_Val(4)
+
+
+@pytest.mark.parametrize("variant", [api.ASM_ATOMIC, api.ASM_COLORED])
+def test_fluid_assembly(prob, variant):
+    m, p = prob
+    Rs, Vs = cm.oracle_assemble([p])
+    R, V = gpu_assemble(p, variant)
+    assert cm.rel_err(R[:, :3], Rs[0][:, :3]) <= TOL_ASM
+    assert cm.rel_err(R[:, 3], Rs[0][:, 3]) <= TOL_ASM
+    errs = cm.block_class_errs(V, Vs[0])
+    assert max(errs.values()) <= TOL_ASM, errs
+
+
+def test_colored_assembly_is_deterministic(prob):
+    m, p = prob
+    R1, V1 = gpu_assemble(p, api.ASM_COLORED)
+    R2, V2 = gpu_assemble(p, api.ASM_COLORED)
+    assert np.array_equal(R1, R2) and np.array_equal(V1, V2)
+    assert api.mesh_ncolors() >= 24          # interior node valence of the Kuhn lattice
+
+
+def test_heat_assembly(prob):
+    m, p = prob
+    rng = np.random.default_rng(7)
+    Tg = rng.uniform(0, 1, p.rm.nNo); Ad = rng.uniform(-1, 1, p.rm.nNo)
+    par = ora.heat_par(1.3, 0.2, 1.1, cm.DT, cm.GA["af"], cm.GA["am"], cm.GA["gam"])
+    Rr, Vr = ora.construct_heats(par, p.rm.IEN, p.rm.x, Ad, Tg, p.rowPtr, p.colPtr)
+    for variant in (api.ASM_ATOMIC, api.ASM_COLORED):
+        api.CONSTRUCT_HEATS(Ad, Tg, 1.3, 0.2, 1.1, cm.DT, cm.GA["af"], cm.GA["am"], cm.GA["gam"],
+                            variant)
+        assert cm.rel_err(api.get_R(1), Rr) <= TOL_ASM
+        assert cm.rel_err(api.get_Val(1), Vr) <= TOL_ASM
+
+
+@pytest.mark.parametrize("kind,dof", [("VV", 4), ("VV", 3), ("VS", 3), ("SV", 3), ("SS", 1),
+                                       ("VV", 2), ("VV", 1)])
+def test_sparmul(prob, kind, dof):
+    m, p = prob
+    rng = np.random.default_rng(11)
+    nnz, nNo = p.colPtr.size, p.rm.nNo
+    br = dof if kind in ("VV", "SV") else 1
+    bc = dof if kind in ("VV", "VS") else 1
+    K = rng.standard_normal((nnz, br * bc)); U = rng.standard_normal((nNo, bc))
+    w = cm.oracle_world([p], m.nNo, with_faces=False)
+    if kind == "VV" and dof > 1:
+        ref = w.sparmul_vv(dof, [K], [U])[0]
+    elif kind == "VS":
+        ref = w.sparmul_vs(dof, [K], [U])[0]
+    elif kind == "SV":
+        ref = w.sparmul_sv(dof, [K], [U.reshape(-1)])[0]
+    else:
+        ref = w.sparmul_ss([K.reshape(-1)], [U.reshape(-1)])[0]
+    got = api.FSILS_SPARMUL("SS" if dof == 1 else kind, dof, K, U)
+    assert cm.rel_err(got.reshape(ref.shape), ref) <= 1e-14
+
+
+def test_dot(prob):
+    m, p = prob
+    rng = np.random.default_rng(5)
+    U = rng.standard_normal((p.rm.nNo, 4)); V = rng.standard_normal((p.rm.nNo, 4))
+    ref = float((U * V).sum())
+    assert abs(api.FSILS_DOTV(4, U, V) - ref) <= 1e-12 * abs(ref) + 1e-12
+
+
+@pytest.mark.parametrize("relTol,sD,mItr,res_out", [(1e-6, 100, 10, 0.0), (1e-10, 200, 4, 0.0),
+                                                    (1e-6, 100, 10, 5.0), (1e-8, 20, 40, 0.0),
+                                                    (0.1, 250, 4, 0.0)])
+def test_gmres_newton_step(prob, relTol, sD, mItr, res_out):
+    """assembly -> FSILS_SOLVE(GMRES, diagonal precond) == oracle: itr +-1, iNorm/fNorm, solution"""
+    m, p = prob
+    Rs, Vs = cm.oracle_assemble([p])
+    w = cm.oracle_world([p], m.nNo)
+    res = np.array([0.0, 0.0, res_out])
+    ls_o = ora.ls_create(ora.LS_TYPE_GMRES, relTol=relTol, absTol=1e-14, maxItr=mItr, dimKry=sD)
+    Ro = Rs[0].copy()
+    w.solve(ls_o, 4, [Ro], [Vs[0].copy()], incL=[1, 1, 1], res=res)
+
+    api.CONSTRUCT_FLUID(p.Ag, p.Yg, None, cm.RHO, cm.MU, cm.F, cm.DT, cm.GA["af"], cm.GA["am"],
+                        cm.GA["gam"], api.ASM_COLORED)
+    ls = api.FSILS_LS_CREATE(api.LS_TYPE_GMRES, relTol=relTol, absTol=1e-14, maxItr=mItr, dimKry=sD)
+    api.solve_dev(ls, 4, incL=[1, 1, 1], res=res)
+    X = api.get_R(4)
+    assert abs(ls.RI.itr - ls_o.RI.itr) <= 1, (ls.RI.itr, ls_o.RI.itr)
+    assert bool(ls.RI.suc) == bool(ls_o.RI.suc)
+    assert abs(ls.RI.iNorm - ls_o.RI.iNorm) <= 1e-10 * ls_o.RI.iNorm
+    if relTol <= 1e-6:
+        num = np.linalg.norm(X - Ro) / np.linalg.norm(Ro)
+        # the linear solve is only converged to relTol: both sides stop at the same iteration,
+        # so the difference is round-off amplified by the Krylov recurrence
+        assert num <= TOL_SOL, num
+
+
+def test_host_matrix_solve_matches_device_resident(prob):
+    """FSILS_SOLVE with host Ri/Val (the reference call shape) == device-resident path"""
+    m, p = prob
+    Rs, Vs = cm.oracle_assemble([p])
+    ls = api.FSILS_LS_CREATE(api.LS_TYPE_GMRES, relTol=1e-8, absTol=1e-14, maxItr=10, dimKry=50)
+    Ri = Rs[0].copy()
+    api.FSILS_SOLVE(ls, 4, Ri, Vs[0], incL=[1, 1, 1], res=[0, 0, 0])
+    w = cm.oracle_world([p], m.nNo)
+    ls_o = ora.ls_create(ora.LS_TYPE_GMRES, relTol=1e-8, absTol=1e-14, maxItr=10, dimKry=50)
+    Ro = Rs[0].copy()
+    w.solve(ls_o, 4, [Ro], [Vs[0].copy()], incL=[1, 1, 1], res=[0.0, 0.0, 0.0])
+    assert abs(ls.RI.itr - ls_o.RI.itr) <= 1
+    assert np.linalg.norm(Ri - Ro) / np.linalg.norm(Ro) <= TOL_SOL
+
+
+def test_heat_cg(prob):
+    m, p = prob
+    rng = np.random.default_rng(3)
+    Tg = rng.uniform(0, 1, p.rm.nNo); Ad = rng.uniform(-1, 1, p.rm.nNo)
+    par = ora.heat_par(1.0, 0.0, 1.0, cm.DT, cm.GA["af"], cm.GA["am"], cm.GA["gam"])
+    Rr, Vr = ora.construct_heats(par, p.rm.IEN, p.rm.x, Ad, Tg, p.rowPtr, p.colPtr)
+    w = ora.World(m.nNo, [p.rm.ltg], [p.rowPtr], [p.colPtr], 2)
+    for fi, name in enumerate(("inlet", "outlet"), start=1):
+        w.bc_create(fi, [p.faces[name]["gN"]], 1, ora.BC_TYPE_Dir, None)
+    ls_o = ora.ls_create(ora.LS_TYPE_CG, relTol=1e-8, absTol=1e-14, maxItr=500)
+    Ro = Rr.copy()
+    w.solve(ls_o, 1, [Ro], [Vr.copy()], incL=[1, 1], res=None)
+
+    api.FSILS_LHS_FREE()
+    api.FSILS_LHS_CREATE(m.nNo, p.rm.nNo, p.colPtr.size, p.rm.ltg, p.rowPtr, p.colPtr, 2)
+    for fi, name in enumerate(("inlet", "outlet"), start=1):
+        api.FSILS_BC_CREATE(fi, p.faces[name]["gN"].size, 1, api.BC_TYPE_Dir, p.faces[name]["gN"])
+    api.mesh_create(p.rm.IEN, p.rm.x)
+    api.CONSTRUCT_HEATS(Ad, Tg, 1.0, 0.0, 1.0, cm.DT, cm.GA["af"], cm.GA["am"], cm.GA["gam"],
+                        api.ASM_COLORED)
+    ls = api.FSILS_LS_CREATE(api.LS_TYPE_CG, relTol=1e-8, absTol=1e-14, maxItr=500)
+    api.solve_dev(ls, 1, incL=[1, 1])
+    X = api.get_R(1)
+    assert abs(ls.RI.itr - ls_o.RI.itr) <= 1, (ls.RI.itr, ls_o.RI.itr)
+    assert np.linalg.norm(X - Ro) / np.linalg.norm(Ro) <= TOL_SOL
+    # restore the fluid lhs for any later test in this module
+    api.FSILS_LHS_FREE()
+    api.FSILS_LHS_CREATE(m.nNo, p.rm.nNo, p.colPtr.size, p.rm.ltg, p.rowPtr, p.colPtr, 3)
+    for fi, name in enumerate(cm.FACE_ORDER, start=1):
+        fa = p.faces[name]
+        api.FSILS_BC_CREATE(fi, fa["gN"].size, 3,
+                            api.BC_TYPE_Neu if fa["bc"] == "Neu" else api.BC_TYPE_Dir, fa["gN"],
+                            fa["val"])
+    api.mesh_create(p.rm.IEN, p.rm.x)

@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- fluid Newton-iterations/s (assembly + GMRES) on the synthetic 10M-tet pipe.
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port on host cores
+    (N > 1: launched by torch.distributed.run, one rank per GPU; strong scaling, the 10M-tet mesh
+     is split into N axial slabs)
+
+One "step" = one Newton iteration of the reference's hot path (S/MAIN.f:133-198): LSALLOC zeroing,
+CONSTRUCT_FLUID element loop + block-CSR scatter, COMMU(R) halo sum, FSILS_SOLVE (Jacobi scaling +
+restarted GMRES).  `value` times it with the state already resident in HBM; `e2e` times the same
+step through the C-ABI with HOST buffers (Ag, Yg uploaded from pinned memory, the increment
+downloaded) inside the timed region.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# workload: BASELINE.json configs[2] / SURVEY.md 8d "C3 10M": 64 x 64 x 408 Kuhn lattice
+DIMS = (64, 64, 408)
+R_PIPE, L_PIPE = 2.0, 30.0
+RHO, MU, DT = 1.06, 0.04, 5e-3
+RHO_INF = 0.2
+F_BODY = (0.0, 0.0, 0.0)
+# FSILS GMRES + diagonal (FSILS) preconditioner; svFSI-Tests-like pipe settings
+LS = dict(relTol=1e-3, absTol=1e-12, maxItr=10, dimKry=50)
+RES_OUT = 0.0  # outlet resistance gamma*dt*r; 0 = plain Neumann outlet
+
+
+def gen_alpha(rho_inf):
+    am = 0.5 * (3.0 - rho_inf) / (1.0 + rho_inf)
+    af = 1.0 / (1.0 + rho_inf)
+    return dict(am=am, af=af, gam=0.5 + am - af)
+
+
+GA = gen_alpha(RHO_INF)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=mx,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def setup_rank(api, mesh, dims, rank, nparts):
+    gnNo, p = mesh.build_rank_problem(*dims, rank=rank, nparts=nparts, R=R_PIPE, L=L_PIPE)
+    api.FSILS_LHS_CREATE(gnNo, p.rm.nNo, p.colPtr.size, p.rm.ltg, p.rowPtr, p.colPtr, 3)
+    for fi, name in enumerate(("inlet", "wall", "outlet"), start=1):
+        fa = p.faces[name]
+        api.FSILS_BC_CREATE(fi, fa["gN"].size, 3,
+                            api.BC_TYPE_Neu if fa["bc"] == "Neu" else api.BC_TYPE_Dir, fa["gN"],
+                            fa["val"])
+    api.mesh_create(p.rm.IEN, p.rm.x)
+    return gnNo, p
+
+
+def newton_step_dev(api, variant):
+    """device-resident Newton iteration: R=0, Val=0, element loop, COMMU(R), FSILS_SOLVE"""
+    api.construct_fluid_dev(RHO, MU, F_BODY, DT, GA["af"], GA["am"], GA["gam"], variant)
+    api.commu_dev(4)
+    ls = api.FSILS_LS_CREATE(api.LS_TYPE_GMRES, **LS)
+    api.solve_dev(ls, 4, incL=[1, 1, 1], res=[0.0, 0.0, RES_OUT])
+    return ls
+
+
+def newton_step_e2e(api, variant, Ag, Yg, Rout):
+    """same step through the reference-facing calls with HOST buffers"""
+    api.CONSTRUCT_FLUID(Ag, Yg, None, RHO, MU, F_BODY, DT, GA["af"], GA["am"], GA["gam"], variant)
+    api.commu_dev(4)
+    ls = api.FSILS_LS_CREATE(api.LS_TYPE_GMRES, **LS)
+    api.solve_dev(ls, 4, incL=[1, 1, 1], res=[0.0, 0.0, RES_OUT])
+    import ctypes as C
+    api._check(api.lib().gpu_get_r_(api._ci(4), api._d(Rout)))
+    return ls
+
+
+def cpu_newton_sample(nz_sample, threads_note="1 (scalar port, single simulated rank)"):
+    """Oracle port (-O3 -march=native, the reference's own flags) on a slice of the same pipe:
+    one Newton iteration (assembly incl. the reference's per-element overheads + COMMU + GMRES
+    with the bench's solver settings), scaled to the full mesh by element count."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle import oracle as ora
+    from svfsi_b200 import mesh
+    ora.build(native=True, force=True)      # -march=native must be compiled on THIS host
+    dims = (DIMS[0], DIMS[1], nz_sample)
+    Ls = L_PIPE * nz_sample / DIMS[2]
+    gnNo, p = mesh.build_rank_problem(*dims, rank=0, nparts=1, R=R_PIPE, L=Ls)
+    par = ora.fluid_par(RHO, MU, F_BODY, DT, GA["af"], GA["am"], GA["gam"])
+    w = ora.World(gnNo, [p.rm.ltg], [p.rowPtr], [p.colPtr], 3, native=True)
+    for fi, name in enumerate(("inlet", "wall", "outlet"), start=1):
+        fa = p.faces[name]
+        w.bc_create(fi, [fa["gN"]], 3, ora.BC_TYPE_Neu if fa["bc"] == "Neu" else ora.BC_TYPE_Dir,
+                    None if fa["val"] is None else [fa["val"]])
+    t0 = time.perf_counter()
+    Rr, Vr = ora.construct_fluid(par, p.rm.IEN, p.rm.x, p.Ag, p.Yg, np.zeros((p.rm.nNo, 3)),
+                                 p.rowPtr, p.colPtr, faithful=True, native=True)
+    t_asm = time.perf_counter() - t0
+    ls = ora.ls_create(ora.LS_TYPE_GMRES, **LS)
+    t1 = time.perf_counter()
+    w.solve(ls, 4, [Rr], [Vr], incL=[1, 1, 1], res=[0.0, 0.0, RES_OUT])
+    t_sol = time.perf_counter() - t1
+    nEl_full = 6 * DIMS[0] * DIMS[1] * DIMS[2]
+    scale = nEl_full / p.rm.nEl
+    return dict(t_asm=t_asm, t_sol=t_sol, nEl=p.rm.nEl, itr=ls.RI.itr, scale=scale,
+                t_full=(t_asm + t_sol) * scale, threads=threads_note)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--nz", type=int, default=DIMS[2], help="axial cells (default = 10M-tet workload)")
+    ap.add_argument("--variant", default="atomic", choices=["atomic", "colored"])
+    ap.add_argument("--cpu-nz", type=int, default=24, help="axial cells of the CPU-baseline slice")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dims = (DIMS[0], DIMS[1], args.nz)
+    nEl_total = 6 * dims[0] * dims[1] * dims[2]
+    workload = (f"synthetic {nEl_total / 1e6:.2f}M-tet cylinder {dims[0]}x{dims[1]}x{dims[2]} Kuhn lattice, "
+                f"unsteady VMS Navier-Stokes, FSILS GMRES(sD={LS['dimKry']}, relTol={LS['relTol']}, "
+                f"mItr={LS['maxItr']}) + diagonal preconditioner")
+    config = dict(workload=workload, partition=f"{max(world, 1)} axial slabs",
+                  l2="inputs larger than L2 (Val = 128 B x nnz >> 126 MB)", assembly=args.variant,
+                  dt=DT, rho=RHO, mu=MU)
+    metric, unit = "fluid_newton_iters_per_sec", "Newton-iter/s"
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        times = []
+        for _ in range(args.warmup + args.steps):
+            times.append(cpu_newton_sample(args.cpu_nz))
+        times = times[args.warmup:] if len(times) > args.warmup else times
+        t_full = float(np.mean([t["t_full"] for t in times]))
+        s = times[-1]
+        sample = (f"one Newton iteration (faithful CONSTRUCT_FLUID + FSILS GMRES, same settings) on a "
+                  f"{dims[0]}x{dims[1]}x{args.cpu_nz} slice ({s['nEl']} tets, {s['itr']} SpMVs), time scaled by "
+                  f"nEl ratio {s['scale']:.1f}")
+        val = 1.0 / t_full
+        out = dict(metric=metric, value=val, unit=unit, n_gpus=args.gpus, steps=args.steps,
+                   warmup=args.warmup, ms_per_step=t_full * 1e3, higher_is_better=True,
+                   scaling="strong", vs_baseline=None, dtype="f64", data="synthetic", config=config,
+                   impl="reference",
+                   cpu_baseline=dict(value=val, unit=unit, cores=1, kind="port", sample=sample),
+                   e2e=dict(value=val, unit=unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(out))
+        return 0
+
+    # ------------------------------------------------------------------ native arm (CUDA)
+    import torch
+    from svfsi_b200 import api, mesh
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the native arm has no CPU fallback")
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        api.init_distributed(device=local)
+    else:
+        dist = None
+        api.init(device=0, rank=0, nranks=1)
+    variant = api.ASM_ATOMIC if args.variant == "atomic" else api.ASM_COLORED
+    t_setup = time.perf_counter()
+    gnNo, p = setup_rank(api, mesh, dims, rank, world)
+    api.state_upload(4, p.Ag, p.Yg, None)
+    api.sync()
+    t_setup = time.perf_counter() - t_setup
+    nNo, nnz, nEl = p.rm.nNo, p.colPtr.size, p.rm.nEl
+
+    stream = torch.cuda.ExternalStream(api.stream_ptr(), device=torch.device("cuda", local))
+
+    def barrier():
+        api.sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    def timed(fn, steps):
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        last = None
+        for _ in range(steps):
+            last = fn()
+        e1.record(stream)
+        api.sync(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms, last
+
+    # device-resident leg
+    for _ in range(args.warmup):
+        ls = newton_step_dev(api, variant)
+    l0 = api.launch_count()
+    api.prof_reset(); api.prof_enable(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev, ls = timed(lambda: newton_step_dev(api, variant), args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    prof = api.prof_get()
+    api.prof_enable(False)
+    launches = api.launch_count() - l0
+
+    # e2e leg: host buffers (pinned), H2D + D2H inside the timed region
+    Ag_h = torch.from_numpy(p.Ag).pin_memory().numpy()
+    Yg_h = torch.from_numpy(p.Yg).pin_memory().numpy()
+    R_h = torch.empty((nNo, 4), dtype=torch.float64).pin_memory().numpy()
+    for _ in range(max(1, args.warmup - 1)):
+        newton_step_e2e(api, variant, Ag_h, Yg_h, R_h)
+    ms_e2e, ls2 = timed(lambda: newton_step_e2e(api, variant, Ag_h, Yg_h, R_h), args.steps)
+
+    # SpMV roofline: event pairs around every SPARMULVV kernel of the timed region
+    spmv_ms, spmv_n = prof["spmv"]
+    alg_bytes = nnz * (128 + 4) + nNo * (8 + 32 + 32)           # SURVEY.md 8d, per launch, this rank
+    peak, peak_src = measured_peak()
+    achieved = alg_bytes / (spmv_ms / max(spmv_n, 1) * 1e-3) / 1e9 if spmv_n else None
+    asm_ms, asm_n = prof["asm"]
+    melem = (nEl * world) / (asm_ms / max(asm_n, 1) * 1e-3) / 1e6 if asm_n else None
+    scatter_bytes = nEl * (16 + 4 * 14 * 8 + 2048 + 128)        # element-scatter model, SURVEY.md 8d
+
+    if rank == 0:
+        per = ms_dev / args.steps
+        out = dict(metric=metric, value=1e3 / per, unit=unit, n_gpus=world, steps=args.steps,
+                   warmup=args.warmup, ms_per_step=per, higher_is_better=True, scaling="strong",
+                   vs_baseline=None, dtype="f64", data="synthetic", config=config, clocks=clocks,
+                   e2e=dict(value=1e3 / (ms_e2e / args.steps), unit=unit,
+                            h2d_bytes_per_step=int(Ag_h.nbytes + Yg_h.nbytes),
+                            d2h_bytes_per_step=int(R_h.nbytes), ms_per_step=ms_e2e / args.steps),
+                   gpu_launches=int(launches),
+                   roofline=dict(bound="hbm", kernel="spmv_vv4_kernel (FSILS_SPARMULVV dof=4)",
+                                 achieved=achieved, peak=peak, unit="GB/s",
+                                 frac=(achieved / peak) if achieved else None, peak_source=peak_src,
+                                 traffic=None, algorithmic_bytes_per_launch=int(alg_bytes),
+                                 avg_launch_ms=spmv_ms / max(spmv_n, 1), launches=int(spmv_n)),
+                   detail=dict(nEl_rank0=int(nEl), nNo_rank0=int(nNo), nnz_rank0=int(nnz),
+                               gmres_spmv_count=int(ls.RI.itr), gmres_suc=int(ls.RI.suc),
+                               iNorm=ls.RI.iNorm, fNorm=ls.RI.fNorm,
+                               assembly_Melem_per_s=melem,
+                               assembly_scatter_GBps=(scatter_bytes / (asm_ms / max(asm_n, 1) * 1e-3) / 1e9
+                                                      if asm_n else None),
+                               phase_ms_per_step={k: v[0] / args.steps for k, v in prof.items()},
+                               setup_s=t_setup))
+        if world == 1 and not args.no_cpu:
+            c = cpu_newton_sample(args.cpu_nz)
+            out["cpu_baseline"] = dict(
+                value=1.0 / c["t_full"], unit=unit, cores=1, kind="port",
+                sample=(f"oracle port (-O3 -march=native), one Newton iteration on a {dims[0]}x{dims[1]}x"
+                        f"{args.cpu_nz} slice ({c['nEl']} tets; assembly {c['t_asm']:.2f}s, GMRES "
+                        f"{c['t_sol']:.2f}s / {c['itr']} SpMVs) scaled by nEl ratio {c['scale']:.1f}"))
+        else:
+            out["cpu_baseline"] = None
+        print(json.dumps(out))
+    api.finalize()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -312,3 +312,68 @@ def build_problem(nx, ny, nz, nparts=1, R=2.0, L=30.0, umax=10.0, pert=0.01, acc
         out.append(RankProblem(rm, rowPtr, colPtr, scatter_nodal(rm, Ag), scatter_nodal(rm, Yg),
                                faces))
     return m, out, (Ag, Yg)
+
+
+# ----------------------------------------------------------------------------------------------
+def _hash_noise(gid: np.ndarray, salt: int) -> np.ndarray:
+    """Deterministic uniform(-1,1) noise keyed by GLOBAL node id, so that every rank generating
+    its own slab gives a shared node the same state (DISTRIBUTE.f:221-231 semantics)."""
+    with np.errstate(over="ignore"):
+        return _hash_noise_impl(gid, (salt * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF)
+
+
+def _hash_noise_impl(gid, salt64):
+    v = gid.astype(np.uint64) + np.uint64(salt64)
+    v ^= v >> np.uint64(30); v *= np.uint64(0xBF58476D1CE4E5B9)
+    v ^= v >> np.uint64(27); v *= np.uint64(0x94D049BB133111EB)
+    v ^= v >> np.uint64(31)
+    return (v >> np.uint64(11)).astype(np.float64) / float(1 << 53) * 2.0 - 1.0
+
+
+def build_rank_problem(nx, ny, nz, rank=0, nparts=1, R=2.0, L=30.0, umax=10.0, pert=0.01):
+    """One rank's share of the (nx, ny, nz) pipe WITHOUT building the global mesh: axial slab
+    `rank` of `nparts` (same split as partition_slabs), first-touch local numbering, global ids
+    identical to make_cylinder's.  Used by bench.py at the 10M-tet size, one call per GPU rank."""
+    bounds = np.linspace(0, nz, nparts + 1).round().astype(np.int64)
+    k0, k1 = int(bounds[rank]), int(bounds[rank + 1])
+    dz = L / nz
+    sl = make_cylinder(nx, ny, k1 - k0, R=R, L=(k1 - k0) * dz)
+    sl.x[:, 2] += k0 * dz
+    idx = np.arange(sl.nNo)
+    nzl = k1 - k0
+    k = idx % (nzl + 1)
+    ij = idx // (nzl + 1)
+    gid = (ij * (nz + 1) + k + k0 + 1).astype(np.int64)          # 1-based global node ids
+    # first-touch local numbering over the slab's elements (DISTRIBUTE.f:1455-1467)
+    order, inv = first_touch_unique(sl.IEN.astype(np.int64).ravel() - 1)
+    ien_l = (inv.reshape(-1, 4) + 1).astype(np.int32)
+    ltg = gid[order].astype(np.int32)
+    x = np.ascontiguousarray(sl.x[order])
+    old2new = np.empty(sl.nNo, dtype=np.int64)
+    old2new[order] = np.arange(1, sl.nNo + 1)
+    rm = RankMesh(rank=rank, ltg=ltg, IEN=ien_l, x=x, elems=np.zeros(0, dtype=np.int64))
+    rowPtr, colPtr = csr_pattern(rm.nNo, rm.IEN)
+    faces = {}
+    for name in ("inlet", "wall", "outlet"):
+        fa = sl.faces[name]
+        present = (name == "wall") or (name == "inlet" and k0 == 0) or (name == "outlet" and k1 == nz)
+        if not present:
+            faces[name] = dict(gN=np.zeros(0, dtype=np.int32), val=None if name != "outlet" else np.zeros((0, 3)),
+                               bc="Neu" if name == "outlet" else "Dir")
+            continue
+        gN_old = fa.gN.astype(np.int64)
+        if name == "outlet":
+            val = face_normal_integrals(sl, fa, fa.gN)
+            faces[name] = dict(gN=old2new[gN_old - 1].astype(np.int32), val=val, bc="Neu")
+        else:
+            faces[name] = dict(gN=old2new[gN_old - 1].astype(np.int32), val=None, bc="Dir")
+    g = ltg.astype(np.int64)
+    r2 = (x[:, 0] ** 2 + x[:, 1] ** 2) / (R ** 2)
+    Yg = np.zeros((rm.nNo, 4))
+    Yg[:, 2] = umax * np.clip(1.0 - r2, 0.0, None)
+    for c in range(3):
+        Yg[:, c] += pert * umax * _hash_noise(g, c + 1)
+    Yg[:, 3] = -1.0 * (x[:, 2] - L)
+    Ag = np.zeros((rm.nNo, 4))
+    gnNo = (nx + 1) * (ny + 1) * (nz + 1)
+    return gnNo, RankProblem(rm, rowPtr, colPtr, Ag, Yg, faces)

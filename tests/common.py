@@ -58,3 +58,35 @@ def oracle_commu(w, probs, Rs, dof=4):
         t = np.zeros_like(R); t[mp] = R; tmp.append(t)
     w.commuv(dof, tmp)
     return [t[mp].copy() for t, mp in zip(tmp, maps)]
+
+
+def oracle_gmres_global(nparts, relTol, sD, mItr, res_out, dims=(8, 8, 20), L=4.0,
+                        ls_type=None, **lskw):
+    """Assemble + COMMU + FSILS_SOLVE with the oracle on `nparts` simulated ranks; returns
+    (ls, X_global) with X gathered by global node id."""
+    m, probs, _ = mesh.build_problem(*dims, nparts=nparts, L=L)
+    Rs, Vs = oracle_assemble(probs)
+    w = oracle_world(probs, m.nNo)
+    Rc = oracle_commu(w, probs, Rs)
+    ls = ora.ls_create(ls_type or ora.LS_TYPE_GMRES, relTol=relTol, absTol=1e-14, maxItr=mItr,
+                       dimKry=sD, **lskw)
+    X = [r.copy() for r in Rc]
+    w.solve(ls, 4, X, [v.copy() for v in Vs], incL=[1, 1, 1], res=np.array([0.0, 0.0, res_out]))
+    G = np.zeros((m.nNo, 4))
+    for p, x in zip(probs, X):
+        G[p.rm.ltg - 1] = x
+    return ls, G
+
+
+def reference_reproducibility_floor(relTol, sD, mItr, res_out, ls_type=None, **kw):
+    """How far the REFERENCE ALGORITHM moves when only its summation order changes: oracle on
+    2 and 3 simulated MPI ranks vs 1 rank (the reference's own partition-to-partition drift,
+    SURVEY.md Appendix F).  Returns (floor on ||dX||/||X||, floor on |d fNorm|/fNorm, max |d itr|)."""
+    ls1, G1 = oracle_gmres_global(1, relTol, sD, mItr, res_out, ls_type=ls_type, **kw)
+    fx = ff = 0.0; di = 0
+    for k in (2, 3):
+        lsk, Gk = oracle_gmres_global(k, relTol, sD, mItr, res_out, ls_type=ls_type, **kw)
+        fx = max(fx, float(np.linalg.norm(Gk - G1) / np.linalg.norm(G1)))
+        ff = max(ff, abs(lsk.RI.fNorm - ls1.RI.fNorm) / ls1.RI.fNorm)
+        di = max(di, abs(lsk.RI.itr - ls1.RI.itr))
+    return fx, ff, di

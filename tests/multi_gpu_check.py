@@ -1,0 +1,161 @@
+"""Multi-rank parity check, one process per GPU (run under torch.distributed.run):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tests/multi_gpu_check.py
+Every rank builds ITS partition of the synthetic pipe, goes through the C-ABI (NCCL halo sums and
+all-reduces inside) and compares with the oracle run on the same number of simulated MPI ranks
+(and with the 1-rank oracle for partition independence).  Exits non-zero on any failure."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import common as cm  # noqa: E402
+from oracle import oracle as ora  # noqa: E402
+from svfsi_b200 import api, mesh  # noqa: E402
+
+
+def main():
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    api.init_distributed(device=local)
+    dims, L = (8, 8, 24), 4.0
+    m, probs, _ = mesh.build_problem(*dims, nparts=world, L=L)
+    p = probs[rank]
+    fails = []
+
+    def check(name, ok, info=""):
+        if not ok:
+            fails.append(f"rank {rank}: {name} {info}")
+        if rank == 0:
+            print(("PASS " if ok else "FAIL ") + name, info, flush=True)
+
+    # ---- FSILS_LHS_CREATE: map / mynNo / halo schedule vs oracle world
+    api.FSILS_LHS_CREATE(m.nNo, p.rm.nNo, p.colPtr.size, p.rm.ltg, p.rowPtr, p.colPtr, 3)
+    w = cm.oracle_world(probs, m.nNo)
+    info = api.lhs_info()
+    oi = w.info(rank)
+    check("lhs mynNo/shnNo/nReq", (info["mynNo"], info["shnNo"], info["nReq"]) ==
+          (oi["mynNo"], oi["shnNo"], oi["nReq"]))
+    check("lhs map", np.array_equal(info["map"], w.map(rank)))
+    ocs = w.cs(rank)
+    check("lhs cS", len(ocs) == len(info["cS"]) and all(
+        a[0] == b[0] and np.array_equal(a[1], b[1]) for a, b in zip(info["cS"], ocs)))
+    for fi, name in enumerate(cm.FACE_ORDER, start=1):
+        fa = p.faces[name]
+        api.FSILS_BC_CREATE(fi, fa["gN"].size, 3,
+                            api.BC_TYPE_Neu if fa["bc"] == "Neu" else api.BC_TYPE_Dir, fa["gN"],
+                            fa["val"])
+    api.mesh_create(p.rm.IEN, p.rm.x)
+
+    # ---- COMMU(R) on a host vector
+    rng = np.random.default_rng(100 + rank)
+    Rl = [np.random.default_rng(100 + r).standard_normal((probs[r].rm.nNo, 4)) for r in range(world)]
+    ref = cm.oracle_commu(w, probs, [r.copy() for r in Rl])
+    mine = Rl[rank].copy()
+    api.FSILS_COMMUV(4, mine)
+    check("COMMU(R)", cm.rel_err(mine, ref[rank]) <= 1e-15, f"{cm.rel_err(mine, ref[rank]):.2e}")
+
+    # ---- SPARMULVV incl. halo sum
+    Ks = [np.random.default_rng(200 + r).standard_normal((probs[r].colPtr.size, 16)) for r in range(world)]
+    Us = [np.random.default_rng(300).standard_normal((m.nNo, 4))[probs[r].rm.ltg - 1] for r in range(world)]
+    maps = [w.map(r).astype(np.int64) - 1 for r in range(world)]
+    Uf = []
+    for r in range(world):
+        t = np.zeros_like(Us[r]); t[maps[r]] = Us[r]; Uf.append(t)
+    # oracle sparmul works in FSILS order with Val in svFSI position order
+    KU = w.sparmul_vv(4, Ks, Uf)
+    got = api.FSILS_SPARMUL("VV", 4, Ks[rank], Us[rank])
+    check("SPARMULVV+halo", cm.rel_err(got, KU[rank][maps[rank]]) <= 1e-14)
+
+    # ---- DOTV over owned nodes + allreduce
+    Vs = [np.random.default_rng(301).standard_normal((m.nNo, 4))[probs[r].rm.ltg - 1] for r in range(world)]
+    dref = float((np.random.default_rng(300).standard_normal((m.nNo, 4)) *
+                  np.random.default_rng(301).standard_normal((m.nNo, 4))).sum())
+    d = api.FSILS_DOTV(4, Us[rank], Vs[rank])
+    check("DOTV", abs(d - dref) <= 1e-12 * abs(dref), f"{d} {dref}")
+
+    # ---- Newton iteration: assembly -> COMMU(R) -> FSILS_SOLVE(GMRES)
+    Rs, Vals = cm.oracle_assemble(probs)
+    for relTol, sD, mItr, res_out in [(1e-3, 100, 10, 0.0), (1e-6, 100, 10, 0.0), (1e-4, 20, 40, 0.0),
+                                      (1e-4, 100, 10, 5.0)]:
+        api.CONSTRUCT_FLUID(p.Ag, p.Yg, None, cm.RHO, cm.MU, cm.F, cm.DT, cm.GA["af"], cm.GA["am"],
+                            cm.GA["gam"], api.ASM_COLORED)
+        R = api.get_R(4); V = api.get_Val(4)
+        check("assembly R", cm.rel_err(R, Rs[rank]) <= 1e-12)
+        check("assembly Val", max(cm.block_class_errs(V, Vals[rank]).values()) <= 1e-12)
+        api.commu_dev(4)
+        ls = api.FSILS_LS_CREATE(api.LS_TYPE_GMRES, relTol=relTol, absTol=1e-14, maxItr=mItr, dimKry=sD)
+        res = [0.0, 0.0, res_out]
+        api.solve_dev(ls, 4, incL=[1, 1, 1], res=res)
+        X = api.get_R(4)
+        ls_o, G = cm.oracle_gmres_global(world, relTol, sD, mItr, res_out, dims=dims, L=L)
+        ls_1, G1 = cm.oracle_gmres_global(1, relTol, sD, mItr, res_out, dims=dims, L=L)
+        floor = float(np.linalg.norm(G - G1) / np.linalg.norm(G1))
+        Xref = G[p.rm.ltg - 1]
+        # global error over all ranks
+        num = torch.tensor([float(((X - Xref) ** 2)[: info["mynNo"]].sum()) if False else
+                            float(((X - Xref) ** 2).sum()), float((Xref ** 2).sum())],
+                           dtype=torch.float64, device="cuda")
+        dist.all_reduce(num)
+        err = float(torch.sqrt(num[0] / num[1]))
+        tag = f"GMRES relTol={relTol} sD={sD} res={res_out}"
+        check(tag + " itr", abs(ls.RI.itr - ls_o.RI.itr) <= 1, f"{ls.RI.itr} vs {ls_o.RI.itr} (1-rank {ls_1.RI.itr})")
+        check(tag + " iNorm", abs(ls.RI.iNorm - ls_o.RI.iNorm) <= 1e-10 * ls_o.RI.iNorm)
+        if ls.RI.itr == ls_o.RI.itr:
+            check(tag + " step", err <= max(1e-8, 2 * floor), f"err={err:.2e} ref-floor={floor:.2e}")
+
+    # ---- heat / CG (dof = 1)
+    api.FSILS_LHS_FREE()
+    api.FSILS_LHS_CREATE(m.nNo, p.rm.nNo, p.colPtr.size, p.rm.ltg, p.rowPtr, p.colPtr, 2)
+    wh = ora.World(m.nNo, [q.rm.ltg for q in probs], [q.rowPtr for q in probs],
+                   [q.colPtr for q in probs], 2)
+    for fi, name in enumerate(("inlet", "outlet"), start=1):
+        wh.bc_create(fi, [q.faces[name]["gN"] for q in probs], 1, ora.BC_TYPE_Dir, None)
+        api.FSILS_BC_CREATE(fi, p.faces[name]["gN"].size, 1, api.BC_TYPE_Dir, p.faces[name]["gN"])
+    api.mesh_create(p.rm.IEN, p.rm.x)
+    Tg = np.random.default_rng(7).uniform(0, 1, m.nNo); Ad = np.random.default_rng(8).uniform(-1, 1, m.nNo)
+    par = ora.heat_par(1.0, 0.0, 1.0, cm.DT, cm.GA["af"], cm.GA["am"], cm.GA["gam"])
+    Rh, Vh = [], []
+    for q in probs:
+        g = q.rm.ltg - 1
+        r_, v_ = ora.construct_heats(par, q.rm.IEN, q.rm.x, Ad[g], Tg[g], q.rowPtr, q.colPtr)
+        Rh.append(r_); Vh.append(v_)
+    Rhc = cm.oracle_commu(wh, probs, [r.reshape(-1, 1) for r in Rh], dof=1)
+    Rhc = [r.reshape(-1).copy() for r in Rhc]
+    ls_o = ora.ls_create(ora.LS_TYPE_CG, relTol=1e-8, absTol=1e-14, maxItr=500)
+    wh.solve(ls_o, 1, Rhc, [v.copy() for v in Vh], incL=[1, 1], res=None)
+    g = p.rm.ltg - 1
+    api.CONSTRUCT_HEATS(Ad[g], Tg[g], 1.0, 0.0, 1.0, cm.DT, cm.GA["af"], cm.GA["am"], cm.GA["gam"],
+                        api.ASM_ATOMIC)
+    check("heat assembly", cm.rel_err(api.get_Val(1), Vh[rank]) <= 1e-12)
+    api.commu_dev(1)
+    ls = api.FSILS_LS_CREATE(api.LS_TYPE_CG, relTol=1e-8, absTol=1e-14, maxItr=500)
+    api.solve_dev(ls, 1, incL=[1, 1])
+    X = api.get_R(1)
+    e = np.linalg.norm(X - Rhc[rank]) / np.linalg.norm(Rhc[rank])
+    check("heat CG itr", abs(ls.RI.itr - ls_o.RI.itr) <= 1, f"{ls.RI.itr} vs {ls_o.RI.itr}")
+    check("heat CG solution", e <= 1e-8, f"{e:.2e}")
+
+    nf = torch.tensor([len(fails)], device="cuda")
+    dist.all_reduce(nf)
+    for f in fails:
+        print(f, flush=True)
+    api.finalize()
+    dist.destroy_process_group()
+    if int(nf.item()):
+        print(f"MULTI-GPU CHECK FAILED ({int(nf.item())} failures)")
+        sys.exit(1)
+    if rank == 0:
+        print("MULTI-GPU CHECK OK")
+
+
+if __name__ == "__main__":
+    main()

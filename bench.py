@@ -170,7 +170,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--nz", type=int, default=DIMS[2], help="axial cells (default = 10M-tet workload)")
-    ap.add_argument("--variant", default="atomic", choices=["atomic", "colored"])
+    ap.add_argument("--variant", default="gather", choices=["atomic", "colored", "gather"])
     ap.add_argument("--cpu-nz", type=int, default=24, help="axial cells of the CPU-baseline slice")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
@@ -224,7 +224,7 @@ def main():
     else:
         dist = None
         api.init(device=0, rank=0, nranks=1)
-    variant = api.ASM_ATOMIC if args.variant == "atomic" else api.ASM_COLORED
+    variant = dict(atomic=api.ASM_ATOMIC, colored=api.ASM_COLORED, gather=api.ASM_GATHER)[args.variant]
     t_setup = time.perf_counter()
     gnNo, p = setup_rank(api, mesh, dims, rank, world)
     api.state_upload(4, p.Ag, p.Yg, None)

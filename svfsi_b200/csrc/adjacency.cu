@@ -1,0 +1,98 @@
+// adjacency.cu -- setup-time construction (on the device) of the lists the gather assembly
+// walks: for every Val block the (element, a, b) triples that contribute to it, for every node
+// the (element, a) pairs, both in ascending element order (the reference's accumulation order,
+// S/LHSA.f:275-295 inside the element loop S/FLUID.f:74-182), plus a block processing order that
+// groups blocks of similar list length into the same warp (diagonal blocks collect ~24
+// elements, off-diagonal ones 4-6).
+#include <cuda_runtime.h>
+#include <thrust/execution_policy.h>
+#include <thrust/scan.h>
+
+#include "ctx.h"
+#include "kernels.h"
+
+namespace svfsi {
+
+__global__ void count_kernel(size_t n, const int *__restrict__ key, int *__restrict__ cnt) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) atomicAdd(cnt + key[t], 1);
+}
+// payload = (t >> shift) << shift_keep | (t & mask): for blocks t = e*16 + blk -> e<<4|blk = t
+__global__ void fill_kernel(size_t n, const int *__restrict__ key, const int *__restrict__ ptr,
+                            int *__restrict__ cursor, int *__restrict__ out) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int k = key[t];
+  const int pos = atomicAdd(cursor + k, 1);
+  out[ptr[k] + pos] = (int)t;
+}
+// ascending sort of every (short) segment: one thread per segment, insertion sort
+__global__ void segsort_kernel(int nseg, const int *__restrict__ ptr, int *__restrict__ v) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nseg) return;
+  const int a = ptr[s], b = ptr[s + 1];
+  for (int i = a + 1; i < b; i++) {
+    const int x = v[i];
+    int j = i - 1;
+    while (j >= a && v[j] > x) { v[j + 1] = v[j]; j--; }
+    v[j + 1] = x;
+  }
+}
+// within chunks of CH consecutive blocks, order by descending list length (stable)
+template <int CH>
+__global__ void __launch_bounds__(CH) order_kernel(int n, const int *__restrict__ ptr,
+                                                   int *__restrict__ order) {
+  __shared__ int len[CH];
+  const int base = blockIdx.x * CH, t = threadIdx.x, me = base + t;
+  len[t] = (me < n) ? ptr[me + 1] - ptr[me] : -1;
+  __syncthreads();
+  if (me >= n) return;
+  int rank = 0;
+  const int mine = len[t];
+  for (int u = 0; u < CH; u++) {
+    const int l = len[u];
+    rank += (l > mine) || (l == mine && u < t);
+  }
+  order[base + rank] = me;
+}
+
+static int build_lists(cudaStream_t st, size_t nItems, const int *key, int nseg, int **ptrOut,
+                       int **listOut) {
+  int *cnt = nullptr, *ptr = nullptr, *list = nullptr;
+  CUDA_TRY(cudaMalloc(&cnt, sizeof(int) * ((size_t)nseg + 1)));
+  CUDA_TRY(cudaMalloc(&ptr, sizeof(int) * ((size_t)nseg + 1)));
+  CUDA_TRY(cudaMalloc(&list, sizeof(int) * (nItems ? nItems : 1)));
+  CUDA_TRY(cudaMemsetAsync(cnt, 0, sizeof(int) * ((size_t)nseg + 1), st));
+  const unsigned blocks = (unsigned)((nItems + 255) / 256);
+  count_kernel<<<blocks, 256, 0, st>>>(nItems, key, cnt);
+  thrust::exclusive_scan(thrust::cuda::par.on(st), cnt, cnt + nseg + 1, ptr);
+  CUDA_TRY(cudaMemsetAsync(cnt, 0, sizeof(int) * ((size_t)nseg + 1), st));
+  fill_kernel<<<blocks, 256, 0, st>>>(nItems, key, ptr, cnt, list);
+  segsort_kernel<<<(nseg + 255) / 256, 256, 0, st>>>(nseg, ptr, list);
+  count_launch(4);
+  CUDA_TRY(cudaStreamSynchronize(st));
+  cudaFree(cnt);
+  *ptrOut = ptr;
+  *listOut = list;
+  return 0;
+}
+
+int build_gather_adjacency(cudaStream_t st, int nEl, int nNo, int nnz, const int *ien,
+                           const int *edest, int **blkAdjPtr, int **blkAdj, int **nodeAdjPtr,
+                           int **nodeAdj, int **blkOrder) {
+  // item t = e*16 + (a*4+b) has key edest[t]; the stored payload t equals e<<4 | a<<2 | b
+  if (int rc = build_lists(st, (size_t)nEl * 16, edest, nnz, blkAdjPtr, blkAdj)) return rc;
+  // item t = e*4 + a has key ien[t]; payload t = e<<2 | a
+  if (int rc = build_lists(st, (size_t)nEl * 4, ien, nNo, nodeAdjPtr, nodeAdj)) return rc;
+  int *order = nullptr;
+  constexpr int CH = 512;
+  const int padded = ((nnz + CH - 1) / CH) * CH;
+  CUDA_TRY(cudaMalloc(&order, sizeof(int) * (size_t)padded));
+  order_kernel<CH><<<padded / CH, CH, 0, st>>>(nnz, *blkAdjPtr, order);
+  count_launch();
+  CUDA_TRY(cudaStreamSynchronize(st));
+  *blkOrder = order;
+  return 0;
+}
+
+}  // namespace svfsi

@@ -30,17 +30,18 @@ namespace svfsi {
 static constexpr int NE = 128;       // elements per CTA
 static constexpr int NEP = NE + 1;   // padded field stride in shared memory (bank spread)
 
-// field ids of the per-element compact record in shared memory
+// The per-element compact record: 64 doubles (512 B).
+//   node record a (8 doubles at a*8): Nx(1..3,a), C2_a, sum tauC, wl, sum tauM, R2_a
+//       C2_a = rho sum_g tauM uaNx_a ; R2_a = rho sum_g tauM (uNx_a + amd N_a)
+//       (the three element-wide scalars are replicated in every node record so that one
+//        64-byte node record holds everything a tangent block needs from that node)
+//   D(a,b) at 32 + a*4 + b : 4 mu Nx_a.Nx_b + A_ab  (diagonal term of the momentum tangent)
+//   lR(i,a) at 48 + a*4 + i
+// In shared memory (scatter variants) field f of slot s lives at f*NEP + s; in global memory
+// (gather variant) at e*64 + f.
 enum {
-  F_NX = 0,     // 12: Nx(i,a) at F_NX + a*3 + i
-  F_D = 12,     // 16: 4 mu NxNx_ab + A_ab at F_D + a*4 + b
-  F_C2 = 28,    // 4 : rho sum_g tauM uaNx_a
-  F_R2 = 32,    // 4 : rho sum_g tauM (uNx_b + amd N_b)
-  F_STC = 36,   // sum_g tauC
-  F_STM = 37,   // sum_g tauM
-  F_WL = 38,    // wl = w * af*gam*dt
-  F_LR = 39,    // 16: lR(i,a) at F_LR + a*4 + i
-  F_COUNT = 55
+  N_NX = 0, N_C2 = 3, N_STC = 4, N_WL = 5, N_STM = 6, N_R2 = 7,
+  F_D = 32, F_LR = 48, F_COUNT = 64
 };
 
 // S/UTIL.f:879-903 ISZERO(x) with one argument
@@ -111,30 +112,15 @@ __device__ __forceinline__ void gnn_tet4(const double xl[4][3], double Nx[4][3],
 __device__ __forceinline__ void red_add(double *p, double v) { atomicAdd(p, v); }
 
 // ---------------------------------------------------------------------------
-template <bool ATOMIC>
-__global__ void __launch_bounds__(NE) fluid_asm_kernel(FluidPar par, int n, int e0,
-                                                       const int *__restrict__ elems,
-                                                       const int *__restrict__ ien,
-                                                       const int *__restrict__ edest,
-                                                       const double *__restrict__ x,
-                                                       const double *__restrict__ Ag,
-                                                       const double *__restrict__ Yg,
-                                                       const double *__restrict__ Bf,
-                                                       double *__restrict__ R,
-                                                       double *__restrict__ Val,
-                                                       int *__restrict__ badJac) {
-  extern __shared__ double sm[];      // [F_COUNT][NEP]
-  __shared__ int sEl[NE];             // element id per slot (-1 = none)
-  __shared__ int sNode[NE * 4];
-
-  const int slot = threadIdx.x;
-  const int idx = blockIdx.x * NE + slot;
-  int e = -1;
-  if (idx < n) e = elems ? elems[e0 + idx] : e0 + idx;
-  sEl[slot] = e;
-
-  // ---------------- phase 1: one thread per element ----------------
-  if (e >= 0) {
+// Phase 1 for one element: gather, GNN, the four Gauss points reduced to the compact record.
+// rec[f * NEP] receives field f (the caller's shared-memory slot).
+__device__ __forceinline__ void fluid_elem_record(const FluidPar &par, int e,
+                                                  const int *__restrict__ ien,
+                                                  const double *__restrict__ x,
+                                                  const double *__restrict__ Ag,
+                                                  const double *__restrict__ Yg,
+                                                  const double *__restrict__ Bf, double *rec,
+                                                  int *nodeOut, int *__restrict__ badJac) {
     Tet4Tab tab;
     tet4_tab(tab);
     int nd[4];
@@ -145,7 +131,7 @@ __global__ void __launch_bounds__(NE) fluid_asm_kernel(FluidPar par, int n, int 
     double xl[4][3], al[4][3], yl[4][4];
 #pragma unroll
     for (int a = 0; a < 4; a++) {
-      sNode[slot * 4 + a] = nd[a];
+      nodeOut[a] = nd[a];
       const double *xp = x + (size_t)nd[a] * 3;
       xl[a][0] = __ldg(xp); xl[a][1] = __ldg(xp + 1); xl[a][2] = __ldg(xp + 2);
       const double2 *ap = (const double2 *)(Ag + (size_t)nd[a] * 4);
@@ -306,18 +292,20 @@ __global__ void __launch_bounds__(NE) fluid_asm_kernel(FluidPar par, int n, int 
     }
 
     // store the compact record
-    double *rec = sm + slot;
 #pragma unroll
     for (int a = 0; a < 4; a++) {
 #pragma unroll
-      for (int i = 0; i < 3; i++) rec[(F_NX + a * 3 + i) * NEP] = Nx[a][i];
+      for (int i = 0; i < 3; i++) rec[(a * 8 + N_NX + i) * NEP] = Nx[a][i];
+      rec[(a * 8 + N_C2) * NEP] = rho * c2[a];
+      rec[(a * 8 + N_STC) * NEP] = sTC;
+      rec[(a * 8 + N_WL) * NEP] = wl;
+      rec[(a * 8 + N_STM) * NEP] = sTM;
+      rec[(a * 8 + N_R2) * NEP] = rho * r2[a];
 #pragma unroll
       for (int b = 0; b < 4; b++) {
         const double nn = Nx[a][0] * Nx[b][0] + Nx[a][1] * Nx[b][1] + Nx[a][2] * Nx[b][2];
         rec[(F_D + a * 4 + b) * NEP] = 4.0 * (mu * nn) + A[a][b];
       }
-      rec[(F_C2 + a) * NEP] = rho * c2[a];
-      rec[(F_R2 + a) * NEP] = rho * r2[a];
 #pragma unroll
       for (int i = 0; i < 3; i++)
         rec[(F_LR + a * 4 + i) * NEP] =
@@ -325,10 +313,73 @@ __global__ void __launch_bounds__(NE) fluid_asm_kernel(FluidPar par, int n, int 
             w * (Nx[a][0] * sRM[0][i] + Nx[a][1] * sRM[1][i] + Nx[a][2] * sRM[2][i]);
       rec[(F_LR + a * 4 + 3) * NEP] = w * lR4[a];
     }
-    rec[F_STC * NEP] = sTC;
-    rec[F_STM * NEP] = sTM;
-    rec[F_WL * NEP] = wl;
+}
+
+// The pair of tangent entries (row i = q>>1, columns 2(q&1), 2(q&1)+1) of block (a,b) that lane q
+// of an 8-lane group owns, expanded from the compact record (field f at rec[f*stride]).
+// S/FLUID.f:482-557 (momentum rows) and :1052-1081 (continuity row), Gauss sums pre-reduced.
+template <int STRIDE>
+__device__ __forceinline__ void tangent_pair(const double *__restrict__ rec, int a, int b, int q,
+                                             double mu4, const double sN[4], double &v0,
+                                             double &v1) {
+  const int i = q >> 1, j0 = (q & 1) * 2;
+  const double *ra = rec + (size_t)(a * 8) * STRIDE, *rb = rec + (size_t)(b * 8) * STRIDE;
+  const double wl = ra[N_WL * STRIDE];
+  const double na_j0 = ra[(size_t)j0 * STRIDE], nb_j0 = rb[(size_t)j0 * STRIDE];
+  if (i < 3) {
+    const double nai = ra[(size_t)i * STRIDE], nbi = rb[(size_t)i * STRIDE];
+    const double sTC = ra[N_STC * STRIDE];
+    v0 = mu4 * (na_j0 * nbi) + sTC * (nai * nb_j0);
+    if (j0 == 0) {
+      const double na1 = ra[1 * STRIDE], nb1 = rb[1 * STRIDE];
+      v1 = mu4 * (na1 * nbi) + sTC * (nai * nb1);
+      if (i < 2) {
+        const double d = rec[(size_t)(F_D + a * 4 + b) * STRIDE];
+        if (i == 0) v0 += d; else v1 += d;
+      }
+      v0 *= wl;
+      v1 *= wl;
+    } else {
+      if (i == 2) v0 += rec[(size_t)(F_D + a * 4 + b) * STRIDE];
+      v0 *= wl;
+      v1 = -wl * (nai * sN[b] - nbi * ra[N_C2 * STRIDE]);   // pressure column, :547-557
+    }
+  } else {
+    const double sNa = sN[a], r2b = rb[N_R2 * STRIDE];
+    v0 = wl * (sNa * nb_j0 + na_j0 * r2b);
+    if (j0 == 0) {
+      v1 = wl * (sNa * rb[1 * STRIDE] + ra[1 * STRIDE] * r2b);
+    } else {
+      const double nn = ra[0] * rb[0] + ra[1 * STRIDE] * rb[1 * STRIDE] + na_j0 * nb_j0;
+      v1 = wl * (ra[N_STM * STRIDE] * nn);               // dC/dP, :1072-1081
+    }
   }
+}
+
+// ---------------------------------------------------------------------------
+// Scatter variants (atomic / coloured): phases 1 and 2 in one CTA through shared memory.
+template <bool ATOMIC>
+__global__ void __launch_bounds__(NE) fluid_asm_kernel(FluidPar par, int n, int e0,
+                                                       const int *__restrict__ elems,
+                                                       const int *__restrict__ ien,
+                                                       const int *__restrict__ edest,
+                                                       const double *__restrict__ x,
+                                                       const double *__restrict__ Ag,
+                                                       const double *__restrict__ Yg,
+                                                       const double *__restrict__ Bf,
+                                                       double *__restrict__ R,
+                                                       double *__restrict__ Val,
+                                                       int *__restrict__ badJac) {
+  extern __shared__ double sm[];      // [F_COUNT][NEP]
+  __shared__ int sEl[NE];             // element id per slot (-1 = none)
+  __shared__ int sNode[NE * 4];
+
+  const int slot = threadIdx.x;
+  const int idx = blockIdx.x * NE + slot;
+  int e = -1;
+  if (idx < n) e = elems ? elems[e0 + idx] : e0 + idx;
+  sEl[slot] = e;
+  if (e >= 0) fluid_elem_record(par, e, ien, x, Ag, Yg, Bf, sm + slot, sNode + slot * 4, badJac);
   __syncthreads();
 
   // ---------------- phase 2a: residual scatter, R(:,Ac) += lR(:,a) ----------------
@@ -350,50 +401,8 @@ __global__ void __launch_bounds__(NE) fluid_asm_kernel(FluidPar par, int n, int 
     const int el = sEl[s];
     if (el < 0) continue;
     const int blk = (it >> 3) & 15, q = it & 7;
-    const int a = blk >> 2, b = blk & 3;
-    const int i = q >> 1, j0 = (q & 1) * 2;
-    const double *rec = sm + s;
-    const double wl = rec[F_WL * NEP];
     double v0, v1;
-    if (i < 3) {
-      const double nai = rec[(F_NX + a * 3 + i) * NEP];
-      const double nbi = rec[(F_NX + b * 3 + i) * NEP];
-      if (j0 == 0) {
-        // columns 0,1
-        const double sTC = rec[F_STC * NEP];
-        const double na0 = rec[(F_NX + a * 3 + 0) * NEP], na1 = rec[(F_NX + a * 3 + 1) * NEP];
-        const double nb0 = rec[(F_NX + b * 3 + 0) * NEP], nb1 = rec[(F_NX + b * 3 + 1) * NEP];
-        v0 = mu4 * (na0 * nbi) + sTC * (nai * nb0);
-        v1 = mu4 * (na1 * nbi) + sTC * (nai * nb1);
-        const double d = rec[(F_D + a * 4 + b) * NEP];
-        if (i == 0) v0 += d;
-        if (i == 1) v1 += d;
-        v0 *= wl;
-        v1 *= wl;
-      } else {
-        // column 2 and the pressure column 3 (S/FLUID.f:547-557)
-        const double sTC = rec[F_STC * NEP];
-        const double na2 = rec[(F_NX + a * 3 + 2) * NEP], nb2 = rec[(F_NX + b * 3 + 2) * NEP];
-        v0 = mu4 * (na2 * nbi) + sTC * (nai * nb2);
-        if (i == 2) v0 += rec[(F_D + a * 4 + b) * NEP];
-        v0 *= wl;
-        v1 = -wl * (nai * tab2.sN[b] - nbi * rec[(F_C2 + a) * NEP]);
-      }
-    } else {
-      // continuity row (S/FLUID.f:1052-1081)
-      const double sNa = tab2.sN[a];
-      const double r2b = rec[(F_R2 + b) * NEP];
-      if (j0 == 0) {
-        v0 = wl * (sNa * rec[(F_NX + b * 3 + 0) * NEP] + rec[(F_NX + a * 3 + 0) * NEP] * r2b);
-        v1 = wl * (sNa * rec[(F_NX + b * 3 + 1) * NEP] + rec[(F_NX + a * 3 + 1) * NEP] * r2b);
-      } else {
-        v0 = wl * (sNa * rec[(F_NX + b * 3 + 2) * NEP] + rec[(F_NX + a * 3 + 2) * NEP] * r2b);
-        const double nn = rec[(F_NX + a * 3 + 0) * NEP] * rec[(F_NX + b * 3 + 0) * NEP] +
-                          rec[(F_NX + a * 3 + 1) * NEP] * rec[(F_NX + b * 3 + 1) * NEP] +
-                          rec[(F_NX + a * 3 + 2) * NEP] * rec[(F_NX + b * 3 + 2) * NEP];
-        v1 = wl * (rec[F_STM * NEP] * nn);
-      }
-    }
+    tangent_pair<NEP>(sm + s, blk >> 2, blk & 3, q, mu4, tab2.sN, v0, v1);
     const int p = __ldg(edest + (size_t)el * 16 + blk);
     double *dst = Val + (size_t)p * 16 + q * 2;
     if (ATOMIC) {
@@ -408,6 +417,91 @@ __global__ void __launch_bounds__(NE) fluid_asm_kernel(FluidPar par, int n, int 
   }
 }
 
+// ---------------------------------------------------------------------------
+// Gather variant ("owner computes", deterministic, no atomics, no colouring):
+//   kernel A: compact records of all elements -> elemP[e][64] (coalesced through smem)
+//   kernel B: 8 lanes per Val block sum the contributions of the elements around that
+//             (row,col) edge in ascending element order -- the reference's DOASSEM
+//             accumulation order (S/LHSA.f:275-295) -- and write the block ONCE.
+//   kernel C: same for the residual, one thread per (node, component).
+__global__ void __launch_bounds__(NE) fluid_record_kernel(FluidPar par, int n,
+                                                          const int *__restrict__ ien,
+                                                          const double *__restrict__ x,
+                                                          const double *__restrict__ Ag,
+                                                          const double *__restrict__ Yg,
+                                                          const double *__restrict__ Bf,
+                                                          double *__restrict__ elemP,
+                                                          int *__restrict__ badJac) {
+  extern __shared__ double sm[];  // [F_COUNT][NEP]
+  const int slot = threadIdx.x;
+  const int e = blockIdx.x * NE + slot;
+  int nodes[4];
+  if (e < n) fluid_elem_record(par, e, ien, x, Ag, Yg, Bf, sm + slot, nodes, badJac);
+  __syncthreads();
+  const int nHere = min(NE, n - blockIdx.x * NE);
+  double *out = elemP + (size_t)blockIdx.x * NE * F_COUNT;
+  for (int t = threadIdx.x; t < nHere * F_COUNT; t += NE) {
+    const int s = t >> 6, f = t & 63;
+    __stcs(out + t, sm[f * NEP + s]);
+  }
+}
+
+__global__ void __launch_bounds__(256) fluid_gather_val_kernel(int nnz, double mu4,
+                                                               const int *__restrict__ blkOrder,
+                                                               const int *__restrict__ adjPtr,
+                                                               const int *__restrict__ adj,
+                                                               const double *__restrict__ elemP,
+                                                               double *__restrict__ Val) {
+  const int lane = threadIdx.x & 31, q = lane & 7;
+  const unsigned gmask = 0xFFu << (lane & 24);
+  const int g = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 3);
+  if (g >= nnz) return;
+  Tet4Tab tab;
+  tet4_tab(tab);
+  const int p = blkOrder ? __ldg(blkOrder + g) : g;
+  const int s = __ldg(adjPtr + p), e = __ldg(adjPtr + p + 1);
+  double acc0 = 0.0, acc1 = 0.0;
+  for (int base = s; base < e; base += 8) {
+    const int mine = base + q;
+    const int cq = (mine < e) ? __ldg(adj + mine) : 0;
+    const int cnt = min(8, e - base);
+    for (int k = 0; k < cnt; k++) {
+      const int pk = __shfl_sync(gmask, cq, k, 8);
+      double v0, v1;
+      tangent_pair<1>(elemP + (size_t)(pk >> 4) * F_COUNT, (pk >> 2) & 3, pk & 3, q, mu4, tab.sN,
+                      v0, v1);
+      acc0 += v0;
+      acc1 += v1;
+    }
+  }
+  __stcs((double2 *)(Val + (size_t)p * 16) + q, make_double2(acc0, acc1));
+}
+
+__global__ void __launch_bounds__(256) fluid_gather_r_kernel(int nNo, const int *__restrict__ adjPtr,
+                                                             const int *__restrict__ adj,
+                                                             const double *__restrict__ elemP,
+                                                             double *__restrict__ R) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nNo * 4) return;
+  const int node = t >> 2, i = t & 3;
+  double acc = 0.0;
+  for (int k = __ldg(adjPtr + node); k < __ldg(adjPtr + node + 1); k++) {
+    const int pk = __ldg(adj + k);
+    acc += __ldg(elemP + (size_t)(pk >> 2) * F_COUNT + F_LR + (pk & 3) * 4 + i);
+  }
+  R[t] = acc;
+}
+
+static void fluid_attr_once() {
+  static bool attr = false;
+  if (attr) return;
+  const int smem = (int)((size_t)F_COUNT * NEP * sizeof(double));
+  cudaFuncSetAttribute(fluid_asm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(fluid_asm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(fluid_record_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  attr = true;
+}
+
 void launch_fluid_asm(cudaStream_t st, const FluidPar &par, int n, int e0, const int *elems,
                       const int *ien, const int *edest, const double *x, const double *Ag,
                       const double *Yg, const double *Bf, double *R, double *Val, int atomic,
@@ -415,14 +509,7 @@ void launch_fluid_asm(cudaStream_t st, const FluidPar &par, int n, int e0, const
   if (n <= 0) return;
   count_launch();
   const size_t smem = (size_t)F_COUNT * NEP * sizeof(double);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(fluid_asm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)smem);
-    cudaFuncSetAttribute(fluid_asm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)smem);
-    attr = true;
-  }
+  fluid_attr_once();
   const int blocks = (n + NE - 1) / NE;
   if (atomic)
     fluid_asm_kernel<true><<<blocks, NE, smem, st>>>(par, n, e0, elems, ien, edest, x, Ag, Yg, Bf,
@@ -430,6 +517,22 @@ void launch_fluid_asm(cudaStream_t st, const FluidPar &par, int n, int e0, const
   else
     fluid_asm_kernel<false><<<blocks, NE, smem, st>>>(par, n, e0, elems, ien, edest, x, Ag, Yg, Bf,
                                                       R, Val, badJac);
+}
+
+void launch_fluid_gather(cudaStream_t st, const FluidPar &par, int nEl, int nNo, int nnz,
+                         const int *ien, const double *x, const double *Ag, const double *Yg,
+                         const double *Bf, double *elemP, const int *blkOrder,
+                         const int *blkAdjPtr, const int *blkAdj, const int *nodeAdjPtr,
+                         const int *nodeAdj, double *R, double *Val, int *badJac) {
+  if (nEl <= 0) return;
+  count_launch(3);
+  const size_t smem = (size_t)F_COUNT * NEP * sizeof(double);
+  fluid_attr_once();
+  fluid_record_kernel<<<(nEl + NE - 1) / NE, NE, smem, st>>>(par, nEl, ien, x, Ag, Yg, Bf, elemP,
+                                                             badJac);
+  fluid_gather_val_kernel<<<(unsigned)(((size_t)nnz * 8 + 255) / 256), 256, 0, st>>>(
+      nnz, 4.0 * par.mu, blkOrder, blkAdjPtr, blkAdj, elemP, Val);
+  fluid_gather_r_kernel<<<(nNo * 4 + 255) / 256, 256, 0, st>>>(nNo, nodeAdjPtr, nodeAdj, elemP, R);
 }
 
 // ---------------------------------------------------------------------------

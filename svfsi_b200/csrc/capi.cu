@@ -97,9 +97,12 @@ int run_fluid_asm(const FluidPar &par, int variant) {
   Ctx &c = ctx();
   if (!c.mesh) return fail(SVFSI_ERR_STATE, "gpu_mesh_create_ has not been called");
   if (int rc = ensure_system(4)) return rc;
-  // LSALLOC: R = 0, Val = 0 (S/LS.f:44-51)
-  CUDA_TRY(cudaMemsetAsync(c.d_R, 0, sizeof(double) * (size_t)c.nNo * 4, c.stream));
-  CUDA_TRY(cudaMemsetAsync(c.d_Val, 0, sizeof(double) * (size_t)c.nnz * 16, c.stream));
+  // LSALLOC: R = 0, Val = 0 (S/LS.f:44-51); the gather variant writes every block and every
+  // residual entry exactly once (0 + contributions), so it needs no zero fill
+  if (variant != SVFSI_ASM_GATHER) {
+    CUDA_TRY(cudaMemsetAsync(c.d_R, 0, sizeof(double) * (size_t)c.nNo * 4, c.stream));
+    CUDA_TRY(cudaMemsetAsync(c.d_Val, 0, sizeof(double) * (size_t)c.nnz * 16, c.stream));
+  }
   CUDA_TRY(cudaMemsetAsync(c.d_flag, 0, sizeof(int), c.stream));
   const double *bf = g_haveBf ? c.d_Bf : nullptr;
   {
@@ -112,6 +115,11 @@ int run_fluid_asm(const FluidPar &par, int variant) {
         launch_fluid_asm(c.stream, par, c.colorOff[k + 1] - c.colorOff[k], c.colorOff[k],
                          c.d_colorElems, c.d_ien, c.d_edest, c.d_x, c.d_Ag, c.d_Yg, bf, c.d_R,
                          c.d_Val, 0, c.d_flag);
+    } else if (variant == SVFSI_ASM_GATHER) {
+      if (!c.d_elemP) CUDA_TRY(cudaMalloc(&c.d_elemP, sizeof(double) * 64 * (size_t)c.nEl));
+      launch_fluid_gather(c.stream, par, c.nEl, c.nNo, c.nnz, c.d_ien, c.d_x, c.d_Ag, c.d_Yg, bf,
+                          c.d_elemP, c.d_blkOrder, c.d_blkAdjPtr, c.d_blkAdj, c.d_nodeAdjPtr,
+                          c.d_nodeAdj, c.d_R, c.d_Val, c.d_flag);
     } else {
       return fail(SVFSI_ERR_ARG, "unknown assembly variant");
     }
@@ -207,6 +215,8 @@ int32_t gpu_lhs_free_(void) {
   dev_free(&c.d_vperm); dev_free(&c.d_rowOf); dev_free(&c.d_packIdx); dev_free(&c.d_uniqNode);
   dev_free(&c.d_uniqPtr); dev_free(&c.d_uniqSlot); dev_free(&c.d_sbuf); dev_free(&c.d_rbuf);
   dev_free(&c.d_ien); dev_free(&c.d_edest); dev_free(&c.d_x); dev_free(&c.d_colorElems);
+  dev_free(&c.d_blkAdjPtr); dev_free(&c.d_blkAdj); dev_free(&c.d_nodeAdjPtr);
+  dev_free(&c.d_nodeAdj); dev_free(&c.d_blkOrder); dev_free(&c.d_elemP);
   dev_free(&c.d_R); dev_free(&c.d_Val); dev_free(&c.d_Ag); dev_free(&c.d_Yg); dev_free(&c.d_Bf);
   c.lhs = false;
   c.mesh = false;
@@ -453,6 +463,12 @@ int32_t gpu_mesh_create_(const int32_t *nEl_, const int32_t *eNoN, const int32_t
   }
   c.ncolors = (int)c.colorOff.size() - 1;
   if (int rc = dev_upload(&c.d_colorElems, colorElems)) return rc;
+  dev_free(&c.d_blkAdjPtr); dev_free(&c.d_blkAdj); dev_free(&c.d_nodeAdjPtr);
+  dev_free(&c.d_nodeAdj); dev_free(&c.d_blkOrder); dev_free(&c.d_elemP);
+  if (int rc = build_gather_adjacency(c.stream, nEl, c.nNo, c.nnz, c.d_ien, c.d_edest,
+                                      &c.d_blkAdjPtr, &c.d_blkAdj, &c.d_nodeAdjPtr, &c.d_nodeAdj,
+                                      &c.d_blkOrder))
+    return rc;
   CUDA_TRY(cudaStreamSynchronize(c.stream));
   // every (a,b) of every element must exist in the pattern
   c.mesh = true;

@@ -98,7 +98,8 @@ struct Ctx {
   int *d_blkAdj = nullptr;      // [16*nEl] (e<<4 | a<<2 | b)
   int *d_nodeAdjPtr = nullptr;  // [nNo+1]
   int *d_nodeAdj = nullptr;     // [4*nEl] (e<<2 | a)
-  double *d_elemP = nullptr;    // per-element compact data for the gather variant
+  double *d_elemP = nullptr;    // [nEl][64] per-element compact records (gather variant)
+  int *d_blkOrder = nullptr;    // [nnz padded] block processing order (length-sorted chunks)
 
   // ---- system ----
   int dof = 0;                // dof of the resident R/Val

@@ -125,6 +125,16 @@ void launch_fluid_asm(cudaStream_t st, const FluidPar &par, int n, int e0, const
 void launch_heat_asm(cudaStream_t st, const HeatPar &par, int n, int e0, const int *elems,
                      const int *ien, const int *edest, const double *x, const double *Ag,
                      const double *Yg, double *R, double *Val, int atomic, int *badJac);
+// gather variant: element records + owner-computes accumulation (deterministic, no atomics)
+void launch_fluid_gather(cudaStream_t st, const FluidPar &par, int nEl, int nNo, int nnz,
+                         const int *ien, const double *x, const double *Ag, const double *Yg,
+                         const double *Bf, double *elemP, const int *blkOrder,
+                         const int *blkAdjPtr, const int *blkAdj, const int *nodeAdjPtr,
+                         const int *nodeAdj, double *R, double *Val, int *badJac);
+// adjacency lists for the gather variant (built once at gpu_mesh_create_)
+int build_gather_adjacency(cudaStream_t st, int nEl, int nNo, int nnz, const int *ien,
+                           const int *edest, int **blkAdjPtr, int **blkAdj, int **nodeAdjPtr,
+                           int **nodeAdj, int **blkOrder);
 // edest[e][a*4+b] = device block index of (row ien[e][a], col ien[e][b])
 void launch_build_edest(cudaStream_t st, int nEl, const int *ien, const int *rowPtr,
                         const int *col, int *edest);

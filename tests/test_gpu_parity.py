@@ -36,7 +36,7 @@ def gpu_assemble(p, variant):
     return api.get_R(4), api.get_Val(4)
 
 
-@pytest.mark.parametrize("variant", [api.ASM_ATOMIC, api.ASM_COLORED])
+@pytest.mark.parametrize("variant", [api.ASM_ATOMIC, api.ASM_COLORED, api.ASM_GATHER])
 def test_fluid_assembly(prob, variant):
     m, p = prob
     Rs, Vs = cm.oracle_assemble([p])
@@ -47,10 +47,12 @@ def test_fluid_assembly(prob, variant):
     assert max(errs.values()) <= TOL_ASM, errs
 
 
-def test_colored_assembly_is_deterministic(prob):
+@pytest.mark.parametrize("variant", [api.ASM_COLORED, api.ASM_GATHER])
+def test_deterministic_assembly_variants_are_bitwise_repeatable(prob, variant):
     m, p = prob
-    R1, V1 = gpu_assemble(p, api.ASM_COLORED)
-    R2, V2 = gpu_assemble(p, api.ASM_COLORED)
+    R1, V1 = gpu_assemble(p, variant)
+    gpu_assemble(p, api.ASM_ATOMIC)              # scribble over R / Val in between
+    R2, V2 = gpu_assemble(p, variant)
     assert np.array_equal(R1, R2) and np.array_equal(V1, V2)
     assert api.mesh_ncolors() >= 24          # interior node valence of the Kuhn lattice
 

@@ -30,18 +30,19 @@ namespace svfsi {
 static constexpr int NE = 128;       // elements per CTA
 static constexpr int NEP = NE + 1;   // padded field stride in shared memory (bank spread)
 
-// The per-element compact record: 64 doubles (512 B).
+// The per-element compact record: 80 doubles (640 B).
 //   node record a (8 doubles at a*8): Nx(1..3,a), C2_a, sum tauC, wl, sum tauM, R2_a
 //       C2_a = rho sum_g tauM uaNx_a ; R2_a = rho sum_g tauM (uNx_a + amd N_a)
 //       (the three element-wide scalars are replicated in every node record so that one
 //        64-byte node record holds everything a tangent block needs from that node)
-//   D(a,b) at 32 + a*4 + b : 4 mu Nx_a.Nx_b + A_ab  (diagonal term of the momentum tangent)
-//   lR(i,a) at 48 + a*4 + i
+//   (D,E)(a,b) at 32 + (a*4+b)*2 : D = 4 mu Nx_a.Nx_b + A_ab (diagonal term of the momentum
+//       tangent), E = sum tauM * Nx_a.Nx_b (dC/dP entry)
+//   lR(i,a) at 64 + a*4 + i
 // In shared memory (scatter variants) field f of slot s lives at f*NEP + s; in global memory
-// (gather variant) at e*64 + f.
+// (gather variant) at e*80 + f.
 enum {
   N_NX = 0, N_C2 = 3, N_STC = 4, N_WL = 5, N_STM = 6, N_R2 = 7,
-  F_D = 32, F_LR = 48, F_COUNT = 64
+  F_DE = 32, F_LR = 64, F_COUNT = 80
 };
 
 // S/UTIL.f:879-903 ISZERO(x) with one argument
@@ -121,8 +122,7 @@ __device__ __forceinline__ void fluid_elem_record(const FluidPar &par, int e,
                                                   const double *__restrict__ Yg,
                                                   const double *__restrict__ Bf, double *rec,
                                                   int *nodeOut, int *__restrict__ badJac) {
-    Tet4Tab tab;
-    tet4_tab(tab);
+    const double gs = (5.0 + 3.0 * sqrt(5.0)) / 20.0, gt = (5.0 - sqrt(5.0)) / 20.0;
     int nd[4];
     {
       const int4 v = __ldg((const int4 *)ien + e);
@@ -211,9 +211,12 @@ __device__ __forceinline__ void fluid_elem_record(const FluidPar &par, int e,
 
 #pragma unroll 1
     for (int g = 0; g < 4; g++) {
+      // N(:,g): S/NN.f:268-275 (xi) and :654-658 (N4 = 1 - xi1 - xi2 - xi3 as computed)
       double Ng[4];
-#pragma unroll
-      for (int a = 0; a < 4; a++) Ng[a] = tab.N[g][a];
+      Ng[0] = (g == 0) ? gs : gt;
+      Ng[1] = (g == 1) ? gs : gt;
+      Ng[2] = (g == 2) ? gs : gt;
+      Ng[3] = 1.0 - Ng[0] - Ng[1] - Ng[2];
       double ud[3], u[3], p = 0.0;
 #pragma unroll
       for (int i = 0; i < 3; i++) { ud[i] = -par.f[i]; u[i] = 0.0; }
@@ -304,7 +307,8 @@ __device__ __forceinline__ void fluid_elem_record(const FluidPar &par, int e,
 #pragma unroll
       for (int b = 0; b < 4; b++) {
         const double nn = Nx[a][0] * Nx[b][0] + Nx[a][1] * Nx[b][1] + Nx[a][2] * Nx[b][2];
-        rec[(F_D + a * 4 + b) * NEP] = 4.0 * (mu * nn) + A[a][b];
+        rec[(F_DE + (a * 4 + b) * 2) * NEP] = 4.0 * (mu * nn) + A[a][b];
+        rec[(F_DE + (a * 4 + b) * 2 + 1) * NEP] = sTM * nn;
       }
 #pragma unroll
       for (int i = 0; i < 3; i++)
@@ -316,44 +320,47 @@ __device__ __forceinline__ void fluid_elem_record(const FluidPar &par, int e,
 }
 
 // The pair of tangent entries (row i = q>>1, columns 2(q&1), 2(q&1)+1) of block (a,b) that lane q
-// of an 8-lane group owns, expanded from the compact record (field f at rec[f*stride]).
+// of an 8-lane group owns, expanded from the compact record (field f at rec[f*STRIDE]).
 // S/FLUID.f:482-557 (momentum rows) and :1052-1081 (continuity row), Gauss sums pre-reduced.
+// Branch-free: every lane issues the same six loads (two of them 128-bit in the global layout)
+// and selects, so a warp never serialises over the four (row kind, column pair) cases.
+template <int STRIDE>
+__device__ __forceinline__ double2 ld2(const double *p) {
+  if (STRIDE == 1) return __ldg((const double2 *)p);
+  return make_double2(p[0], p[STRIDE]);
+}
+__device__ __forceinline__ double sN_of(int a) {
+  // sum_g N(a,g) with N from S/NN.f:268-275,654-658 (mathematically 1; kept as computed)
+  const double s = (5.0 + 3.0 * sqrt(5.0)) / 20.0, t = (5.0 - sqrt(5.0)) / 20.0;
+  const double s012 = ((s + t) + t) + t, s1 = ((t + s) + t) + t, s2 = ((t + t) + s) + t;
+  const double n30 = 1.0 - s - t - t, n31 = 1.0 - t - s - t, n32 = 1.0 - t - t - s, n33 = 1.0 - t - t - t;
+  const double s3 = ((n30 + n31) + n32) + n33;
+  return a == 0 ? s012 : (a == 1 ? s1 : (a == 2 ? s2 : s3));
+}
 template <int STRIDE>
 __device__ __forceinline__ void tangent_pair(const double *__restrict__ rec, int a, int b, int q,
-                                             double mu4, const double sN[4], double &v0,
-                                             double &v1) {
+                                             double mu4, double &v0, double &v1) {
   const int i = q >> 1, j0 = (q & 1) * 2;
+  const bool row3 = (i == 3), col2 = (j0 == 2);
   const double *ra = rec + (size_t)(a * 8) * STRIDE, *rb = rec + (size_t)(b * 8) * STRIDE;
-  const double wl = ra[N_WL * STRIDE];
-  const double na_j0 = ra[(size_t)j0 * STRIDE], nb_j0 = rb[(size_t)j0 * STRIDE];
-  if (i < 3) {
-    const double nai = ra[(size_t)i * STRIDE], nbi = rb[(size_t)i * STRIDE];
-    const double sTC = ra[N_STC * STRIDE];
-    v0 = mu4 * (na_j0 * nbi) + sTC * (nai * nb_j0);
-    if (j0 == 0) {
-      const double na1 = ra[1 * STRIDE], nb1 = rb[1 * STRIDE];
-      v1 = mu4 * (na1 * nbi) + sTC * (nai * nb1);
-      if (i < 2) {
-        const double d = rec[(size_t)(F_D + a * 4 + b) * STRIDE];
-        if (i == 0) v0 += d; else v1 += d;
-      }
-      v0 *= wl;
-      v1 *= wl;
-    } else {
-      if (i == 2) v0 += rec[(size_t)(F_D + a * 4 + b) * STRIDE];
-      v0 *= wl;
-      v1 = -wl * (nai * sN[b] - nbi * ra[N_C2 * STRIDE]);   // pressure column, :547-557
-    }
-  } else {
-    const double sNa = sN[a], r2b = rb[N_R2 * STRIDE];
-    v0 = wl * (sNa * nb_j0 + na_j0 * r2b);
-    if (j0 == 0) {
-      v1 = wl * (sNa * rb[1 * STRIDE] + ra[1 * STRIDE] * r2b);
-    } else {
-      const double nn = ra[0] * rb[0] + ra[1 * STRIDE] * rb[1 * STRIDE] + na_j0 * nb_j0;
-      v1 = wl * (ra[N_STM * STRIDE] * nn);               // dC/dP, :1072-1081
-    }
-  }
+  const double2 A = ld2<STRIDE>(ra + (size_t)j0 * STRIDE);   // (Nx_j0, Nx_j0+1) of a; j0=2: (Nx_2, C2_a)
+  const double2 B = ld2<STRIDE>(rb + (size_t)j0 * STRIDE);
+  const double2 S = ld2<STRIDE>(ra + (size_t)N_STC * STRIDE);  // (sum tauC, wl)
+  const double ai = ra[(size_t)i * STRIDE];                   // Nx_i of a (row 3: unused)
+  const double bi = rb[(size_t)(row3 ? N_R2 : i) * STRIDE];    // Nx_i of b, or R2_b on the continuity row
+  const double de = rec[(size_t)(F_DE + (a * 4 + b) * 2 + (row3 ? 1 : 0)) * STRIDE];
+  const double wl = S.y, sTC = S.x;
+  const double sNa = sN_of(a), sNb = sN_of(b);
+  // momentum rows, velocity columns
+  const double m0 = (mu4 * (A.x * bi) + sTC * (ai * B.x) + ((i == j0) ? de : 0.0)) * wl;
+  const double m1 = (mu4 * (A.y * bi) + sTC * (ai * B.y) + ((i == 1) ? de : 0.0)) * wl;
+  const double mp = -wl * (ai * sNb - bi * A.y);               // pressure column (A.y = C2_a)
+  // continuity row
+  const double c0 = wl * (sNa * B.x + A.x * bi);               // bi = R2_b
+  const double c1 = wl * (sNa * B.y + A.y * bi);
+  const double cp = wl * de;                                   // de = sum tauM Nx_a.Nx_b
+  v0 = row3 ? c0 : m0;
+  v1 = row3 ? (col2 ? cp : c1) : (col2 ? mp : m1);
 }
 
 // ---------------------------------------------------------------------------
@@ -393,8 +400,6 @@ __global__ void __launch_bounds__(NE) fluid_asm_kernel(FluidPar par, int n, int 
   }
 
   // ---------------- phase 2b: tangent scatter, 8 lanes per 4x4 block ----------------
-  Tet4Tab tab2;
-  tet4_tab(tab2);
   const double mu4 = 4.0 * par.mu;
   for (int it = threadIdx.x; it < NE * 128; it += NE) {
     const int s = it >> 7;
@@ -402,7 +407,7 @@ __global__ void __launch_bounds__(NE) fluid_asm_kernel(FluidPar par, int n, int 
     if (el < 0) continue;
     const int blk = (it >> 3) & 15, q = it & 7;
     double v0, v1;
-    tangent_pair<NEP>(sm + s, blk >> 2, blk & 3, q, mu4, tab2.sN, v0, v1);
+    tangent_pair<NEP>(sm + s, blk >> 2, blk & 3, q, mu4, v0, v1);
     const int p = __ldg(edest + (size_t)el * 16 + blk);
     double *dst = Val + (size_t)p * 16 + q * 2;
     if (ATOMIC) {
@@ -441,8 +446,8 @@ __global__ void __launch_bounds__(NE) fluid_record_kernel(FluidPar par, int n,
   const int nHere = min(NE, n - blockIdx.x * NE);
   double *out = elemP + (size_t)blockIdx.x * NE * F_COUNT;
   for (int t = threadIdx.x; t < nHere * F_COUNT; t += NE) {
-    const int s = t >> 6, f = t & 63;
-    __stcs(out + t, sm[f * NEP + s]);
+    const int s = t / F_COUNT, f = t - s * F_COUNT;
+    out[t] = sm[f * NEP + s];
   }
 }
 
@@ -456,8 +461,6 @@ __global__ void __launch_bounds__(256) fluid_gather_val_kernel(int nnz, double m
   const unsigned gmask = 0xFFu << (lane & 24);
   const int g = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 3);
   if (g >= nnz) return;
-  Tet4Tab tab;
-  tet4_tab(tab);
   const int p = blkOrder ? __ldg(blkOrder + g) : g;
   const int s = __ldg(adjPtr + p), e = __ldg(adjPtr + p + 1);
   double acc0 = 0.0, acc1 = 0.0;
@@ -468,8 +471,7 @@ __global__ void __launch_bounds__(256) fluid_gather_val_kernel(int nnz, double m
     for (int k = 0; k < cnt; k++) {
       const int pk = __shfl_sync(gmask, cq, k, 8);
       double v0, v1;
-      tangent_pair<1>(elemP + (size_t)(pk >> 4) * F_COUNT, (pk >> 2) & 3, pk & 3, q, mu4, tab.sN,
-                      v0, v1);
+      tangent_pair<1>(elemP + (size_t)(pk >> 4) * F_COUNT, (pk >> 2) & 3, pk & 3, q, mu4, v0, v1);
       acc0 += v0;
       acc1 += v1;
     }

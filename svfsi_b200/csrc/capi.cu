@@ -116,7 +116,7 @@ int run_fluid_asm(const FluidPar &par, int variant) {
                          c.d_colorElems, c.d_ien, c.d_edest, c.d_x, c.d_Ag, c.d_Yg, bf, c.d_R,
                          c.d_Val, 0, c.d_flag);
     } else if (variant == SVFSI_ASM_GATHER) {
-      if (!c.d_elemP) CUDA_TRY(cudaMalloc(&c.d_elemP, sizeof(double) * 64 * (size_t)c.nEl));
+      if (!c.d_elemP) CUDA_TRY(cudaMalloc(&c.d_elemP, sizeof(double) * 80 * (size_t)c.nEl));
       launch_fluid_gather(c.stream, par, c.nEl, c.nNo, c.nnz, c.d_ien, c.d_x, c.d_Ag, c.d_Yg, bf,
                           c.d_elemP, c.d_blkOrder, c.d_blkAdjPtr, c.d_blkAdj, c.d_nodeAdjPtr,
                           c.d_nodeAdj, c.d_R, c.d_Val, c.d_flag);

@@ -353,6 +353,7 @@ int32_t gpu_lhs_create_(const int32_t *gnNo_, const int32_t *nNo_, const int32_t
   CUDA_TRY(cudaMalloc(&c.d_sbuf, sizeof(double) * 4 * std::max(c.nShared, 1)));
   CUDA_TRY(cudaMalloc(&c.d_rbuf, sizeof(double) * 4 * std::max(c.nShared, 1)));
   c.lhs = true;
+  c.lhsGen++;
   c.dof = 0;
   return 0;
 }

@@ -64,6 +64,7 @@ struct Ctx {
 
   // ---- lhs (FSILS_lhsType) ----
   bool lhs = false;
+  int lhsGen = 0;            // bumped by every FSILS_LHS_CREATE (invalidates cached maps)
   int gnNo = 0, nNo = 0, nnz = 0, nFaces = 0, mynNo = 0, shnNo = 0;
   std::vector<int> map;       // [nNo] svFSI local id (0-based) -> reordered id (0-based)
   std::vector<int> rowPtrDev; // host copy of device rowPtr (0-based, nNo+1)

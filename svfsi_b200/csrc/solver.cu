@@ -17,17 +17,11 @@
 #include <chrono>
 
 #include "core.h"
+#include "solver_int.h"
 
 namespace svfsi {
 
-namespace {
 
-constexpr int kLookahead = 4;  // iterations the host may run ahead of the device
-
-struct HostMirror {  // mapped pinned words written by the device
-  volatile int progress;
-  volatile int done;
-};
 HostMirror *g_hm = nullptr;      // host pointer
 HostMirror *g_hm_dev = nullptr;  // device alias
 int g_seq = 0;
@@ -37,8 +31,7 @@ int ensure_mirror() {
   void *p = nullptr;
   CUDA_TRY(cudaHostAlloc(&p, sizeof(HostMirror), cudaHostAllocMapped));
   g_hm = (HostMirror *)p;
-  g_hm->progress = 0;
-  g_hm->done = 0;
+  memset((void *)g_hm, 0, sizeof(HostMirror));
   void *d = nullptr;
   CUDA_TRY(cudaHostGetDevicePointer(&d, p, 0));
   g_hm_dev = (HostMirror *)d;
@@ -47,9 +40,34 @@ int ensure_mirror() {
 
 // progress/done publication + small scalar steps
 __global__ void publish_kernel(HostMirror *hm, int seq, const KrylovCtl *ctl) {
-  hm->progress = seq;
-  if (ctl->done) hm->done = 1;
+  hm->flag[seq & 63] = ctl->done;
   __threadfence_system();
+  hm->progress = seq;
+  __threadfence_system();
+}
+
+int publish(const KrylovCtl *ctl) {
+  Ctx &c = ctx();
+  g_seq++;
+  publish_kernel<<<1, 1, 0, c.stream>>>(g_hm_dev, g_seq, ctl);
+  count_launch();
+  return g_seq;
+}
+
+int wait_flag(int seq, int *flag) {
+  Ctx &c = ctx();
+  unsigned long spins = 0;
+  while (g_hm->progress - seq < 0) {
+    if ((++spins & 0xFFFFF) == 0) {  // every ~1M polls make sure the stream is still alive
+      cudaError_t e = cudaStreamQuery(c.stream);
+      if (e != cudaSuccess && e != cudaErrorNotReady)
+        return fail(SVFSI_ERR_CUDA, std::string("Krylov loop: ") + cudaGetErrorString(e));
+      if (e == cudaSuccess && g_hm->progress - seq < 0)
+        return fail(SVFSI_ERR_CUDA, "Krylov loop: stream drained without publishing progress");
+    }
+  }
+  *flag = g_hm->flag[seq & 63];
+  return 0;
 }
 
 __global__ void ctl_reset_kernel(KrylovCtl *ctl, int clear_all) {
@@ -153,16 +171,6 @@ __global__ void __launch_bounds__(256) cg_pupdate_kernel(const KrylovCtl *ctl, d
     P[e] = (P[e] + s1 * R[e]) * s2;
 }
 
-struct Bump {
-  char *base;
-  size_t off = 0;
-  explicit Bump(void *b) : base((char *)b) {}
-  double *take(size_t nd) {
-    double *p = (double *)(base + off);
-    off += ((nd * sizeof(double) + 255) / 256) * 256;
-    return p;
-  }
-};
 size_t padded(size_t nd) { return ((nd * sizeof(double) + 255) / 256) * 256; }
 
 bool any_coupled() {
@@ -235,12 +243,6 @@ double now_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-// layout of the scalar area used by GMRES
-struct GmresScal {
-  KrylovCtl *ctl;
-  double *hcol, *h, *cc, *ss, *err, *y, *coef, *faceS, *tmp;
-  size_t doubles;
-};
 GmresScal gmres_scal(double *base, int sD, int nFaces) {
   GmresScal g;
   size_t o = 0;
@@ -282,11 +284,8 @@ int arnoldi_cycle(int kind, int dof, const double *Val, double *u, size_t stride
                   size_t nOwned, int sD, GmresScal &g, bool pre, double *unCondU) {
   Ctx &c = ctx();
   const int *done = &g.ctl->done;
-  g_hm->done = 0;
-  const int seq0 = g_seq;
+  int seqPrev = -1;
   for (int i = 1; i <= sD; i++) {
-    if (g_hm->done) break;
-    while (g_seq - g_hm->progress > kLookahead && !g_hm->done) { /* spin: bounded run-ahead */ }
     double *ui = u + (size_t)i * stride, *um = u + (size_t)(i - 1) * stride;
     if (int rc = sparmul(kind, dof, Val, um, ui, done)) return rc;
     if (kind == 0) {
@@ -313,11 +312,14 @@ int arnoldi_cycle(int kind, int dof, const double *Val, double *u, size_t stride
       // u(:,:,i+1) (L/GMRES.f:363-381 sums j = 1..i), so skipping is exact.
       launch_multi_axpy_scale(c.stream, u, stride, ui, n, i, g.coef, &g.ctl->inv, done);
     }
-    g_seq++;
-    publish_kernel<<<1, 1, 0, c.stream>>>(g_hm_dev, g_seq, g.ctl);
-    count_launch();
+    const int seq = publish(g.ctl);
+    if (seqPrev >= 0) {  // flag of the PREVIOUS iteration: deterministic across ranks
+      int flag = 0;
+      if (int rc = wait_flag(seqPrev, &flag)) return rc;
+      if (flag) break;
+    }
+    seqPrev = seq;
   }
-  (void)seq0;
   return 0;
 }
 
@@ -420,13 +422,8 @@ int cgrad(svfsi_subls_t *ls, int dof, const double *K, double *R) {
   count_launch();
   launch_vecop(c.stream, VOP_COPY, P, R, nullptr, n, nullptr, 0.0, nullptr);
   launch_vecop(c.stream, VOP_ZERO, X, nullptr, nullptr, n, nullptr, 0.0, nullptr);
-  g_hm->done = 0;
-  g_seq++;
-  publish_kernel<<<1, 1, 0, c.stream>>>(g_hm_dev, g_seq, ctl);
-  count_launch();
+  int seqPrev = publish(ctl);
   for (int i = 1; i <= ls->mItr; i++) {
-    if (g_hm->done) break;
-    while (g_seq - g_hm->progress > kLookahead && !g_hm->done) { /* bounded run-ahead */ }
     if (int rc = sparmul(kind, dof, K, P, KP, done)) return rc;
     if (int rc = dot_dev(P, KP, nOwned, sc, done)) return rc;
     cg_alpha_kernel<<<1, 1, 0, c.stream>>>(ctl, sc);
@@ -441,9 +438,12 @@ int cgrad(svfsi_subls_t *ls, int dof, const double *K, double *R) {
       ProfScope ps(PROF_AXPY);
       cg_pupdate_kernel<<<148 * 8, 256, 0, c.stream>>>(ctl, P, R, n);
     }
-    g_seq++;
-    publish_kernel<<<1, 1, 0, c.stream>>>(g_hm_dev, g_seq, ctl);
-    count_launch(5);
+    count_launch(4);
+    const int seq = publish(ctl);
+    int flag = 0;
+    if (int rc = wait_flag(seqPrev, &flag)) return rc;
+    if (flag) break;
+    seqPrev = seq;
   }
   launch_vecop(c.stream, VOP_COPY, R, X, nullptr, n, nullptr, 0.0, nullptr);
   KrylovCtl hc;
@@ -455,6 +455,158 @@ int cgrad(svfsi_subls_t *ls, int dof, const double *K, double *R) {
   const double err = hc.scal[0], errO = hc.scal[1];
   ls->fNorm = sqrt(err);
   ls->callD = now_s() - t0;
+  if (errO < DBL_EPSILON) ls->dB = 0.0;
+  else ls->dB = 5.0 * log(err / errO);
+  return 0;
+}
+
+// GMRES(lhs, ls, dof, Val, R, X), out of place (L/GMRES.f:51-169): the inner solver of NSSOLVER.
+// ls%itr and ls%callD ACCUMULATE over calls; the Sherman-Morrison-like BCOP_TYPE_PRE correction is
+// applied whenever a face is coupled (:88-91, :112-115).
+size_t gmres_out_work(int sD, size_t n) { return ((size_t)(sD + 2)) * (padded(n) / sizeof(double)) + 64; }
+
+int gmres_outofplace(svfsi_subls_t *ls, int dof, const double *Val, const double *R, double *X,
+                     double *work, double *scal) {
+  Ctx &c = ctx();
+  const int sD = ls->sD;
+  const size_t n = (size_t)c.nNo * dof, nOwned = (size_t)c.mynNo * dof;
+  const size_t stride = padded(n) / sizeof(double);
+  if (int rc = ensure_mirror()) return rc;
+  GmresScal g = gmres_scal(scal, sD, (int)c.face.size());
+  double *u = work;
+  double *unCondU = work + (size_t)(sD + 1) * stride;
+  const bool coupled = any_coupled();
+  const double t0 = now_s();
+  ls->suc = 0;
+  ctl_reset_kernel<<<1, 1, 0, c.stream>>>(g.ctl, 1);
+  count_launch();
+  launch_vecop(c.stream, VOP_ZERO, X, nullptr, nullptr, n, nullptr, 0.0, nullptr);
+  KrylovCtl hc;
+  memset(&hc, 0, sizeof(hc));
+  int itrHost = 0;
+  for (int l = 1; l <= ls->mItr; l++) {
+    ctl_reset_kernel<<<1, 1, 0, c.stream>>>(g.ctl, 0);
+    count_launch();
+    if (l == 1) {
+      launch_vecop(c.stream, VOP_COPY, u, R, nullptr, n, nullptr, 0.0, nullptr);
+    } else {
+      itrHost++;
+      if (int rc = sparmul(0, dof, Val, X, u, nullptr)) return rc;
+      if (int rc = addbcmul(0, dof, X, u, g.faceS, nullptr)) return rc;
+      launch_vecop(c.stream, VOP_SUB_FROM, u, R, nullptr, n, nullptr, 0.0, nullptr);
+    }
+    if (coupled) {
+      launch_vecop(c.stream, VOP_COPY, unCondU, u, nullptr, n, nullptr, 0.0, nullptr);
+      if (int rc = addbcmul(1, dof, unCondU, u, g.faceS, nullptr)) return rc;
+    }
+    if (int rc = dot_dev(u, u, nOwned, g.tmp, nullptr)) return rc;
+    gmres_err0_kernel<<<1, 1, 0, c.stream>>>(g.tmp, g.err);
+    count_launch();
+    if (l == 1) {
+      // eps = err(1); early return when already below absTol (:95-104)
+      gmres_init_kernel<<<1, 1, 0, c.stream>>>(g.ctl, g.tmp, ls->absTol, ls->relTol);
+      count_launch();
+      CUDA_TRY(cudaMemcpyAsync(&hc, g.ctl, sizeof(hc), cudaMemcpyDeviceToHost, c.stream));
+      CUDA_TRY(cudaStreamSynchronize(c.stream));
+      if (hc.iNorm <= ls->absTol) {
+        ls->callD = DBL_EPSILON;
+        ls->dB = 0.0;
+        return 0;
+      }
+      ls->iNorm = hc.iNorm;
+      ls->fNorm = hc.iNorm;
+    }
+    ls->dB = ls->fNorm;
+    launch_vecop(c.stream, VOP_DIV_DEV, u, nullptr, nullptr, n, g.err, 0.0, nullptr);
+    if (int rc = arnoldi_cycle(0, dof, Val, u, stride, n, nOwned, sD, g, true, unCondU)) return rc;
+    {
+      ProfScope ps(PROF_SMALL);
+      launch_gmres_backsub(c.stream, g.ctl, sD, g.h, g.err, g.y);
+    }
+    {
+      ProfScope ps(PROF_AXPY);
+      launch_multi_axpy_acc(c.stream, u, stride, X, n, &g.ctl->ilast, sD, g.y);
+    }
+    CUDA_TRY(cudaMemcpyAsync(&hc, g.ctl, sizeof(hc), cudaMemcpyDeviceToHost, c.stream));
+    CUDA_TRY(cudaStreamSynchronize(c.stream));
+    ls->fNorm = hc.fNorm;
+    if (hc.suc) {
+      ls->suc = 1;
+      break;
+    }
+  }
+  ls->itr += itrHost + hc.itr;
+  ls->callD = now_s() - t0 + ls->callD;
+  ls->dB = 10.0 * log(ls->fNorm / ls->dB);
+  return 0;
+}
+
+// CGRAD_SCHUR (L/CGRAD.f:51-123): CG on the operator  L p - D (G p)  (NSSOLVER passes D = Gt = -G^T).
+size_t cg_schur_work(size_t nNo, int dof) {
+  return 4 * (padded(nNo) / sizeof(double)) + 2 * (padded(nNo * dof) / sizeof(double)) + 64;
+}
+
+int cgrad_schur(svfsi_subls_t *ls, int dof, const double *D, const double *G, const double *L,
+                double *R, double *work, double *scal) {
+  Ctx &c = ctx();
+  const size_t n = (size_t)c.nNo, nOwned = (size_t)c.mynNo, nv = n * dof;
+  if (int rc = ensure_mirror()) return rc;
+  KrylovCtl *ctl = (KrylovCtl *)scal;
+  double *sc = scal + 32;
+  double *faceS = scal + 48;
+  Bump b(work);
+  double *X = b.take(n), *P = b.take(n), *SP = b.take(n), *DGP = b.take(n);
+  double *GP = b.take(nv), *unCondU = b.take(nv);
+  const int *done = &ctl->done;
+  const int nblk = multidot_nblk();
+  const bool coupled = any_coupled();
+
+  const double t0 = now_s();
+  if (int rc = dot_dev(R, R, nOwned, sc, nullptr)) return rc;
+  cg_init_kernel<<<1, 1, 0, c.stream>>>(ctl, sc, ls->absTol, ls->relTol);
+  count_launch();
+  launch_vecop(c.stream, VOP_COPY, P, R, nullptr, n, nullptr, 0.0, nullptr);
+  launch_vecop(c.stream, VOP_ZERO, X, nullptr, nullptr, n, nullptr, 0.0, nullptr);
+  int seqPrev = publish(ctl);
+  for (int i = 1; i <= ls->mItr; i++) {
+    if (int rc = sparmul(2, dof, G, P, GP, done)) return rc;
+    if (coupled) {
+      launch_vecop(c.stream, VOP_COPY, unCondU, GP, nullptr, nv, nullptr, 0.0, done);
+      if (int rc = addbcmul(1, dof, unCondU, GP, faceS, done)) return rc;
+    }
+    if (int rc = sparmul(1, dof, D, GP, DGP, done)) return rc;
+    if (int rc = sparmul(3, 1, L, P, SP, done)) return rc;
+    launch_vecop(c.stream, VOP_AXPY, SP, DGP, nullptr, n, nullptr, -1.0, done);  // SP = SP - DGP
+    if (int rc = dot_dev(P, SP, nOwned, sc, done)) return rc;
+    cg_alpha_kernel<<<1, 1, 0, c.stream>>>(ctl, sc);
+    {
+      ProfScope ps(PROF_AXPY);
+      cg_update_kernel<<<nblk, 256, 0, c.stream>>>(ctl, X, R, P, SP, n, nOwned, c.d_partial);
+      launch_reduce_partials(c.stream, c.d_partial, 1, sc + 1, done);
+    }
+    if (int rc = allreduce_dev(sc + 1, 1)) return rc;
+    cg_err_kernel<<<1, 1, 0, c.stream>>>(ctl, sc + 1, ls->mItr);
+    {
+      ProfScope ps(PROF_AXPY);
+      cg_pupdate_kernel<<<148 * 8, 256, 0, c.stream>>>(ctl, P, R, n);
+    }
+    count_launch(4);
+    const int seq = publish(ctl);
+    int flag = 0;
+    if (int rc = wait_flag(seqPrev, &flag)) return rc;
+    if (flag) break;
+    seqPrev = seq;
+  }
+  launch_vecop(c.stream, VOP_COPY, R, X, nullptr, n, nullptr, 0.0, nullptr);
+  KrylovCtl hc;
+  CUDA_TRY(cudaMemcpyAsync(&hc, ctl, sizeof(hc), cudaMemcpyDeviceToHost, c.stream));
+  CUDA_TRY(cudaStreamSynchronize(c.stream));
+  ls->suc = hc.suc;
+  ls->iNorm = hc.iNorm;
+  const double err = hc.scal[0], errO = hc.scal[1];
+  ls->fNorm = sqrt(err);
+  ls->callD = now_s() - t0 + ls->callD;
+  ls->itr = ls->itr + hc.ilast;
   if (errO < DBL_EPSILON) ls->dB = 0.0;
   else ls->dB = 5.0 * log(err / errO);
   return 0;
@@ -481,8 +633,6 @@ int preconddiag(int dof, double *Val, double *R, double *W) {
   return 0;
 }
 
-}  // namespace
-
 int nssolver_dev(svfsi_ls_t *ls, int dof, const double *Val, double *R);  // nssolver.cu
 
 void ls_defaults(svfsi_ls_t *ls, int LS_type) {
@@ -508,13 +658,6 @@ void ls_defaults(svfsi_ls_t *ls, int LS_type) {
   }
   ls->RI.absTol = 1.e-10; ls->GM.absTol = 1.e-10; ls->CG.absTol = 1.e-10;
 }
-
-// exported to nssolver.cu
-int solver_addbcmul(int op, int dof, const double *X, double *Y, double *sS, const int *done) {
-  return addbcmul(op, dof, X, Y, sS, done);
-}
-int solver_bcpre(int nsd, double *sS) { return bcpre(nsd, sS); }
-bool solver_any_coupled() { return any_coupled(); }
 
 int fsils_solve_dev(svfsi_ls_t *ls, int dof, int prec, const int32_t *incL, const double *res) {
   Ctx &c = ctx();

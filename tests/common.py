@@ -69,7 +69,7 @@ def oracle_gmres_global(nparts, relTol, sD, mItr, res_out, dims=(8, 8, 20), L=4.
     w = oracle_world(probs, m.nNo)
     Rc = oracle_commu(w, probs, Rs)
     ls = ora.ls_create(ls_type or ora.LS_TYPE_GMRES, relTol=relTol, absTol=1e-14, maxItr=mItr,
-                       dimKry=sD, **lskw)
+                       dimKry=sD, **{k: v for k, v in lskw.items() if v is not None})
     X = [r.copy() for r in Rc]
     w.solve(ls, 4, X, [v.copy() for v in Vs], incL=[1, 1, 1], res=np.array([0.0, 0.0, res_out]))
     G = np.zeros((m.nNo, 4))

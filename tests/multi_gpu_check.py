@@ -112,6 +112,28 @@ def main():
         if ls.RI.itr == ls_o.RI.itr:
             check(tag + " step", err <= max(1e-8, 2 * floor), f"err={err:.2e} ref-floor={floor:.2e}")
 
+    # ---- NSSOLVER (svFSI's default for fluid)
+    for kw in [dict(relTol=0.4, sD=100, mItr=10, res_out=0.0), dict(relTol=1e-3, sD=100, mItr=10, res_out=3.0)]:
+        api.CONSTRUCT_FLUID(p.Ag, p.Yg, None, cm.RHO, cm.MU, cm.F, cm.DT, cm.GA["af"], cm.GA["am"],
+                            cm.GA["gam"], api.ASM_GATHER)
+        api.commu_dev(4)
+        ls = api.FSILS_LS_CREATE(api.LS_TYPE_NS, relTol=kw["relTol"], absTol=1e-14, maxItr=kw["mItr"],
+                                 dimKry=kw["sD"])
+        api.solve_dev(ls, 4, incL=[1, 1, 1], res=[0.0, 0.0, kw["res_out"]])
+        X = api.get_R(4)
+        ls_o, G = cm.oracle_gmres_global(world, ls_type=ora.LS_TYPE_NS, dims=dims, L=L, **kw)
+        Xref = G[p.rm.ltg - 1]
+        num = torch.tensor([float(((X - Xref) ** 2).sum()), float((Xref ** 2).sum())],
+                           dtype=torch.float64, device="cuda")
+        dist.all_reduce(num)
+        err = float(torch.sqrt(num[0] / num[1]))
+        tag = f"NS relTol={kw['relTol']} res={kw['res_out']}"
+        check(tag + " counters", ls.RI.itr == ls_o.RI.itr and abs(ls.GM.itr - ls_o.GM.itr) <= 1 and
+              abs(ls.CG.itr - ls_o.CG.itr) <= 1,
+              f"RI {ls.RI.itr}/{ls_o.RI.itr} GM {ls.GM.itr}/{ls_o.GM.itr} CG {ls.CG.itr}/{ls_o.CG.itr}")
+        if (ls.GM.itr, ls.CG.itr) == (ls_o.GM.itr, ls_o.CG.itr):
+            check(tag + " step", err <= 1e-8, f"err={err:.2e}")
+
     # ---- heat / CG (dof = 1)
     api.FSILS_LHS_FREE()
     api.FSILS_LHS_CREATE(m.nNo, p.rm.nNo, p.colPtr.size, p.rm.ltg, p.rowPtr, p.colPtr, 2)

@@ -135,6 +135,37 @@ def test_gmres_newton_step(prob, relTol, sD, mItr, res_out):
         assert num <= max(TOL_SOL, 2 * fx), (num, fx)
 
 
+@pytest.mark.parametrize("kw", [
+    dict(relTol=0.4, sD=100, mItr=10, res_out=0.0),                       # FSILS defaults (L/LS.f:70-78)
+    dict(relTol=1e-3, sD=100, mItr=10, res_out=0.0),
+    dict(relTol=1e-5, sD=100, mItr=15, res_out=0.0, relTolIn=(1e-3, 1e-2)),
+    dict(relTol=1e-3, sD=100, mItr=10, res_out=3.0),                      # coupled resistance outlet
+    dict(relTol=1e-3, sD=8, mItr=10, res_out=0.0, maxItrIn=(3, 40)),      # inner GMRES restarts, CG cap
+])
+def test_nssolver_newton_step(prob, kw):
+    """FSILS_SOLVE(LS_TYPE_NS): outer/inner iteration counters and the Newton step vs the oracle"""
+    m, p = prob
+    kw = dict(kw)
+    res_out = kw.pop("res_out")
+    ls_o, G = cm.oracle_gmres_global(1, res_out=res_out, ls_type=ora.LS_TYPE_NS, **kw)
+    Ro = G[p.rm.ltg - 1]
+    api.CONSTRUCT_FLUID(p.Ag, p.Yg, None, cm.RHO, cm.MU, cm.F, cm.DT, cm.GA["af"], cm.GA["am"],
+                        cm.GA["gam"], api.ASM_GATHER)
+    ls = api.FSILS_LS_CREATE(api.LS_TYPE_NS, relTol=kw["relTol"], absTol=1e-14, maxItr=kw["mItr"],
+                             dimKry=kw["sD"], relTolIn=kw.get("relTolIn"), maxItrIn=kw.get("maxItrIn"))
+    api.solve_dev(ls, 4, incL=[1, 1, 1], res=[0.0, 0.0, res_out])
+    X = api.get_R(4)
+    assert ls.RI.itr == ls_o.RI.itr and bool(ls.RI.suc) == bool(ls_o.RI.suc)
+    assert abs(ls.GM.itr - ls_o.GM.itr) <= 1 and abs(ls.CG.itr - ls_o.CG.itr) <= 1
+    assert abs(ls.RI.iNorm - ls_o.RI.iNorm) <= 1e-10 * ls_o.RI.iNorm
+    assert (ls.Resm, ls.Resc) == (ls_o.Resm, ls_o.Resc)
+    if (ls.GM.itr, ls.CG.itr) == (ls_o.GM.itr, ls_o.CG.itr):
+        # fNorm**2 = iNorm**2 - sum(xB*B) (L/NSSOLVER.f:177) is a cancelling difference: its
+        # absolute accuracy is a few hundred ulps of iNorm**2
+        assert abs(ls.RI.fNorm ** 2 - ls_o.RI.fNorm ** 2) <= 1e-13 * ls_o.RI.iNorm ** 2
+        assert np.linalg.norm(X - Ro) / np.linalg.norm(Ro) <= TOL_SOL
+
+
 def test_host_matrix_solve_matches_device_resident(prob):
     """FSILS_SOLVE with host Ri/Val (the reference call shape) == device-resident path"""
     m, p = prob

@@ -100,34 +100,70 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+PHYSICS = "fluid"      # --physics heat switches to BASELINE.json configs[3] (heatS, CGRADS)
+SOLVER = "gmres"       # --solver ns switches to FSILS_NSSOLVER with the FSILS defaults (configs[4])
+HEAT = dict(nu=1.0, s=0.0, rho=1.0)
+HEAT_LS = dict(relTol=1e-6, absTol=1e-12, maxItr=1000)
+
+
 def setup_rank(api, mesh, dims, rank, nparts):
     gnNo, p = mesh.build_rank_problem(*dims, rank=rank, nparts=nparts, R=R_PIPE, L=L_PIPE)
-    api.FSILS_LHS_CREATE(gnNo, p.rm.nNo, p.colPtr.size, p.rm.ltg, p.rowPtr, p.colPtr, 3)
-    for fi, name in enumerate(("inlet", "wall", "outlet"), start=1):
-        fa = p.faces[name]
-        api.FSILS_BC_CREATE(fi, fa["gN"].size, 3,
-                            api.BC_TYPE_Neu if fa["bc"] == "Neu" else api.BC_TYPE_Dir, fa["gN"],
-                            fa["val"])
+    if PHYSICS == "heat":
+        api.FSILS_LHS_CREATE(gnNo, p.rm.nNo, p.colPtr.size, p.rm.ltg, p.rowPtr, p.colPtr, 2)
+        for fi, name in enumerate(("inlet", "outlet"), start=1):
+            fa = p.faces[name]
+            api.FSILS_BC_CREATE(fi, fa["gN"].size, 1, api.BC_TYPE_Dir, fa["gN"], None)
+        p.Ag = np.ascontiguousarray(p.Yg[:, 0] * 0.1)        # dT/dt
+        p.Yg = np.ascontiguousarray(p.Yg[:, 2])              # T
+    else:
+        api.FSILS_LHS_CREATE(gnNo, p.rm.nNo, p.colPtr.size, p.rm.ltg, p.rowPtr, p.colPtr, 3)
+        for fi, name in enumerate(("inlet", "wall", "outlet"), start=1):
+            fa = p.faces[name]
+            api.FSILS_BC_CREATE(fi, fa["gN"].size, 3,
+                                api.BC_TYPE_Neu if fa["bc"] == "Neu" else api.BC_TYPE_Dir, fa["gN"],
+                                fa["val"])
     api.mesh_create(p.rm.IEN, p.rm.x)
     return gnNo, p
 
 
+def make_ls(api):
+    if PHYSICS == "heat":
+        return api.FSILS_LS_CREATE(api.LS_TYPE_CG, **HEAT_LS)
+    if SOLVER == "ns":
+        return api.FSILS_LS_CREATE(api.LS_TYPE_NS)          # L/LS.f:70-78 defaults
+    return api.FSILS_LS_CREATE(api.LS_TYPE_GMRES, **LS)
+
+
 def newton_step_dev(api, variant):
     """device-resident Newton iteration: R=0, Val=0, element loop, COMMU(R), FSILS_SOLVE"""
+    if PHYSICS == "heat":
+        api.construct_heats_dev(HEAT["nu"], HEAT["s"], HEAT["rho"], DT, GA["af"], GA["am"], GA["gam"],
+                                min(variant, 1))
+        api.commu_dev(1)
+        ls = make_ls(api)
+        api.solve_dev(ls, 1, incL=[1, 1])
+        return ls
     api.construct_fluid_dev(RHO, MU, F_BODY, DT, GA["af"], GA["am"], GA["gam"], variant)
     api.commu_dev(4)
-    ls = api.FSILS_LS_CREATE(api.LS_TYPE_GMRES, **LS)
+    ls = make_ls(api)
     api.solve_dev(ls, 4, incL=[1, 1, 1], res=[0.0, 0.0, RES_OUT])
     return ls
 
 
 def newton_step_e2e(api, variant, Ag, Yg, Rout):
     """same step through the reference-facing calls with HOST buffers"""
+    if PHYSICS == "heat":
+        api.CONSTRUCT_HEATS(Ag, Yg, HEAT["nu"], HEAT["s"], HEAT["rho"], DT, GA["af"], GA["am"],
+                            GA["gam"], min(variant, 1))
+        api.commu_dev(1)
+        ls = make_ls(api)
+        api.solve_dev(ls, 1, incL=[1, 1])
+        api._check(api.lib().gpu_get_r_(api._ci(1), api._d(Rout)))
+        return ls
     api.CONSTRUCT_FLUID(Ag, Yg, None, RHO, MU, F_BODY, DT, GA["af"], GA["am"], GA["gam"], variant)
     api.commu_dev(4)
-    ls = api.FSILS_LS_CREATE(api.LS_TYPE_GMRES, **LS)
+    ls = make_ls(api)
     api.solve_dev(ls, 4, incL=[1, 1, 1], res=[0.0, 0.0, RES_OUT])
-    import ctypes as C
     api._check(api.lib().gpu_get_r_(api._ci(4), api._d(Rout)))
     return ls
 
@@ -173,16 +209,30 @@ def main():
     ap.add_argument("--variant", default="gather", choices=["atomic", "colored", "gather"])
     ap.add_argument("--cpu-nz", type=int, default=24, help="axial cells of the CPU-baseline slice")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--solver", default="gmres", choices=["gmres", "ns"],
+                    help="non-default: FSILS_NSSOLVER with FSILS defaults (BASELINE configs[4])")
+    ap.add_argument("--physics", default="fluid", choices=["fluid", "heat"],
+                    help="non-default: heatS + CGRADS (BASELINE configs[3])")
     args = ap.parse_args()
+    global PHYSICS, SOLVER
+    PHYSICS, SOLVER = args.physics, args.solver
+    if PHYSICS != "fluid" or SOLVER != "gmres":
+        args.no_cpu = True
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dims = (DIMS[0], DIMS[1], args.nz)
     nEl_total = 6 * dims[0] * dims[1] * dims[2]
-    workload = (f"synthetic {nEl_total / 1e6:.2f}M-tet cylinder {dims[0]}x{dims[1]}x{dims[2]} Kuhn lattice, "
-                f"unsteady VMS Navier-Stokes, FSILS GMRES(sD={LS['dimKry']}, relTol={LS['relTol']}, "
+    if PHYSICS == "heat":
+        what = f"unsteady heat diffusion (dof=1), FSILS CGRADS(relTol={HEAT_LS['relTol']}) + diagonal preconditioner"
+    elif SOLVER == "ns":
+        what = "unsteady VMS Navier-Stokes, FSILS NSSOLVER (BIPN, FSILS defaults) + diagonal preconditioner"
+    else:
+        what = (f"unsteady VMS Navier-Stokes, FSILS GMRES(sD={LS['dimKry']}, relTol={LS['relTol']}, "
                 f"mItr={LS['maxItr']}) + diagonal preconditioner")
+    workload = (f"synthetic {nEl_total / 1e6:.2f}M-tet cylinder {dims[0]}x{dims[1]}x{dims[2]} Kuhn lattice, "
+                + what)
     config = dict(workload=workload, partition=f"{max(world, 1)} axial slabs",
                   l2="inputs larger than L2 (Val = 128 B x nnz >> 126 MB)", assembly=args.variant,
                   dt=DT, rho=RHO, mu=MU)
@@ -227,7 +277,8 @@ def main():
     variant = dict(atomic=api.ASM_ATOMIC, colored=api.ASM_COLORED, gather=api.ASM_GATHER)[args.variant]
     t_setup = time.perf_counter()
     gnNo, p = setup_rank(api, mesh, dims, rank, world)
-    api.state_upload(4, p.Ag, p.Yg, None)
+    dof = 1 if PHYSICS == "heat" else 4
+    api.state_upload(dof, p.Ag, p.Yg, None)
     api.sync()
     t_setup = time.perf_counter() - t_setup
     nNo, nnz, nEl = p.rm.nNo, p.colPtr.size, p.rm.nEl
@@ -274,14 +325,15 @@ def main():
     # e2e leg: host buffers (pinned), H2D + D2H inside the timed region
     Ag_h = torch.from_numpy(p.Ag).pin_memory().numpy()
     Yg_h = torch.from_numpy(p.Yg).pin_memory().numpy()
-    R_h = torch.empty((nNo, 4), dtype=torch.float64).pin_memory().numpy()
+    R_h = torch.empty((nNo, dof) if dof > 1 else (nNo,), dtype=torch.float64).pin_memory().numpy()
     for _ in range(max(1, args.warmup - 1)):
         newton_step_e2e(api, variant, Ag_h, Yg_h, R_h)
     ms_e2e, ls2 = timed(lambda: newton_step_e2e(api, variant, Ag_h, Yg_h, R_h), args.steps)
 
     # SpMV roofline: event pairs around every SPARMULVV kernel of the timed region
     spmv_ms, spmv_n = prof["spmv"]
-    alg_bytes = nnz * (128 + 4) + nNo * (8 + 32 + 32)           # SURVEY.md 8d, per launch, this rank
+    # SURVEY.md 8d, per launch, this rank (NS solver: mixed shapes -> bytes of the K (3x3) SpMV only approx.)
+    alg_bytes = nnz * (8 * dof * dof + 4) + nNo * (8 + 16 * dof)
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (spmv_ms / max(spmv_n, 1) * 1e-3) / 1e9 if spmv_n else None
     asm_ms, asm_n = prof["asm"]
@@ -297,13 +349,14 @@ def main():
                             h2d_bytes_per_step=int(Ag_h.nbytes + Yg_h.nbytes),
                             d2h_bytes_per_step=int(R_h.nbytes), ms_per_step=ms_e2e / args.steps),
                    gpu_launches=int(launches),
-                   roofline=dict(bound="hbm", kernel="spmv_vv4_kernel (FSILS_SPARMULVV dof=4)",
+                   roofline=dict(bound="hbm", kernel=("spmv_vv4_kernel (FSILS_SPARMULVV dof=4)" if dof == 4 and SOLVER == "gmres"
+                                                    else "spmv kernels (mixed shapes; bytes of the dof x dof shape)"),
                                  achieved=achieved, peak=peak, unit="GB/s",
                                  frac=(achieved / peak) if achieved else None, peak_source=peak_src,
                                  traffic=None, algorithmic_bytes_per_launch=int(alg_bytes),
                                  avg_launch_ms=spmv_ms / max(spmv_n, 1), launches=int(spmv_n)),
                    detail=dict(nEl_rank0=int(nEl), nNo_rank0=int(nNo), nnz_rank0=int(nnz),
-                               gmres_spmv_count=int(ls.RI.itr), gmres_suc=int(ls.RI.suc),
+                               gmres_spmv_count=int(ls.RI.itr), gmres_suc=int(ls.RI.suc), gm_itr=int(ls.GM.itr), cg_itr=int(ls.CG.itr),
                                iNorm=ls.RI.iNorm, fNorm=ls.RI.fNorm,
                                assembly_Melem_per_s=melem,
                                assembly_scatter_GBps=(scatter_bytes / (asm_ms / max(asm_n, 1) * 1e-3) / 1e9

@@ -312,15 +312,18 @@ def main():
     for _ in range(args.warmup):
         ls = newton_step_dev(api, variant)
     l0 = api.launch_count()
-    api.prof_reset(); api.prof_enable(True)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ms_dev, ls = timed(lambda: newton_step_dev(api, variant), args.steps)
     clocks = sampler.stop() if rank == 0 else None
+    launches = api.launch_count() - l0
+    # second timed pass over the same K steps with CUDA-event pairs around every kernel group
+    # (roofline + phase split); kept separate so that the events do not perturb `value`
+    api.prof_reset(); api.prof_enable(True)
+    ms_prof, _ = timed(lambda: newton_step_dev(api, variant), args.steps)
     prof = api.prof_get()
     api.prof_enable(False)
-    launches = api.launch_count() - l0
 
     # e2e leg: host buffers (pinned), H2D + D2H inside the timed region
     Ag_h = torch.from_numpy(p.Ag).pin_memory().numpy()
@@ -362,6 +365,7 @@ def main():
                                assembly_scatter_GBps=(scatter_bytes / (asm_ms / max(asm_n, 1) * 1e-3) / 1e9
                                                       if asm_n else None),
                                phase_ms_per_step={k: v[0] / args.steps for k, v in prof.items()},
+                               profiled_pass_ms_per_step=ms_prof / args.steps,
                                setup_s=t_setup))
         if world == 1 and not args.no_cpu:
             c = cpu_newton_sample(args.cpu_nz)

@@ -204,6 +204,8 @@ int32_t gpu_last_error_(char *buf, const int32_t *len) {
 
 int32_t gpu_lhs_free_(void) {
   Ctx &c = ctx();
+  if (c.stream) cudaStreamSynchronize(c.stream);
+  p2p_teardown();
   for (Face &f : c.face) {
     dev_free(&f.d_glob);
     dev_free(&f.d_val);
@@ -355,6 +357,7 @@ int32_t gpu_lhs_create_(const int32_t *gnNo_, const int32_t *nNo_, const int32_t
   c.lhs = true;
   c.lhsGen++;
   c.dof = 0;
+  if (int rc = p2p_setup()) return rc;
   return 0;
 }
 
@@ -630,8 +633,7 @@ int32_t gpu_dot_(const int32_t *dof, const double *U, const double *V, double *r
   if (!rc) rc = upload_nodal(V, *dof, dV);
   if (!rc) {
     launch_multidot(c.stream, dU, 0, dV, (size_t)c.mynNo * *dof, 1, c.d_partial, nullptr);
-    launch_reduce_partials(c.stream, c.d_partial, 1, c.d_small + 64, nullptr);
-    rc = allreduce_dev(c.d_small + 64, 1);
+    rc = reduce_allreduce(c.d_partial, 1, c.d_small + 64, nullptr);
   }
   if (!rc) {
     cudaMemcpyAsync(result, c.d_small + 64, sizeof(double), cudaMemcpyDeviceToHost, c.stream);

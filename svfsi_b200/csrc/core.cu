@@ -6,6 +6,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace svfsi {
@@ -121,23 +122,194 @@ int nccl_sendrecv(const double *sbuf, double *rbuf, const std::vector<Neighbor> 
   return 0;
 }
 
+// ------------------------------------------------------------------ peer-memory arena
+// One cudaMalloc per rank, exported with cudaIpcGetMemHandle and mapped by every peer
+// (cudaIpcOpenMemHandle): NVSwitch gives every GPU load/store access to every peer.  The 64-byte
+// handles travel through the host all-gather the caller lent us (MPI in the Fortran shim).
+template <typename T>
+static int upload_vec(T **d, const std::vector<T> &h) {
+  if (*d) cudaFree(*d);
+  *d = nullptr;
+  CUDA_TRY(cudaMalloc((void **)d, sizeof(T) * (h.empty() ? 1 : h.size())));
+  if (!h.empty()) CUDA_TRY(cudaMemcpy(*d, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+void p2p_teardown() {
+  Ctx &c = ctx();
+  P2P &p = c.p2p;
+  if (p.on || p.arena) {
+    cudaDeviceSynchronize();
+    for (int r = 0; r < (int)p.peer.size(); r++)
+      if (r != c.rank && p.peer[r]) cudaIpcCloseMemHandle(p.peer[r]);
+    if (p.arena) cudaFree(p.arena);
+  }
+  if (p.d_peer) cudaFree(p.d_peer);
+  if (p.d_nbrRank) cudaFree(p.d_nbrRank);
+  if (p.d_nbrOff) cudaFree(p.d_nbrOff);
+  if (p.d_nbrPeerOff) cudaFree(p.d_nbrPeerOff);
+  if (p.d_nbrN) cudaFree(p.d_nbrN);
+  if (p.d_slotNbr) cudaFree(p.d_slotNbr);
+  if (p.d_counter) cudaFree(p.d_counter);
+  p = P2P();
+}
+
+int p2p_setup() {
+  Ctx &c = ctx();
+  P2P &p = c.p2p;
+  if (c.nranks == 1) return 0;
+  const char *env = getenv("SVFSI_COMM");
+  int want = !(env && strcmp(env, "nccl") == 0);
+  // every rank must take the same decision: all-gather the local capability
+  int can = want;
+  if (can) {
+    int ndev = 0;
+    cudaGetDeviceCount(&ndev);
+    if (ndev < c.nranks) can = 0;  // single-node, one visible device per rank expected
+  }
+  std::vector<int32_t> all(c.nranks);
+  int32_t mine = can;
+  if (int rc = host_allgather_i32(&mine, 1, all.data())) return rc;
+  for (int v : all)
+    if (!v) return 0;  // stay on NCCL
+
+  // layout (identical on all ranks): halo capacity = max over ranks
+  int32_t myShared = c.nShared;
+  if (int rc = host_allgather_i32(&myShared, 1, all.data())) return rc;
+  int maxShared = 0;
+  for (int v : all) maxShared = v > maxShared ? v : maxShared;
+  p.haloCap = ((maxShared * 4 + 31) / 32) * 32;
+  p.offMail = 4096;
+  p.offHalo = p.offMail + sizeof(double) * 2 * (size_t)c.nranks * kArMax;
+  p.bytes = p.offHalo + sizeof(double) * 2 * (size_t)(p.haloCap > 0 ? p.haloCap : 32);
+  CUDA_TRY(cudaMalloc((void **)&p.arena, p.bytes));
+  CUDA_TRY(cudaMemset(p.arena, 0, p.bytes));
+  CUDA_TRY(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t hnd;
+  CUDA_TRY(cudaIpcGetMemHandle(&hnd, p.arena));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+  std::vector<int32_t> hs((size_t)16 * c.nranks);
+  if (int rc = host_allgather_i32((const int32_t *)&hnd, 16, hs.data())) return rc;
+  p.peer.assign(c.nranks, nullptr);
+  int ok = 1;
+  for (int r = 0; r < c.nranks; r++) {
+    if (r == c.rank) { p.peer[r] = p.arena; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, hs.data() + (size_t)16 * r, 64);
+    void *ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+    p.peer[r] = (char *)ptr;
+  }
+  mine = ok;
+  if (int rc = host_allgather_i32(&mine, 1, all.data())) return rc;
+  for (int v : all)
+    if (!v) { p2p_teardown(); return 0; }
+
+  // where does MY slab start inside each neighbour's receive buffer?  all-gather the offset tables
+  std::vector<int32_t> offRow(c.nranks, -1), offAll((size_t)c.nranks * c.nranks);
+  for (const Neighbor &nb : c.nbr) offRow[nb.iP] = nb.off;
+  if (int rc = host_allgather_i32(offRow.data(), c.nranks, offAll.data())) return rc;
+  std::vector<int> nbrRank, nbrOff, nbrPeerOff, nbrN, slotNbr(c.nShared);
+  for (size_t i = 0; i < c.nbr.size(); i++) {
+    const Neighbor &nb = c.nbr[i];
+    nbrRank.push_back(nb.iP);
+    nbrOff.push_back(nb.off);
+    nbrN.push_back(nb.n);
+    const int po = offAll[(size_t)nb.iP * c.nranks + c.rank];
+    if (po < 0) return fail(SVFSI_ERR_COMM, "asymmetric halo schedule");
+    nbrPeerOff.push_back(po);
+    for (int s = 0; s < nb.n; s++) slotNbr[nb.off + s] = (int)i;
+  }
+  if (int rc = upload_vec(&p.d_peer, p.peer)) return rc;
+  if (int rc = upload_vec(&p.d_nbrRank, nbrRank)) return rc;
+  if (int rc = upload_vec(&p.d_nbrOff, nbrOff)) return rc;
+  if (int rc = upload_vec(&p.d_nbrPeerOff, nbrPeerOff)) return rc;
+  if (int rc = upload_vec(&p.d_nbrN, nbrN)) return rc;
+  if (int rc = upload_vec(&p.d_slotNbr, slotNbr)) return rc;
+  CUDA_TRY(cudaMalloc((void **)&p.d_counter, sizeof(unsigned int)));
+  CUDA_TRY(cudaMemset(p.d_counter, 0, sizeof(unsigned int)));
+  p.arSeq = 0;
+  p.haloSeq = 0;
+  p.on = true;
+  // nobody may start writing into a peer before that peer has zeroed its arena: one barrier
+  if (int rc = host_allgather_i32(&mine, 1, all.data())) return rc;
+  return 0;
+}
+
+static P2PDev p2p_dev() {
+  Ctx &c = ctx();
+  P2PDev pd;
+  pd.peer = c.p2p.d_peer;
+  pd.offMail = c.p2p.offMail;
+  pd.offHalo = c.p2p.offHalo;
+  pd.haloCap = c.p2p.haloCap;
+  pd.rank = c.rank;
+  pd.nranks = c.nranks;
+  return pd;
+}
+
 // ------------------------------------------------------------------ collectives
+static int halo_send(const double *R, int dof, const int *done) {
+  Ctx &c = ctx();
+  if (c.p2p.on) {
+    c.p2p.haloSeq++;
+    launch_halo_send(c.stream, p2p_dev(), dof, c.nShared, (int)c.nbr.size(), c.d_packIdx,
+                     c.p2p.d_slotNbr, c.p2p.d_nbrRank, c.p2p.d_nbrOff, c.p2p.d_nbrPeerOff, R,
+                     c.p2p.haloSeq, c.p2p.d_counter);
+    return 0;
+  }
+  launch_pack(c.stream, dof, c.nShared, c.d_packIdx, R, c.d_sbuf, done);
+  return nccl_sendrecv(c.d_sbuf, c.d_rbuf, c.nbr, dof, c.stream);
+}
+static int halo_recv(double *R, int dof, const int *done) {
+  Ctx &c = ctx();
+  if (c.p2p.on) {
+    launch_halo_recv_add(c.stream, p2p_dev(), dof, (int)c.nbr.size(), c.p2p.d_nbrRank, c.nUniq,
+                         c.d_uniqNode, c.d_uniqPtr, c.d_uniqSlot, R, c.p2p.haloSeq);
+    return 0;
+  }
+  launch_unpack_add(c.stream, dof, c.nUniq, c.d_uniqNode, c.d_uniqPtr, c.d_uniqSlot, c.d_rbuf, R,
+                    done);
+  return 0;
+}
+
 int halo_sum(double *R, int dof, const int *done) {
   Ctx &c = ctx();
   if (c.nranks == 1 || c.nbr.empty()) return 0;
   ProfScope ps(PROF_HALO);
-  launch_pack(c.stream, dof, c.nShared, c.d_packIdx, R, c.d_sbuf, done);
-  if (int rc = nccl_sendrecv(c.d_sbuf, c.d_rbuf, c.nbr, dof, c.stream)) return rc;
-  launch_unpack_add(c.stream, dof, c.nUniq, c.d_uniqNode, c.d_uniqPtr, c.d_uniqSlot, c.d_rbuf, R,
-                    done);
-  return 0;
+  if (int rc = halo_send(R, dof, done)) return rc;
+  return halo_recv(R, dof, done);
 }
 
 int allreduce_dev(double *buf, size_t n) {
   Ctx &c = ctx();
   if (c.nranks == 1) return 0;
   ProfScope ps(PROF_ALLREDUCE);
+  if (c.p2p.on && n <= (size_t)kArMax) {
+    c.p2p.arSeq++;
+    launch_p2p_allreduce(c.stream, p2p_dev(), nullptr, 0, (int)n, buf, c.p2p.arSeq);
+    return 0;
+  }
   return nccl_allreduce_sum(buf, n, c.stream);
+}
+
+// out[j] = all-reduce( sum_b partial[j*nblk + b] ), j < k: the tail of every fused multi-dot
+int reduce_allreduce(const double *partial, int k, double *out, const int *done) {
+  Ctx &c = ctx();
+  if (c.nranks > 1 && c.p2p.on && k <= kArMax) {
+    ProfScope ps(PROF_ALLREDUCE);
+    c.p2p.arSeq++;
+    launch_p2p_allreduce(c.stream, p2p_dev(), partial, multidot_nblk(), k, out, c.p2p.arSeq);
+    return 0;
+  }
+  {
+    ProfScope ps(PROF_DOT);
+    launch_reduce_partials(c.stream, partial, k, out, done);
+  }
+  if (c.nranks == 1) return 0;
+  ProfScope ps(PROF_ALLREDUCE);
+  return nccl_allreduce_sum(out, (size_t)k, c.stream);
 }
 
 int host_allgather_i32(const int32_t *send, int32_t n, int32_t *recv) {
@@ -171,11 +343,32 @@ int col_dof(int kind, int dof) { return (kind == 0 || kind == 1) ? dof : 1; }
 int sparmul(int kind, int dof, const double *K, const double *U, double *KU, const int *done) {
   Ctx &c = ctx();
   if (kind == 3) dof = 1;
+  const int rd = row_dof(kind, dof);
+  if (c.nranks > 1 && !c.nbr.empty()) {
+    // rows shared with other ranks first (the two contiguous slabs at the ends of the reordered
+    // numbering, L/LHS.f:134-165), push them to the neighbours, then the interior rows while the
+    // halo is in flight, then add what arrived (L/SPARMUL.f:130 + L/INCOMMU.f:91-96)
+    {
+      ProfScope ps(PROF_SPMV);
+      launch_spmv2(c.stream, kind, dof, 0, c.shnNo, c.mynNo, c.nNo, c.d_rowPtr, c.d_col, K, U, KU,
+                   done);
+    }
+    {
+      ProfScope ps(PROF_HALO);
+      if (int rc = halo_send(KU, rd, done)) return rc;
+    }
+    {
+      ProfScope ps(PROF_SPMV);
+      launch_spmv(c.stream, kind, dof, c.shnNo, c.mynNo, c.d_rowPtr, c.d_col, K, U, KU, done);
+    }
+    ProfScope ps(PROF_HALO);
+    return halo_recv(KU, rd, done);
+  }
   {
     ProfScope ps(PROF_SPMV);
     launch_spmv(c.stream, kind, dof, 0, c.nNo, c.d_rowPtr, c.d_col, K, U, KU, done);
   }
-  return halo_sum(KU, row_dof(kind, dof), done);
+  return 0;
 }
 
 // ------------------------------------------------------------------ memory

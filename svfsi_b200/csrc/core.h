@@ -21,6 +21,11 @@ int nccl_sendrecv(const double *sbuf, double *rbuf, const std::vector<Neighbor> 
 int halo_sum(double *R, int dof, const int *done);
 // MPI_ALLREDUCE(SUM) of n doubles living on the device (L/BCAST.f, L/DOT.f, L/NORM.f)
 int allreduce_dev(double *buf, size_t n);
+// out[j] = all-reduce(sum_b partial[j*nblk+b]), j < k (one kernel on the peer-memory path)
+int reduce_allreduce(const double *partial, int k, double *out, const int *done);
+// peer-memory arena (IPC) set up after the halo schedule is known; falls back to NCCL
+int p2p_setup();
+void p2p_teardown();
 // host-side all-gather of int32 for the setup phase
 int host_allgather_i32(const int32_t *send, int32_t n, int32_t *recv);
 

@@ -47,6 +47,26 @@ struct Neighbor {
   std::vector<int> ptr;   // 0-based reordered node ids (host copy)
 };
 
+// Peer-memory communication arena (one cudaMalloc per rank, IPC-mapped by every peer).
+//   [flags: 4 x 64 ints][all-reduce mailbox: 2 slots x nranks x kArMax doubles]
+//   [halo receive buffer: 2 slots x haloCap doubles]
+// Identical layout on every rank so a peer address is base(peer) + the local offset.
+struct P2P {
+  bool on = false;
+  char *arena = nullptr;
+  size_t bytes = 0;
+  std::vector<char *> peer;      // [nranks] mapped base of every rank's arena (own = arena)
+  size_t offMail = 0, offHalo = 0;
+  int haloCap = 0;               // doubles per halo slot
+  std::vector<int> peerOff;      // [nbr] offset (nodes) of MY slab inside neighbour i's receive buffer
+  int arSeq = 0, haloSeq = 0;    // advance identically on every rank
+  char **d_peer = nullptr;       // device copy of peer[]
+  int *d_nbrRank = nullptr, *d_nbrOff = nullptr, *d_nbrPeerOff = nullptr, *d_nbrN = nullptr;
+  int *d_slotNbr = nullptr;      // [nShared] neighbour index of every pack slot
+  unsigned int *d_counter = nullptr;
+};
+static constexpr int kArMax = 512;
+
 struct EventPair {
   cudaEvent_t a, b;
   int slot;
@@ -84,6 +104,7 @@ struct Ctx {
   int *d_uniqPtr = nullptr;  // [nUniq+1] -> d_uniqSlot
   int *d_uniqSlot = nullptr; // pack-slot ids in ascending neighbour order
   double *d_sbuf = nullptr, *d_rbuf = nullptr;  // [nShared*4]
+  P2P p2p;
 
   // ---- mesh ----
   bool mesh = false;

@@ -33,6 +33,10 @@ struct KrylovCtl {
 // 3 SS.  dof in {1,2,3,4}.
 void launch_spmv(cudaStream_t st, int kind, int dof, int r0, int r1, const int *rowPtr,
                  const int *col, const double *K, const double *U, double *KU, const int *done);
+// rows [r0,r1) and [r2,r3) in ONE launch (the two boundary slabs of the reordered numbering)
+void launch_spmv2(cudaStream_t st, int kind, int dof, int r0, int r1, int r2, int r3,
+                  const int *rowPtr, const int *col, const double *K, const double *U, double *KU,
+                  const int *done);
 
 // ---------------- halo (L/INCOMMU.f) ----------------
 void launch_pack(cudaStream_t st, int dof, int nShared, const int *packIdx, const double *R,
@@ -40,6 +44,22 @@ void launch_pack(cudaStream_t st, int dof, int nShared, const int *packIdx, cons
 void launch_unpack_add(cudaStream_t st, int dof, int nUniq, const int *uniqNode,
                        const int *uniqPtr, const int *uniqSlot, const double *rbuf, double *R,
                        const int *done);
+
+// peer-memory versions (NVLink stores into the neighbour's IPC-mapped receive buffer + flag)
+struct P2PDev {
+  char **peer;          // [nranks] arena bases
+  size_t offMail, offHalo;
+  int haloCap, rank, nranks;
+};
+void launch_halo_send(cudaStream_t st, const P2PDev &pd, int dof, int nShared, int nNbr,
+                      const int *packIdx, const int *slotNbr, const int *nbrRank, const int *nbrOff,
+                      const int *nbrPeerOff, const double *R, int seq, unsigned int *counter);
+void launch_halo_recv_add(cudaStream_t st, const P2PDev &pd, int dof, int nNbr, const int *nbrRank,
+                          int nUniq, const int *uniqNode, const int *uniqPtr, const int *uniqSlot,
+                          double *R, int seq);
+// out[j] = sum over ranks (rank order) of (partial ? sum_b partial[j*nblk+b] : out[j]), j < k <= kArMax
+void launch_p2p_allreduce(cudaStream_t st, const P2PDev &pd, const double *partial, int nblk, int k,
+                          double *out, int seq);
 
 // ---------------- vectors ----------------
 // partial[j*nblk + b] = sum over block b of U_j . w, j < k; U_j = U + j*stride. n doubles.
@@ -108,7 +128,8 @@ void launch_face_norm2(cudaStream_t st, int nFaceNo, int fdof, int nsd, const in
 
 // ---------------- Krylov scalar kernels ----------------
 void launch_gmres_column(cudaStream_t st, KrylovCtl *ctl, int i, int sD, const double *hcol,
-                         double *h, double *c, double *s, double *err, double *coef);
+                         double *h, double *c, double *s, double *err, double *coef,
+                         volatile int *pubFlag, volatile int *pubProgress, int seq);
 void launch_gmres_backsub(cudaStream_t st, KrylovCtl *ctl, int sD, const double *h,
                           const double *err, double *y);
 // DEPART (L/NSSOLVER.f:237-305)

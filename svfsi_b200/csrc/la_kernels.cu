@@ -33,7 +33,8 @@ __device__ __forceinline__ double2 ldg_stream2(const double2 *p) {
 // Column ids of 8 consecutive blocks are fetched by one coalesced load and
 // broadcast by shuffles, so the U gather does not wait on a dependent load per
 // block.
-__global__ void __launch_bounds__(256) spmv_vv4_kernel(int r0, int r1, const int *__restrict__ rowPtr,
+__global__ void __launch_bounds__(256) spmv_vv4_kernel(int r0, int r1, int r2, int r3,
+                                                        const int *__restrict__ rowPtr,
                                                         const int *__restrict__ col,
                                                         const double2 *__restrict__ K,
                                                         const double2 *__restrict__ U,
@@ -44,8 +45,10 @@ __global__ void __launch_bounds__(256) spmv_vv4_kernel(int r0, int r1, const int
   const int q = lane & 7;
   const int h = q & 1;
   const unsigned gmask = 0xFFu << (lane & 24);
+  // rows [r0,r1) followed by rows [r2, ...): the two boundary slabs go out in one launch
   int row = r0 + (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 3);
-  if (row >= r1) return;  // whole 8-lane groups leave together
+  if (row >= r1) row += r2 - r1;
+  if (row >= r3) return;  // whole 8-lane groups leave together
   const int s = __ldg(rowPtr + row), e = __ldg(rowPtr + row + 1);
   double acc = 0.0;
   for (int base = s; base < e; base += 8) {
@@ -71,7 +74,8 @@ __global__ void __launch_bounds__(256) spmv_vv4_kernel(int r0, int r1, const int
 // q, q+4, ... of the row; partial results combined by shuffles.  BR x BC is the
 // block shape: VV d: (d,d); VS d: (1,d); SV d: (d,1); SS: (1,1).
 template <int BR, int BC>
-__global__ void __launch_bounds__(256) spmv_generic_kernel(int r0, int r1, const int *__restrict__ rowPtr,
+__global__ void __launch_bounds__(256) spmv_generic_kernel(int r0, int r1, int r2, int r3,
+                                                            const int *__restrict__ rowPtr,
                                                             const int *__restrict__ col,
                                                             const double *__restrict__ K,
                                                             const double *__restrict__ U,
@@ -82,7 +86,8 @@ __global__ void __launch_bounds__(256) spmv_generic_kernel(int r0, int r1, const
   const int q = lane & 3;
   const unsigned gmask = 0xFu << (lane & 28);
   int row = r0 + (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 2);
-  if (row >= r1) return;
+  if (row >= r1) row += r2 - r1;
+  if (row >= r3) return;
   const int s = __ldg(rowPtr + row), e = __ldg(rowPtr + row + 1);
   double acc[BR];
 #pragma unroll
@@ -110,38 +115,44 @@ __global__ void __launch_bounds__(256) spmv_generic_kernel(int r0, int r1, const
 }
 
 template <int BR, int BC>
-static void launch_generic(cudaStream_t st, int r0, int r1, const int *rowPtr, const int *col,
-                           const double *K, const double *U, double *KU, const int *done) {
-  const int rows = r1 - r0;
+static void launch_generic(cudaStream_t st, int r0, int r1, int r2, int r3, const int *rowPtr,
+                           const int *col, const double *K, const double *U, double *KU,
+                           const int *done) {
+  const int rows = (r1 - r0) + (r3 - r2);
   const int blocks = (rows * 4 + 255) / 256;
-  spmv_generic_kernel<BR, BC><<<blocks, 256, 0, st>>>(r0, r1, rowPtr, col, K, U, KU, done);
+  spmv_generic_kernel<BR, BC><<<blocks, 256, 0, st>>>(r0, r1, r2, r3, rowPtr, col, K, U, KU, done);
+}
+
+void launch_spmv2(cudaStream_t st, int kind, int dof, int r0, int r1, int r2, int r3,
+                  const int *rowPtr, const int *col, const double *K, const double *U, double *KU,
+                  const int *done) {
+  if (r1 < r0) r1 = r0;
+  if (r3 < r2) r3 = r2;
+  const int rows = (r1 - r0) + (r3 - r2);
+  if (rows <= 0) return;
+  count_launch();
+  if (kind == 0 && dof == 4) {
+    const int blocks = (int)(((size_t)rows * 8 + 255) / 256);
+    spmv_vv4_kernel<<<blocks, 256, 0, st>>>(r0, r1, r2, r3, rowPtr, col, (const double2 *)K,
+                                            (const double2 *)U, KU, done);
+    return;
+  }
+#define GEN(BR, BC) launch_generic<BR, BC>(st, r0, r1, r2, r3, rowPtr, col, K, U, KU, done)
+  if (kind == 3 || dof == 1) {
+    GEN(1, 1);
+  } else if (kind == 0) {
+    if (dof == 2) GEN(2, 2); else GEN(3, 3);
+  } else if (kind == 1) {
+    if (dof == 2) GEN(1, 2); else if (dof == 3) GEN(1, 3); else GEN(1, 4);
+  } else {
+    if (dof == 2) GEN(2, 1); else if (dof == 3) GEN(3, 1); else GEN(4, 1);
+  }
+#undef GEN
 }
 
 void launch_spmv(cudaStream_t st, int kind, int dof, int r0, int r1, const int *rowPtr,
                  const int *col, const double *K, const double *U, double *KU, const int *done) {
-  if (r1 <= r0) return;
-  count_launch();
-  if (kind == 0 && dof == 4) {
-    const int rows = r1 - r0;
-    const int blocks = (int)(((size_t)rows * 8 + 255) / 256);
-    spmv_vv4_kernel<<<blocks, 256, 0, st>>>(r0, r1, rowPtr, col, (const double2 *)K,
-                                            (const double2 *)U, KU, done);
-    return;
-  }
-  if (kind == 3 || dof == 1) {
-    launch_generic<1, 1>(st, r0, r1, rowPtr, col, K, U, KU, done);
-  } else if (kind == 0) {
-    if (dof == 2) launch_generic<2, 2>(st, r0, r1, rowPtr, col, K, U, KU, done);
-    else launch_generic<3, 3>(st, r0, r1, rowPtr, col, K, U, KU, done);
-  } else if (kind == 1) {
-    if (dof == 2) launch_generic<1, 2>(st, r0, r1, rowPtr, col, K, U, KU, done);
-    else if (dof == 3) launch_generic<1, 3>(st, r0, r1, rowPtr, col, K, U, KU, done);
-    else launch_generic<1, 4>(st, r0, r1, rowPtr, col, K, U, KU, done);
-  } else {
-    if (dof == 2) launch_generic<2, 1>(st, r0, r1, rowPtr, col, K, U, KU, done);
-    else if (dof == 3) launch_generic<3, 1>(st, r0, r1, rowPtr, col, K, U, KU, done);
-    else launch_generic<4, 1>(st, r0, r1, rowPtr, col, K, U, KU, done);
-  }
+  launch_spmv2(st, kind, dof, r0, r1, r1, r1, rowPtr, col, K, U, KU, done);
 }
 
 // ---------------------------------------------------------------------------
@@ -188,6 +199,135 @@ void launch_unpack_add(cudaStream_t st, int dof, int nUniq, const int *uniqNode,
   int n = nUniq * dof;
   unpack_add_kernel<<<(n + 255) / 256, 256, 0, st>>>(dof, nUniq, uniqNode, uniqPtr, uniqSlot,
                                                      rbuf, R, done);
+}
+
+// ---------------------------------------------------------------------------
+// Peer-memory halo sum and all-reduce: the FSILS_COMMUV / MPI_ALLREDUCE steps written as kernels
+// that store straight into the peers' IPC-mapped arenas over NVLink (no NCCL launch, no
+// host).  Flags carry a sequence number; two alternating slots make back-to-back exchanges safe
+// (a rank can be at most one exchange ahead of a neighbour: it needs the neighbour's previous
+// message to get there).
+__device__ __forceinline__ void st_flag_sys(volatile int *p, int v) {
+  __threadfence_system();
+  *p = v;
+}
+__device__ __forceinline__ void wait_flag_sys(volatile int *p, int v) {
+  while (*p != v) { /* spin on a word in local memory that the peer writes */ }
+  __threadfence_system();
+}
+// flags live at the start of the arena: int[4][64]: 0 = halo slot0, 1 = halo slot1, 2 = ar slot0, 3 = ar slot1
+__device__ __forceinline__ volatile int *flag_ptr(char *base, int which, int src) {
+  return (volatile int *)base + which * 64 + src;
+}
+
+__global__ void __launch_bounds__(256) halo_send_kernel(P2PDev pd, int dof, int nShared, int nNbr,
+                                                        const int *__restrict__ packIdx,
+                                                        const int *__restrict__ slotNbr,
+                                                        const int *__restrict__ nbrRank,
+                                                        const int *__restrict__ nbrOff,
+                                                        const int *__restrict__ nbrPeerOff,
+                                                        const double *__restrict__ R, int seq,
+                                                        unsigned int *counter) {
+  const int slot = seq & 1;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nShared * dof) {
+    const int s = t / dof, d = t - s * dof;
+    const int i = slotNbr[s];
+    double *dst = (double *)(pd.peer[nbrRank[i]] + pd.offHalo) + (size_t)slot * pd.haloCap +
+                  (size_t)(nbrPeerOff[i] + (s - nbrOff[i])) * dof + d;
+    *dst = R[(size_t)packIdx[s] * dof + d];
+  }
+  // last CTA to finish publishes the flags
+  __shared__ bool last;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (last) {
+    if (threadIdx.x < nNbr)
+      st_flag_sys(flag_ptr(pd.peer[nbrRank[threadIdx.x]], slot, pd.rank), seq);
+    if (threadIdx.x == 0) *counter = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) halo_recv_add_kernel(P2PDev pd, int dof, int nNbr,
+                                                            const int *__restrict__ nbrRank, int nUniq,
+                                                            const int *__restrict__ uniqNode,
+                                                            const int *__restrict__ uniqPtr,
+                                                            const int *__restrict__ uniqSlot,
+                                                            double *__restrict__ R, int seq) {
+  const int slot = seq & 1;
+  if (threadIdx.x < nNbr) wait_flag_sys(flag_ptr(pd.peer[pd.rank], slot, nbrRank[threadIdx.x]), seq);
+  __syncthreads();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nUniq * dof) return;
+  const int u = t / dof, d = t - u * dof;
+  const double *rbuf = (const double *)(pd.peer[pd.rank] + pd.offHalo) + (size_t)slot * pd.haloCap;
+  const size_t at = (size_t)uniqNode[u] * dof + d;
+  double v = R[at];
+  for (int k = uniqPtr[u]; k < uniqPtr[u + 1]; k++) v = v + __ldcv(rbuf + (size_t)uniqSlot[k] * dof + d);
+  R[at] = v;
+}
+
+void launch_halo_send(cudaStream_t st, const P2PDev &pd, int dof, int nShared, int nNbr,
+                      const int *packIdx, const int *slotNbr, const int *nbrRank, const int *nbrOff,
+                      const int *nbrPeerOff, const double *R, int seq, unsigned int *counter) {
+  count_launch();
+  const int n = nShared * dof;
+  halo_send_kernel<<<(n + 255) / 256, 256, 0, st>>>(pd, dof, nShared, nNbr, packIdx, slotNbr, nbrRank,
+                                                    nbrOff, nbrPeerOff, R, seq, counter);
+}
+void launch_halo_recv_add(cudaStream_t st, const P2PDev &pd, int dof, int nNbr, const int *nbrRank,
+                          int nUniq, const int *uniqNode, const int *uniqPtr, const int *uniqSlot,
+                          double *R, int seq) {
+  count_launch();
+  const int n = nUniq * dof;
+  halo_recv_add_kernel<<<(n + 255) / 256, 256, 0, st>>>(pd, dof, nNbr, nbrRank, nUniq, uniqNode, uniqPtr,
+                                                        uniqSlot, R, seq);
+}
+
+// reduce the multi-dot partials (optional) and all-reduce k <= kArMax scalars in ONE kernel:
+// every rank stores its k values into every peer's mailbox, flags, waits for all peers, and sums
+// in rank order -- so all ranks obtain bit-identical results (the Krylov control flow depends on it).
+__global__ void __launch_bounds__(512) p2p_allreduce_kernel(P2PDev pd, const double *__restrict__ partial,
+                                                            int nblk, int k, double *__restrict__ out,
+                                                            int seq) {
+  __shared__ double mine[kArMax];
+  const int slot = seq & 1;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (partial) {
+    for (int j = wid; j < k; j += nw) {
+      double v = 0.0;
+      for (int b = lane; b < nblk; b += 32) v += partial[(size_t)j * nblk + b];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) mine[j] = v;
+    }
+  } else {
+    for (int j = threadIdx.x; j < k; j += blockDim.x) mine[j] = out[j];
+  }
+  __syncthreads();
+  for (int p = 0; p < pd.nranks; p++) {
+    double *mb = (double *)(pd.peer[p] + pd.offMail) + ((size_t)slot * pd.nranks + pd.rank) * kArMax;
+    for (int j = threadIdx.x; j < k; j += blockDim.x) mb[j] = mine[j];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < pd.nranks) st_flag_sys(flag_ptr(pd.peer[threadIdx.x], 2 + slot, pd.rank), seq);
+  if (threadIdx.x < pd.nranks) wait_flag_sys(flag_ptr(pd.peer[pd.rank], 2 + slot, threadIdx.x), seq);
+  __syncthreads();
+  const double *mb = (const double *)(pd.peer[pd.rank] + pd.offMail) + (size_t)slot * pd.nranks * kArMax;
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    double v = 0.0;
+    for (int r = 0; r < pd.nranks; r++) v += __ldcv(mb + (size_t)r * kArMax + j);
+    out[j] = v;
+  }
+}
+
+void launch_p2p_allreduce(cudaStream_t st, const P2PDev &pd, const double *partial, int nblk, int k,
+                          double *out, int seq) {
+  count_launch();
+  p2p_allreduce_kernel<<<1, 512, 0, st>>>(pd, partial, nblk, k, out, seq);
 }
 
 // ---------------------------------------------------------------------------
@@ -616,9 +756,10 @@ void launch_face_axpy(cudaStream_t st, int nFaceNo, int fdof, int dof, const int
 __global__ void gmres_column_kernel(KrylovCtl *ctl, int i, int sD, const double *__restrict__ hcol,
                                     double *__restrict__ h, double *__restrict__ c,
                                     double *__restrict__ s, double *__restrict__ err,
-                                    double *__restrict__ coef) {
-  if (ctl->done) return;
+                                    double *__restrict__ coef, volatile int *pubFlag,
+                                    volatile int *pubProgress, int seq) {
   if (threadIdx.x != 0) return;
+  if (!ctl->done) {
   double *hc = h + (size_t)(i - 1) * (sD + 1);  // h(:,i), 0-based rows
   double hh = hcol[i];
   for (int j = 0; j < i; j++) {
@@ -648,11 +789,21 @@ __global__ void gmres_column_kernel(KrylovCtl *ctl, int i, int sD, const double 
     ctl->suc = 1;
     ctl->done = 1;
   }
+  }
+  // publish the stop flag AS OF THIS COLUMN to the host (mapped pinned memory), see solver_int.h
+  if (pubFlag) {
+    *pubFlag = ctl->done;
+    __threadfence_system();
+    *pubProgress = seq;
+    __threadfence_system();
+  }
 }
 void launch_gmres_column(cudaStream_t st, KrylovCtl *ctl, int i, int sD, const double *hcol,
-                         double *h, double *c, double *s, double *err, double *coef) {
+                         double *h, double *c, double *s, double *err, double *coef,
+                         volatile int *pubFlag, volatile int *pubProgress, int seq) {
   count_launch();
-  gmres_column_kernel<<<1, 32, 0, st>>>(ctl, i, sD, hcol, h, c, s, err, coef);
+  gmres_column_kernel<<<1, 32, 0, st>>>(ctl, i, sD, hcol, h, c, s, err, coef, pubFlag, pubProgress,
+                                        seq);
 }
 
 // back substitution, L/GMRES.f:370-376; fNorm = |err(i+1)| (:382)

@@ -118,8 +118,9 @@ __global__ void cg_alpha_kernel(KrylovCtl *ctl, const double *pkp) {
   ctl->scal[2] = ctl->scal[1] / *pkp;
 }
 // err = ||R||^2, convergence test of the NEXT loop trip (L/CGRAD.f:151-154,164-165)
-__global__ void cg_err_kernel(KrylovCtl *ctl, const double *rr, int mItr) {
-  if (ctl->done) return;
+__global__ void cg_err_kernel(KrylovCtl *ctl, const double *rr, int mItr, volatile int *pubFlag,
+                              volatile int *pubProgress, int seq) {
+  if (!ctl->done) {
   double e = sqrt(*rr);
   e = e * e;
   ctl->scal[0] = e;
@@ -132,7 +133,12 @@ __global__ void cg_err_kernel(KrylovCtl *ctl, const double *rr, int mItr) {
     ctl->suc = 1;
     ctl->done = 1;
   }
+  }
   (void)mItr;
+  *pubFlag = ctl->done;
+  __threadfence_system();
+  *pubProgress = seq;
+  __threadfence_system();
 }
 
 // X += alpha P ; R -= alpha KP ; partial sums of R.R over the owned range
@@ -234,9 +240,8 @@ int dot_dev(const double *U, const double *V, size_t nOwned, double *out, const 
   {
     ProfScope ps(PROF_DOT);
     launch_multidot(c.stream, U, 0, V, nOwned, 1, c.d_partial, done);
-    launch_reduce_partials(c.stream, c.d_partial, 1, out, done);
   }
-  return allreduce_dev(out, 1);
+  return reduce_allreduce(c.d_partial, 1, out, done);
 }
 
 double now_s() {
@@ -298,12 +303,13 @@ int arnoldi_cycle(int kind, int dof, const double *Val, double *u, size_t stride
     {
       ProfScope ps(PROF_DOT);
       launch_multidot(c.stream, u, stride, ui, nOwned, i + 1, c.d_partial, done);
-      launch_reduce_partials(c.stream, c.d_partial, i + 1, g.hcol, done);
     }
-    if (int rc = allreduce_dev(g.hcol, (size_t)i + 1)) return rc;
+    if (int rc = reduce_allreduce(c.d_partial, i + 1, g.hcol, done)) return rc;
+    const int seq = ++g_seq;
     {
       ProfScope ps(PROF_SMALL);
-      launch_gmres_column(c.stream, g.ctl, i, sD, g.hcol, g.h, g.cc, g.ss, g.err, g.coef);
+      launch_gmres_column(c.stream, g.ctl, i, sD, g.hcol, g.h, g.cc, g.ss, g.err, g.coef,
+                          &g_hm_dev->flag[seq & 63], &g_hm_dev->progress, seq);
     }
     {
       ProfScope ps(PROF_AXPY);
@@ -312,7 +318,6 @@ int arnoldi_cycle(int kind, int dof, const double *Val, double *u, size_t stride
       // u(:,:,i+1) (L/GMRES.f:363-381 sums j = 1..i), so skipping is exact.
       launch_multi_axpy_scale(c.stream, u, stride, ui, n, i, g.coef, &g.ctl->inv, done);
     }
-    const int seq = publish(g.ctl);
     if (seqPrev >= 0) {  // flag of the PREVIOUS iteration: deterministic across ranks
       int flag = 0;
       if (int rc = wait_flag(seqPrev, &flag)) return rc;
@@ -430,16 +435,16 @@ int cgrad(svfsi_subls_t *ls, int dof, const double *K, double *R) {
     {
       ProfScope ps(PROF_AXPY);
       cg_update_kernel<<<nblk, 256, 0, c.stream>>>(ctl, X, R, P, KP, n, nOwned, c.d_partial);
-      launch_reduce_partials(c.stream, c.d_partial, 1, sc + 1, done);
     }
-    if (int rc = allreduce_dev(sc + 1, 1)) return rc;
-    cg_err_kernel<<<1, 1, 0, c.stream>>>(ctl, sc + 1, ls->mItr);
+    if (int rc = reduce_allreduce(c.d_partial, 1, sc + 1, done)) return rc;
+    const int seq = ++g_seq;
+    cg_err_kernel<<<1, 1, 0, c.stream>>>(ctl, sc + 1, ls->mItr, &g_hm_dev->flag[seq & 63],
+                                         &g_hm_dev->progress, seq);
     {
       ProfScope ps(PROF_AXPY);
       cg_pupdate_kernel<<<148 * 8, 256, 0, c.stream>>>(ctl, P, R, n);
     }
     count_launch(4);
-    const int seq = publish(ctl);
     int flag = 0;
     if (int rc = wait_flag(seqPrev, &flag)) return rc;
     if (flag) break;
@@ -582,16 +587,16 @@ int cgrad_schur(svfsi_subls_t *ls, int dof, const double *D, const double *G, co
     {
       ProfScope ps(PROF_AXPY);
       cg_update_kernel<<<nblk, 256, 0, c.stream>>>(ctl, X, R, P, SP, n, nOwned, c.d_partial);
-      launch_reduce_partials(c.stream, c.d_partial, 1, sc + 1, done);
     }
-    if (int rc = allreduce_dev(sc + 1, 1)) return rc;
-    cg_err_kernel<<<1, 1, 0, c.stream>>>(ctl, sc + 1, ls->mItr);
+    if (int rc = reduce_allreduce(c.d_partial, 1, sc + 1, done)) return rc;
+    const int seq = ++g_seq;
+    cg_err_kernel<<<1, 1, 0, c.stream>>>(ctl, sc + 1, ls->mItr, &g_hm_dev->flag[seq & 63],
+                                         &g_hm_dev->progress, seq);
     {
       ProfScope ps(PROF_AXPY);
       cg_pupdate_kernel<<<148 * 8, 256, 0, c.stream>>>(ctl, P, R, n);
     }
     count_launch(4);
-    const int seq = publish(ctl);
     int flag = 0;
     if (int rc = wait_flag(seqPrev, &flag)) return rc;
     if (flag) break;

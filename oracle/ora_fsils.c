@@ -642,6 +642,133 @@ static void preconddiag(ora_world_t *w, int dof, double *const *Val,
 }
 
 /* ================================================================== */
+/* L/PRECOND.f:150-368 PRECONDRCS: Dirichlet rows/columns killed with a 0/1 mask,
+ * unit diagonal put back, then iterated max-norm row/column equilibration
+ * (at most 10 sweeps, stop when every row/column max is < 3).  W1 scales the RHS,
+ * W2 (the Wc of L/SOLVE.f:136) the solution.  Coupled-face valM is NOT updated
+ * (the block is commented out in the reference, :352-364). */
+static void premul(const ora_lhs_t *lhs, int dof, double *Val, const double *W) {
+  int dd = dof*dof;
+  for (int Ac = 1; Ac <= lhs->nNo; Ac++)
+    for (int j = lhs->rowPtr[2*(Ac-1)]; j <= lhs->rowPtr[2*(Ac-1)+1]; j++)
+      for (int i = 0; i < dof; i++)
+        for (int k = 0; k < dof; k++)
+          Val[(size_t)(j-1)*dd + i*dof + k] =
+              Val[(size_t)(j-1)*dd + i*dof + k]*W[(size_t)(Ac-1)*dof + i];
+}
+static void posmul(const ora_lhs_t *lhs, int dof, double *Val, const double *W) {
+  int dd = dof*dof;
+  for (int Ac = 1; Ac <= lhs->nNo; Ac++)
+    for (int j = lhs->rowPtr[2*(Ac-1)]; j <= lhs->rowPtr[2*(Ac-1)+1]; j++) {
+      int a = lhs->colPtr[j-1];
+      for (int i = 0; i < dof; i++)
+        for (int k = 0; k < dof; k++)
+          Val[(size_t)(j-1)*dd + i*dof + k] =
+              Val[(size_t)(j-1)*dd + i*dof + k]*W[(size_t)(a-1)*dof + k];
+    }
+}
+static void precondrcs(ora_world_t *w, int dof, double *const *Val,
+                       double *const *R, double *const *W1, double *const *W2) {
+  int dd = dof*dof, iter = 0, maxiter = 10, flag = 1;
+  double tol = 2.0;
+  double **Wr = wv_alloc(w, dof), **Wc = wv_alloc(w, dof);
+
+  FOR_RANKS {
+    const ora_lhs_t *lhs = &w->lhs[r];
+    size_t n = (size_t)lhs->nNo*(size_t)dof;
+    for (size_t i = 0; i < n; i++) { W1[r][i] = 1.0; W2[r][i] = 1.0; Wr[r][i] = 1.0; }
+    for (int faIn = 0; faIn < lhs->nFaces; faIn++) {   /* :181-191 */
+      const ora_face_t *f = &lhs->face[faIn];
+      int m;
+      if (!f->incFlag) continue;
+      m = f->dof < dof ? f->dof : dof;
+      if (f->bGrp == ORA_BC_TYPE_DIR)
+        for (int a = 0; a < f->nNo; a++) {
+          size_t Ac = (size_t)(f->glob[a]-1);
+          for (int k = 0; k < m; k++)
+            Wr[r][Ac*dof + k] = Wr[r][Ac*dof + k]*f->val[(size_t)a*f->dof + k];
+        }
+    }
+  }
+  ora_commuv(w, dof, Wr);                               /* :192 */
+  FOR_RANKS {
+    const ora_lhs_t *lhs = &w->lhs[r];
+    size_t n = (size_t)lhs->nNo*(size_t)dof;
+    for (size_t i = 0; i < n; i++) {                    /* :195-197 */
+      double v = Wr[r][i] - 0.5;
+      v = v/fabs(v);
+      Wr[r][i] = (v + fabs(v))*0.5;
+    }
+    premul(lhs, dof, Val[r], Wr[r]);                    /* :199 */
+    for (size_t i = 0; i < n; i++) R[r][i] = Wr[r][i]*R[r][i];
+    posmul(lhs, dof, Val[r], Wr[r]);                    /* :201 */
+    for (int Ac = 1; Ac <= lhs->nNo; Ac++) {            /* :203-237 */
+      int d = lhs->diagPtr[Ac-1];
+      for (int i = 1; i <= dof; i++) {
+        size_t q = (size_t)(d-1)*dd + (size_t)(i*dof-dof+i) - 1;
+        Val[r][q] = Wr[r][(size_t)(Ac-1)*dof + i-1]*(Val[r][q] - 1.0) + 1.0;
+      }
+    }
+  }
+
+  while (flag) {                                        /* :242-344 */
+    int conv = 1;
+    iter = iter + 1;
+    if (iter >= maxiter) flag = 0;
+    FOR_RANKS {
+      const ora_lhs_t *lhs = &w->lhs[r];
+      size_t n = (size_t)lhs->nNo*(size_t)dof;
+      for (size_t i = 0; i < n; i++) { Wr[r][i] = 0.0; Wc[r][i] = 0.0; }
+      for (int Ac = 1; Ac <= lhs->nNo; Ac++)
+        for (int j = lhs->rowPtr[2*(Ac-1)]; j <= lhs->rowPtr[2*(Ac-1)+1]; j++) {
+          int a = lhs->colPtr[j-1];
+          for (int i = 0; i < dof; i++)
+            for (int k = 0; k < dof; k++) {
+              double v = fabs(Val[r][(size_t)(j-1)*dd + i*dof + k]);
+              if (v > Wr[r][(size_t)(Ac-1)*dof + i]) Wr[r][(size_t)(Ac-1)*dof + i] = v;
+              if (v > Wc[r][(size_t)(a-1)*dof + k]) Wc[r][(size_t)(a-1)*dof + k] = v;
+            }
+        }
+    }
+    ora_commuv(w, dof, Wr);                             /* :320-321 */
+    ora_commuv(w, dof, Wc);
+    /* :323-324 -- every rank tests its own vectors and clears ITS flag; the
+     * MPI_ALLGATHER + ANY (:338-342) keeps all ranks sweeping while any rank is
+     * unconverged (and not at maxiter, which all ranks reach together) */
+    FOR_RANKS {
+      size_t n = (size_t)w->lhs[r].nNo*(size_t)dof;
+      double mr = 0.0, mc = 0.0;
+      for (size_t i = 0; i < n; i++) {
+        double a = fabs(1.0 - Wr[r][i]), b = fabs(1.0 - Wc[r][i]);
+        if (a > mr) mr = a;
+        if (b > mc) mc = b;
+      }
+      if (!(mr < tol && mc < tol)) conv = 0;
+    }
+    if (conv) flag = 0;
+    FOR_RANKS {
+      const ora_lhs_t *lhs = &w->lhs[r];
+      size_t n = (size_t)lhs->nNo*(size_t)dof;
+      for (size_t i = 0; i < n; i++) {                  /* :326-327 */
+        Wr[r][i] = 1.0/sqrt(Wr[r][i]);
+        Wc[r][i] = 1.0/sqrt(Wc[r][i]);
+      }
+      premul(lhs, dof, Val[r], Wr[r]);                  /* :329-330 */
+      posmul(lhs, dof, Val[r], Wc[r]);
+      for (size_t i = 0; i < n; i++) {                  /* :332-333 */
+        W1[r][i] = W1[r][i]*Wr[r][i];
+        W2[r][i] = W2[r][i]*Wc[r][i];
+      }
+    }
+  }
+  FOR_RANKS {                                           /* :347 */
+    size_t n = (size_t)w->lhs[r].nNo*(size_t)dof;
+    for (size_t i = 0; i < n; i++) R[r][i] = W1[r][i]*R[r][i];
+  }
+  wv_free(w, Wr); wv_free(w, Wc);
+}
+
+/* ================================================================== */
 /* Arnoldi/Givens core shared by GMRES (L/GMRES.f:106-152), GMRESS (:212-263)
  * and GMRESV (:330-381).  u[k] are world vectors, k = 0..sD.  pre != 0 applies
  * the BCOP_TYPE_PRE correction (only GMRES(...,X) does).  Returns i as left by
@@ -885,6 +1012,67 @@ static void cgrad(ora_world_t *w, ora_subls_t *ls, int dof,
   wv_free(w, P); wv_free(w, KP); wv_free(w, X);
 }
 
+/* L/BICGS.f:50-111 BICGSS (dof = 1) and :113-180 BICGSV: BiCGStab, statement order kept */
+static void bicgs(ora_world_t *w, ora_subls_t *ls, int dof,
+                  const double *const *K, double *const *R) {
+  double **P = wv_alloc(w, dof), **Rh = wv_alloc(w, dof), **X = wv_alloc(w, dof),
+         **V = wv_alloc(w, dof), **S = wv_alloc(w, dof), **T = wv_alloc(w, dof);
+  double errO, err, alpha, beta, rho, rhoO, omega, eps, t0;
+  int i;
+#define CW(x) ((const double *const *)(x))
+  t0        = ora_wtime();
+  ls->suc   = 0;
+  err       = ora_normv(w, dof, CW(R));
+  errO      = err;
+  ls->iNorm = err;
+  eps       = (ls->absTol > ls->relTol*err) ? ls->absTol : ls->relTol*err;
+  rho       = err*err;
+  wv_zero(w, dof, X);
+  wv_copy(w, dof, P, CW(R));
+  wv_copy(w, dof, Rh, CW(R));
+
+  for (i = 1; i <= ls->mItr; i++) {
+    if (err < eps) { ls->suc = 1; break; }
+    if (dof == 1) ora_sparmul_ss(w, K, CW(P), V);
+    else ora_sparmul_vv(w, dof, K, CW(P), V);
+    alpha = rho/ora_dotv(w, dof, CW(Rh), CW(V));
+    FOR_RANKS {                                   /* S = R - alpha*V */
+      size_t n = (size_t)w->lhs[r].nNo*(size_t)dof;
+      for (size_t e = 0; e < n; e++) S[r][e] = R[r][e] - alpha*V[r][e];
+    }
+    if (dof == 1) ora_sparmul_ss(w, K, CW(S), T);
+    else ora_sparmul_vv(w, dof, K, CW(S), T);
+    omega = ora_normv(w, dof, CW(T));
+    omega = ora_dotv(w, dof, CW(T), CW(S))/(omega*omega);
+    FOR_RANKS {
+      size_t n = (size_t)w->lhs[r].nNo*(size_t)dof;
+      for (size_t e = 0; e < n; e++) {
+        X[r][e] = X[r][e] + alpha*P[r][e] + omega*S[r][e];
+        R[r][e] = S[r][e] - omega*T[r][e];
+      }
+    }
+    errO = err;
+    err  = ora_normv(w, dof, CW(R));
+    rhoO = rho;
+    rho  = ora_dotv(w, dof, CW(R), CW(Rh));
+    beta = rho*alpha/(rhoO*omega);
+    FOR_RANKS {
+      size_t n = (size_t)w->lhs[r].nNo*(size_t)dof;
+      for (size_t e = 0; e < n; e++)
+        P[r][e] = R[r][e] + beta*(P[r][e] - omega*V[r][e]);
+    }
+  }
+  wv_copy(w, dof, R, CW(X));
+  ls->itr   = i - 1;
+  ls->fNorm = err;
+  ls->callD = ora_wtime() - t0;
+  if (errO < DBL_EPSILON) ls->dB = 0.0;
+  else ls->dB = 10.0*log(err/errO);
+#undef CW
+  wv_free(w, P); wv_free(w, Rh); wv_free(w, X); wv_free(w, V); wv_free(w, S); wv_free(w, T);
+}
+
+/* ================================================================== */
 /* L/CGRAD.f:51-123 CGRAD_SCHUR: operator L.p - D.(G.p) (+ PRE correction) */
 static void cgrad_schur(ora_world_t *w, ora_subls_t *ls, int dof,
                         const double *const *D, const double *const *G,
@@ -1246,6 +1434,10 @@ void ora_fsils_solve(ora_world_t *w, ora_ls_t *ls, int dof, double *const *Ri,
                      const double *res) {
   double **R = wv_alloc(w, dof), **Wc = wv_alloc(w, dof);
   int nFaces = w->lhs[0].nFaces;
+  if (prec != ORA_PRECOND_FSILS && prec != ORA_PRECOND_RCS) {
+    /* L/SOLVE.f:104-107 only prints and carries on with an undefined Wc */
+    fprintf(stderr, "FSILS: this preconditioner is not supported\n"); abort();
+  }
 
   FOR_RANKS {
     ora_lhs_t *lhs = &w->lhs[r];
@@ -1276,7 +1468,9 @@ void ora_fsils_solve(ora_world_t *w, ora_ls_t *ls, int dof, double *const *Ri,
   if (prec == ORA_PRECOND_FSILS) {
     preconddiag(w, dof, Val, R, Wc);
   } else {
-    fprintf(stderr, "oracle: only PRECOND_FSILS is restated\n"); abort();
+    double **Wr = wv_alloc(w, dof);
+    precondrcs(w, dof, Val, R, Wr, Wc);
+    wv_free(w, Wr);
   }
 
   switch (ls->LS_type) {
@@ -1289,8 +1483,11 @@ void ora_fsils_solve(ora_world_t *w, ora_ls_t *ls, int dof, double *const *Ri,
   case ORA_LS_TYPE_CG:
     cgrad(w, &ls->RI, dof, (const double *const *)Val, R);
     break;
+  case ORA_LS_TYPE_BICGS:
+    bicgs(w, &ls->RI, dof, (const double *const *)Val, R);
+    break;
   default:
-    fprintf(stderr, "oracle: LS_type %d not restated\n", ls->LS_type); abort();
+    fprintf(stderr, "FSILS: LS_type not defined\n"); abort();
   }
 
   FOR_RANKS {

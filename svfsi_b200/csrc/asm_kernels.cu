@@ -21,6 +21,7 @@
 //    elements of a colour share a node: deterministic).
 #include <cuda_runtime.h>
 #include <float.h>
+#include <stdlib.h>
 
 #include "ctx.h"
 #include "kernels.h"
@@ -115,13 +116,21 @@ __device__ __forceinline__ void red_add(double *p, double v) { atomicAdd(p, v); 
 // ---------------------------------------------------------------------------
 // Phase 1 for one element: gather, GNN, the four Gauss points reduced to the compact record.
 // rec[f * NEP] receives field f (the caller's shared-memory slot).
-__device__ __forceinline__ void fluid_elem_record(const FluidPar &par, int e,
-                                                  const int *__restrict__ ien,
-                                                  const double *__restrict__ x,
-                                                  const double *__restrict__ Ag,
-                                                  const double *__restrict__ Yg,
-                                                  const double *__restrict__ Bf, double *rec,
-                                                  int *nodeOut, int *__restrict__ badJac) {
+// Gauss-point sums of one element, before they are folded into the 80-double record
+struct ElemAcc {
+  double Nx[4][3];
+  double A[4][4], c2[4], r2[4], sTC, sTM;
+  double sRM[3][3], sNrV[4][3], lR4[4];
+  double w, wl, wr;
+};
+
+__device__ __forceinline__ void fluid_elem_compute(const FluidPar &par, int e,
+                                                   const int *__restrict__ ien,
+                                                   const double *__restrict__ x,
+                                                   const double *__restrict__ Ag,
+                                                   const double *__restrict__ Yg,
+                                                   const double *__restrict__ Bf, ElemAcc &acc,
+                                                   int *nodeOut, int *__restrict__ badJac) {
     const double gs = (5.0 + 3.0 * sqrt(5.0)) / 20.0, gt = (5.0 - sqrt(5.0)) / 20.0;
     int nd[4];
     {
@@ -294,29 +303,70 @@ __device__ __forceinline__ void fluid_elem_record(const FluidPar &par, int e,
                                rho * tauM * uaNx[a] * (rho * uNx[b]));
     }
 
-    // store the compact record
+    // hand the sums to the caller
 #pragma unroll
     for (int a = 0; a < 4; a++) {
 #pragma unroll
-      for (int i = 0; i < 3; i++) rec[(a * 8 + N_NX + i) * NEP] = Nx[a][i];
-      rec[(a * 8 + N_C2) * NEP] = rho * c2[a];
-      rec[(a * 8 + N_STC) * NEP] = sTC;
-      rec[(a * 8 + N_WL) * NEP] = wl;
-      rec[(a * 8 + N_STM) * NEP] = sTM;
-      rec[(a * 8 + N_R2) * NEP] = rho * r2[a];
+      for (int i = 0; i < 3; i++) { acc.Nx[a][i] = Nx[a][i]; acc.sNrV[a][i] = sNrV[a][i]; }
+#pragma unroll
+      for (int b = 0; b < 4; b++) acc.A[a][b] = A[a][b];
+      acc.c2[a] = c2[a]; acc.r2[a] = r2[a]; acc.lR4[a] = lR4[a];
+    }
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+      for (int i = 0; i < 3; i++) acc.sRM[j][i] = sRM[j][i];
+    acc.sTC = sTC; acc.sTM = sTM; acc.w = w; acc.wl = wl; acc.wr = wr;
+}
+
+// Fold the sums into the compact record.  PH < 0: all 80 fields, field f at rec[f*NEP];
+// PH = 0/1: only fields [40 PH, 40 PH + 40), field f at rec[(f - 40 PH)*NEP] (two-pass staging
+// through half the shared memory).  f is a compile-time constant at every store.
+template <int PH>
+__device__ __forceinline__ void rec_put(double *rec, int f, double v) {
+  if (PH < 0) rec[f * NEP] = v;
+  else if (f / 40 == PH) rec[(f - 40 * PH) * NEP] = v;
+}
+template <int PH>
+__device__ __forceinline__ void fluid_elem_store(const FluidPar &par, const ElemAcc &acc,
+                                                 double *rec) {
+  const double rho = par.rho, mu = par.mu;
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+#pragma unroll
+      for (int i = 0; i < 3; i++) rec_put<PH>(rec, a * 8 + N_NX + i, acc.Nx[a][i]);
+      rec_put<PH>(rec, a * 8 + N_C2, rho * acc.c2[a]);
+      rec_put<PH>(rec, a * 8 + N_STC, acc.sTC);
+      rec_put<PH>(rec, a * 8 + N_WL, acc.wl);
+      rec_put<PH>(rec, a * 8 + N_STM, acc.sTM);
+      rec_put<PH>(rec, a * 8 + N_R2, rho * acc.r2[a]);
 #pragma unroll
       for (int b = 0; b < 4; b++) {
-        const double nn = Nx[a][0] * Nx[b][0] + Nx[a][1] * Nx[b][1] + Nx[a][2] * Nx[b][2];
-        rec[(F_DE + (a * 4 + b) * 2) * NEP] = 4.0 * (mu * nn) + A[a][b];
-        rec[(F_DE + (a * 4 + b) * 2 + 1) * NEP] = sTM * nn;
+        const double nn = acc.Nx[a][0] * acc.Nx[b][0] + acc.Nx[a][1] * acc.Nx[b][1] +
+                          acc.Nx[a][2] * acc.Nx[b][2];
+        rec_put<PH>(rec, F_DE + (a * 4 + b) * 2, 4.0 * (mu * nn) + acc.A[a][b]);
+        rec_put<PH>(rec, F_DE + (a * 4 + b) * 2 + 1, acc.sTM * nn);
       }
 #pragma unroll
       for (int i = 0; i < 3; i++)
-        rec[(F_LR + a * 4 + i) * NEP] =
-            wr * sNrV[a][i] +
-            w * (Nx[a][0] * sRM[0][i] + Nx[a][1] * sRM[1][i] + Nx[a][2] * sRM[2][i]);
-      rec[(F_LR + a * 4 + 3) * NEP] = w * lR4[a];
+        rec_put<PH>(rec, F_LR + a * 4 + i,
+                    acc.wr * acc.sNrV[a][i] +
+                        acc.w * (acc.Nx[a][0] * acc.sRM[0][i] + acc.Nx[a][1] * acc.sRM[1][i] +
+                                 acc.Nx[a][2] * acc.sRM[2][i]));
+      rec_put<PH>(rec, F_LR + a * 4 + 3, acc.w * acc.lR4[a]);
     }
+}
+
+__device__ __forceinline__ void fluid_elem_record(const FluidPar &par, int e,
+                                                  const int *__restrict__ ien,
+                                                  const double *__restrict__ x,
+                                                  const double *__restrict__ Ag,
+                                                  const double *__restrict__ Yg,
+                                                  const double *__restrict__ Bf, double *rec,
+                                                  int *nodeOut, int *__restrict__ badJac) {
+  ElemAcc acc;
+  fluid_elem_compute(par, e, ien, x, Ag, Yg, Bf, acc, nodeOut, badJac);
+  fluid_elem_store<-1>(par, acc, rec);
 }
 
 // The pair of tangent entries (row i = q>>1, columns 2(q&1), 2(q&1)+1) of block (a,b) that lane q
@@ -479,6 +529,85 @@ __global__ void __launch_bounds__(256) fluid_gather_val_kernel(int nnz, double m
   __stcs((double2 *)(Val + (size_t)p * 16) + q, make_double2(acc0, acc1));
 }
 
+// Kernel A, second version: register budget capped at 128 (four CTAs of 128 threads per SM instead
+// of two) and the record staged through shared memory in two halves of 40 fields, so that the
+// staging buffer (41 KB per CTA) no longer limits residency.
+__global__ void __launch_bounds__(NE, 4) fluid_record2_kernel(FluidPar par, int n,
+                                                              const int *__restrict__ ien,
+                                                              const double *__restrict__ x,
+                                                              const double *__restrict__ Ag,
+                                                              const double *__restrict__ Yg,
+                                                              const double *__restrict__ Bf,
+                                                              double *__restrict__ elemP,
+                                                              int *__restrict__ badJac) {
+  extern __shared__ double sm[];  // [40][NEP]
+  const int slot = threadIdx.x;
+  const int e = blockIdx.x * NE + slot;
+  int nodes[4];
+  ElemAcc acc;
+  if (e < n) fluid_elem_compute(par, e, ien, x, Ag, Yg, Bf, acc, nodes, badJac);
+  const int nHere = min(NE, n - blockIdx.x * NE);
+  double *out = elemP + (size_t)blockIdx.x * NE * F_COUNT;
+  if (e < n) fluid_elem_store<0>(par, acc, sm + slot);
+  __syncthreads();
+  for (int t = threadIdx.x; t < nHere * 40; t += NE) {
+    const int s = t / 40, f = t - s * 40;
+    out[s * F_COUNT + f] = sm[f * NEP + s];
+  }
+  __syncthreads();
+  if (e < n) fluid_elem_store<1>(par, acc, sm + slot);
+  __syncthreads();
+  for (int t = threadIdx.x; t < nHere * 40; t += NE) {
+    const int s = t / 40, f = t - s * 40;
+    out[s * F_COUNT + 40 + f] = sm[f * NEP + s];
+  }
+}
+
+// Kernel B, second version: one CTA walks a whole chunk of GCH = 512 consecutive (length-sorted)
+// blocks in 16 rounds of 32 groups, so that the ~34 block rows of a chunk -- whose element records
+// overlap 16-fold -- are gathered through ONE SM's L1; two contributions are in flight per lane.
+static constexpr int GCH = 512;
+__global__ void __launch_bounds__(256, 5) fluid_gather_val2_kernel(int nnz, double mu4,
+                                                                   const int *__restrict__ blkOrder,
+                                                                   const int *__restrict__ adjPtr,
+                                                                   const int *__restrict__ adj,
+                                                                   const double *__restrict__ elemP,
+                                                                   double *__restrict__ Val) {
+  const int lane = threadIdx.x & 31, q = lane & 7;
+  const unsigned gmask = 0xFFu << (lane & 24);
+  const int grp = threadIdx.x >> 3;
+  const int base0 = blockIdx.x * GCH;
+#pragma unroll 1
+  for (int it = 0; it < GCH / 32; it++) {
+    const int g = base0 + it * 32 + grp;
+    if (g >= nnz) break;   // whole 8-lane groups leave together
+    const int p = blkOrder ? __ldg(blkOrder + g) : g;
+    const int s = __ldg(adjPtr + p), e = __ldg(adjPtr + p + 1);
+    double acc0 = 0.0, acc1 = 0.0;
+    for (int base = s; base < e; base += 8) {
+      const int mine = base + q;
+      const int cq = (mine < e) ? __ldg(adj + mine) : 0;
+      const int cnt = min(8, e - base);
+      int k = 0;
+      for (; k + 1 < cnt; k += 2) {
+        const int pa = __shfl_sync(gmask, cq, k, 8), pb = __shfl_sync(gmask, cq, k + 1, 8);
+        double a0, a1, b0, b1;
+        tangent_pair<1>(elemP + (size_t)(pa >> 4) * F_COUNT, (pa >> 2) & 3, pa & 3, q, mu4, a0, a1);
+        tangent_pair<1>(elemP + (size_t)(pb >> 4) * F_COUNT, (pb >> 2) & 3, pb & 3, q, mu4, b0, b1);
+        acc0 += a0; acc1 += a1;      // ascending element order, as the reference's element loop
+        acc0 += b0; acc1 += b1;
+      }
+      if (k < cnt) {
+        const int pa = __shfl_sync(gmask, cq, k, 8);
+        double a0, a1;
+        tangent_pair<1>(elemP + (size_t)(pa >> 4) * F_COUNT, (pa >> 2) & 3, pa & 3, q, mu4, a0, a1);
+        acc0 += a0; acc1 += a1;
+      }
+    }
+    __stcs((double2 *)(Val + (size_t)p * 16) + q, make_double2(acc0, acc1));
+  }
+}
+
 __global__ void __launch_bounds__(256) fluid_gather_r_kernel(int nNo, const int *__restrict__ adjPtr,
                                                              const int *__restrict__ adj,
                                                              const double *__restrict__ elemP,
@@ -501,6 +630,8 @@ static void fluid_attr_once() {
   cudaFuncSetAttribute(fluid_asm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaFuncSetAttribute(fluid_asm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaFuncSetAttribute(fluid_record_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(fluid_record2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)((size_t)40 * NEP * sizeof(double)));
   attr = true;
 }
 
@@ -521,20 +652,60 @@ void launch_fluid_asm(cudaStream_t st, const FluidPar &par, int n, int e0, const
                                                       R, Val, badJac);
 }
 
+// bit 0: record kernel v2 (128 registers, two-pass staging); bit 1: chunked gather kernel.
+// Default = 0 (both measured SLOWER on B200, profiles/r01_asm_variants.md); SVFSI_ASM_TUNE overrides (used by the kernel-variant timings in profiles/).
+int asm_tune() {
+  static int t = -1;
+  if (t < 0) {
+    const char *e = getenv("SVFSI_ASM_TUNE");
+    t = e ? atoi(e) : 0;
+  }
+  return t;
+}
+
+void launch_fluid_gather_parts(cudaStream_t st, int parts, const FluidPar &par, int nEl, int nNo,
+                               int nnz, const int *ien, const double *x, const double *Ag,
+                               const double *Yg, const double *Bf, double *elemP,
+                               const int *blkOrder, const int *blkAdjPtr, const int *blkAdj,
+                               const int *nodeAdjPtr, const int *nodeAdj, double *R, double *Val,
+                               int *badJac, int tune) {
+  if (nEl <= 0) return;
+  fluid_attr_once();
+  if (parts & 1) {
+    count_launch();
+    if (tune & 1) {
+      const size_t smem = (size_t)40 * NEP * sizeof(double);
+      fluid_record2_kernel<<<(nEl + NE - 1) / NE, NE, smem, st>>>(par, nEl, ien, x, Ag, Yg, Bf,
+                                                                  elemP, badJac);
+    } else {
+      const size_t smem = (size_t)F_COUNT * NEP * sizeof(double);
+      fluid_record_kernel<<<(nEl + NE - 1) / NE, NE, smem, st>>>(par, nEl, ien, x, Ag, Yg, Bf,
+                                                                 elemP, badJac);
+    }
+  }
+  if (parts & 2) {
+    count_launch();
+    if (tune & 2)
+      fluid_gather_val2_kernel<<<(unsigned)((nnz + GCH - 1) / GCH), 256, 0, st>>>(
+          nnz, 4.0 * par.mu, blkOrder, blkAdjPtr, blkAdj, elemP, Val);
+    else
+      fluid_gather_val_kernel<<<(unsigned)(((size_t)nnz * 8 + 255) / 256), 256, 0, st>>>(
+          nnz, 4.0 * par.mu, blkOrder, blkAdjPtr, blkAdj, elemP, Val);
+  }
+  if (parts & 4) {
+    count_launch();
+    fluid_gather_r_kernel<<<(nNo * 4 + 255) / 256, 256, 0, st>>>(nNo, nodeAdjPtr, nodeAdj, elemP,
+                                                                 R);
+  }
+}
+
 void launch_fluid_gather(cudaStream_t st, const FluidPar &par, int nEl, int nNo, int nnz,
                          const int *ien, const double *x, const double *Ag, const double *Yg,
                          const double *Bf, double *elemP, const int *blkOrder,
                          const int *blkAdjPtr, const int *blkAdj, const int *nodeAdjPtr,
                          const int *nodeAdj, double *R, double *Val, int *badJac) {
-  if (nEl <= 0) return;
-  count_launch(3);
-  const size_t smem = (size_t)F_COUNT * NEP * sizeof(double);
-  fluid_attr_once();
-  fluid_record_kernel<<<(nEl + NE - 1) / NE, NE, smem, st>>>(par, nEl, ien, x, Ag, Yg, Bf, elemP,
-                                                             badJac);
-  fluid_gather_val_kernel<<<(unsigned)(((size_t)nnz * 8 + 255) / 256), 256, 0, st>>>(
-      nnz, 4.0 * par.mu, blkOrder, blkAdjPtr, blkAdj, elemP, Val);
-  fluid_gather_r_kernel<<<(nNo * 4 + 255) / 256, 256, 0, st>>>(nNo, nodeAdjPtr, nodeAdj, elemP, R);
+  launch_fluid_gather_parts(st, 7, par, nEl, nNo, nnz, ien, x, Ag, Yg, Bf, elemP, blkOrder,
+                            blkAdjPtr, blkAdj, nodeAdjPtr, nodeAdj, R, Val, badJac, asm_tune());
 }
 
 // ---------------------------------------------------------------------------

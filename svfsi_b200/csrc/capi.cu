@@ -676,10 +676,23 @@ int32_t gpu_time_kernel_(const int32_t *what, const int32_t *dof, const int32_t 
       else launch_multi_axpy_scale(c.stream, U, stride, w, n, kk, c.d_small + 64, nullptr, nullptr);
     }
     CUDA_TRY(cudaEventRecord(b, c.stream));
+  } else if (*what == 5) {
+    // one kernel of the gather assembly: k = part mask (1 records, 2 tangent gather, 4 residual
+    // gather), variant = kernel-variant mask (asm_tune()); uses the resident Ag / Yg state
+    if (!c.mesh || !c.d_Ag || !c.d_Yg || !c.d_elemP || !c.d_R || !c.d_Val)
+      return fail(SVFSI_ERR_STATE, "gpu_time_kernel_(5): run the gather assembly once first");
+    FluidPar par;
+    par.rho = 1.06; par.mu = 0.04; par.f[0] = par.f[1] = par.f[2] = 0.0;
+    par.dt = 5e-3; par.af = 1.0 / 1.2; par.am = 0.5 * 2.8 / 1.2; par.gam = 0.5 + par.am - par.af;
+    CUDA_TRY(cudaEventRecord(a, c.stream));
+    for (int r = 0; r < *reps; r++)
+      launch_fluid_gather_parts(c.stream, *k, par, c.nEl, c.nNo, c.nnz, c.d_ien, c.d_x, c.d_Ag,
+                                c.d_Yg, nullptr, c.d_elemP, c.d_blkOrder, c.d_blkAdjPtr, c.d_blkAdj,
+                                c.d_nodeAdjPtr, c.d_nodeAdj, c.d_R, c.d_Val, c.d_flag, *variant);
+    CUDA_TRY(cudaEventRecord(b, c.stream));
   } else {
     return fail(SVFSI_ERR_ARG, "gpu_time_kernel_: unknown kernel id");
   }
-  (void)variant;
   CUDA_TRY(cudaEventSynchronize(b));
   float ms = 0.f;
   CUDA_TRY(cudaEventElapsedTime(&ms, a, b));

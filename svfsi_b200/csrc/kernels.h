@@ -112,6 +112,9 @@ void launch_w_dirichlet(cudaStream_t st, int nFaceNo, int fdof, int dof, const i
                         const double *val, double *W);
 void launch_scale_val(cudaStream_t st, int nnz, int dof, const int *rowOf, const int *col,
                       const double *W, double *Val);
+// Val = (Wrow_row * Val) * Wcol_col: PREMUL(Wrow) then POSMUL(Wcol) (L/PRECOND.f:372-489) fused
+void launch_scale_val2(cudaStream_t st, int nnz, int dof, const int *rowOf, const int *col,
+                       const double *Wrow, const double *Wcol, double *Val);
 void launch_face_valM(cudaStream_t st, int nFaceNo, int fdof, int dof, const int *glob,
                       const double *val, const double *W, double *valM);
 // ADDBCMUL (L/ADDBCMUL.f): S = sum_a sum_i valM(i,a) X(i,glob(a)) over nodes with glob < ownedLimit
@@ -152,6 +155,15 @@ void launch_fluid_gather(cudaStream_t st, const FluidPar &par, int nEl, int nNo,
                          const double *Bf, double *elemP, const int *blkOrder,
                          const int *blkAdjPtr, const int *blkAdj, const int *nodeAdjPtr,
                          const int *nodeAdj, double *R, double *Val, int *badJac);
+// the three kernels separately (parts: 1 records, 2 tangent gather, 4 residual gather) with an
+// explicit kernel-variant mask (see asm_tune()); used by gpu_time_kernel_
+void launch_fluid_gather_parts(cudaStream_t st, int parts, const FluidPar &par, int nEl, int nNo,
+                               int nnz, const int *ien, const double *x, const double *Ag,
+                               const double *Yg, const double *Bf, double *elemP,
+                               const int *blkOrder, const int *blkAdjPtr, const int *blkAdj,
+                               const int *nodeAdjPtr, const int *nodeAdj, double *R, double *Val,
+                               int *badJac, int tune);
+int asm_tune();
 // adjacency lists for the gather variant (built once at gpu_mesh_create_)
 int build_gather_adjacency(cudaStream_t st, int nEl, int nNo, int nnz, const int *ien,
                            const int *edest, int **blkAdjPtr, int **blkAdj, int **nodeAdjPtr,

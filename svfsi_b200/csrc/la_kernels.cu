@@ -621,14 +621,15 @@ __global__ void w_dirichlet_kernel(int nFaceNo, int fdof, int dof, const int *__
 // K = (W_row K) W_col fused (PREMUL then POSMUL, same multiplication order per entry)
 __global__ void __launch_bounds__(256) scale_val4_kernel(int nnz, const int *__restrict__ rowOf,
                                                           const int *__restrict__ col,
-                                                          const double *__restrict__ W,
+                                                          const double *__restrict__ Wrow,
+                                                          const double *__restrict__ Wcol,
                                                           double2 *__restrict__ Val) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t)nnz * 8) return;
   const int p = (int)(t >> 3), q = (int)(t & 7);
   const int i = q >> 1, k0 = (q & 1) * 2;
-  const double wr = __ldg(W + (size_t)__ldg(rowOf + p) * 4 + i);
-  const double2 wc = __ldg((const double2 *)(W + (size_t)__ldg(col + p) * 4 + k0));
+  const double wr = __ldg(Wrow + (size_t)__ldg(rowOf + p) * 4 + i);
+  const double2 wc = __ldg((const double2 *)(Wcol + (size_t)__ldg(col + p) * 4 + k0));
   double2 v = Val[t];
   v.x = (v.x * wr) * wc.x;
   v.y = (v.y * wr) * wc.y;
@@ -636,13 +637,14 @@ __global__ void __launch_bounds__(256) scale_val4_kernel(int nnz, const int *__r
 }
 __global__ void scale_val_generic_kernel(int nnz, int dof, const int *__restrict__ rowOf,
                                          const int *__restrict__ col,
-                                         const double *__restrict__ W, double *__restrict__ Val) {
+                                         const double *__restrict__ Wrow,
+                                         const double *__restrict__ Wcol, double *__restrict__ Val) {
   const int dd = dof * dof;
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t)nnz * dd) return;
   const int p = (int)(t / dd), r = (int)(t - (size_t)p * dd);
   const int i = r / dof, k = r - i * dof;
-  Val[t] = (Val[t] * W[(size_t)rowOf[p] * dof + i]) * W[(size_t)col[p] * dof + k];
+  Val[t] = (Val[t] * Wrow[(size_t)rowOf[p] * dof + i]) * Wcol[(size_t)col[p] * dof + k];
 }
 __global__ void face_valM_kernel(int nFaceNo, int fdof, int dof, const int *__restrict__ glob,
                                  const double *__restrict__ val, const double *__restrict__ W,
@@ -669,18 +671,22 @@ void launch_w_dirichlet(cudaStream_t st, int nFaceNo, int fdof, int dof, const i
   count_launch();
   w_dirichlet_kernel<<<(nFaceNo + 255) / 256, 256, 0, st>>>(nFaceNo, fdof, dof, glob, val, W);
 }
-void launch_scale_val(cudaStream_t st, int nnz, int dof, const int *rowOf, const int *col,
-                      const double *W, double *Val) {
+void launch_scale_val2(cudaStream_t st, int nnz, int dof, const int *rowOf, const int *col,
+                       const double *Wrow, const double *Wcol, double *Val) {
   count_launch();
   if (dof == 4) {
     size_t tot = (size_t)nnz * 8;
-    scale_val4_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(nnz, rowOf, col, W,
+    scale_val4_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(nnz, rowOf, col, Wrow, Wcol,
                                                                      (double2 *)Val);
   } else {
     size_t tot = (size_t)nnz * dof * dof;
     scale_val_generic_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(nnz, dof, rowOf, col,
-                                                                            W, Val);
+                                                                            Wrow, Wcol, Val);
   }
+}
+void launch_scale_val(cudaStream_t st, int nnz, int dof, const int *rowOf, const int *col,
+                      const double *W, double *Val) {
+  launch_scale_val2(st, nnz, dof, rowOf, col, W, W, Val);
 }
 void launch_face_valM(cudaStream_t st, int nFaceNo, int fdof, int dof, const int *glob,
                       const double *val, const double *W, double *valM) {

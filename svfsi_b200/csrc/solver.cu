@@ -129,12 +129,12 @@ __global__ void cg_err_kernel(KrylovCtl *ctl, const double *rr, int mItr, volati
   ctl->ilast += 1;  // completed iterations
   // the reference still updates P before leaving the loop at the next trip's test;
   // P is dead after that, so stopping here gives the same X, R, err, itr
-  if (e < ctl->eps) {
+  // (if this was trip mItr the loop ends without the test: suc stays .FALSE., L/CGRAD.f:150-154)
+  if (ctl->ilast < mItr && e < ctl->eps) {
     ctl->suc = 1;
     ctl->done = 1;
   }
   }
-  (void)mItr;
   *pubFlag = ctl->done;
   __threadfence_system();
   *pubProgress = seq;
@@ -687,8 +687,9 @@ int fsils_solve_dev(svfsi_ls_t *ls, int dof, int prec, const int32_t *incL, cons
       f.coupled = true;
     }
   }
-  if (prec != SVFSI_PRECOND_FSILS)
-    return fail(SVFSI_ERR_UNSUPPORTED, "only PRECOND_FSILS (diagonal) is implemented");
+  if (prec != SVFSI_PRECOND_FSILS && prec != SVFSI_PRECOND_RCS)
+    return fail(SVFSI_ERR_UNSUPPORTED,
+                "FSILS: this linear solver and preconditioner combination is not supported");
   if (int rc = ensure_small()) return rc;
 
   ProfScope ps(PROF_SOLVE);
@@ -701,13 +702,26 @@ int fsils_solve_dev(svfsi_ls_t *ls, int dof, int prec, const int32_t *incL, cons
     CUDA_TRY(cudaMalloc(&d_W, wNeed));
     wCap = wNeed;
   }
-  if (int rc = preconddiag(dof, c.d_Val, c.d_R, d_W)) return rc;
+  if (prec == SVFSI_PRECOND_FSILS) {
+    if (int rc = preconddiag(dof, c.d_Val, c.d_R, d_W)) return rc;
+  } else {
+    static double *d_rcs = nullptr;   // Wr, Wc, W1 of PRECONDRCS
+    static size_t rcsCap = 0;
+    const size_t need = 3 * padded((size_t)c.nNo * dof);
+    if (rcsCap < need) {
+      if (d_rcs) cudaFree(d_rcs);
+      CUDA_TRY(cudaMalloc(&d_rcs, need));
+      rcsCap = need;
+    }
+    if (int rc = precondrcs(dof, c.d_Val, c.d_R, d_W, d_rcs)) return rc;
+  }
 
   int rc = 0;
   switch (ls->LS_type) {
     case SVFSI_LS_TYPE_NS: rc = nssolver_dev(ls, dof, c.d_Val, c.d_R); break;
     case SVFSI_LS_TYPE_GMRES: rc = gmres_inplace(&ls->RI, dof, c.d_Val, c.d_R, dof == 1); break;
     case SVFSI_LS_TYPE_CG: rc = cgrad(&ls->RI, dof, c.d_Val, c.d_R); break;
+    case SVFSI_LS_TYPE_BICGS: rc = bicgs(&ls->RI, dof, c.d_Val, c.d_R); break;
     default: rc = fail(SVFSI_ERR_UNSUPPORTED, "FSILS: LS_type not implemented on the device");
   }
   if (rc) return rc;

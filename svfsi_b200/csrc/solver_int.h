@@ -55,4 +55,8 @@ size_t cg_schur_work(size_t nNo, int dof);
 int cgrad_schur(svfsi_subls_t *ls, int dof, const double *D, const double *G, const double *L,
                 double *R, double *work, double *scal);
 
+// bicgs_rcs.cu: BICGSS/BICGSV (L/BICGS.f:50-180) and PRECONDRCS (L/PRECOND.f:150-368)
+int bicgs(svfsi_subls_t *ls, int dof, const double *K, double *R);
+int precondrcs(int dof, double *Val, double *R, double *W2, double *work);
+
 }  // namespace svfsi

@@ -61,17 +61,22 @@ def oracle_commu(w, probs, Rs, dof=4):
 
 
 def oracle_gmres_global(nparts, relTol, sD, mItr, res_out, dims=(8, 8, 20), L=4.0,
-                        ls_type=None, **lskw):
+                        ls_type=None, prec=ora.PRECOND_FSILS, perturb=None, **lskw):
     """Assemble + COMMU + FSILS_SOLVE with the oracle on `nparts` simulated ranks; returns
     (ls, X_global) with X gathered by global node id."""
     m, probs, _ = mesh.build_problem(*dims, nparts=nparts, L=L)
     Rs, Vs = oracle_assemble(probs)
+    if perturb is not None:      # rounding-level relative noise on the assembled system
+        rng = np.random.default_rng(perturb)
+        Vs = [v * (1.0 + 2e-16 * rng.standard_normal(v.shape)) for v in Vs]
+        Rs = [r * (1.0 + 2e-16 * rng.standard_normal(r.shape)) for r in Rs]
     w = oracle_world(probs, m.nNo)
     Rc = oracle_commu(w, probs, Rs)
     ls = ora.ls_create(ls_type or ora.LS_TYPE_GMRES, relTol=relTol, absTol=1e-14, maxItr=mItr,
                        dimKry=sD, **{k: v for k, v in lskw.items() if v is not None})
     X = [r.copy() for r in Rc]
-    w.solve(ls, 4, X, [v.copy() for v in Vs], incL=[1, 1, 1], res=np.array([0.0, 0.0, res_out]))
+    w.solve(ls, 4, X, [v.copy() for v in Vs], prec=prec, incL=[1, 1, 1],
+            res=np.array([0.0, 0.0, res_out]))
     G = np.zeros((m.nNo, 4))
     for p, x in zip(probs, X):
         G[p.rm.ltg - 1] = x
@@ -86,6 +91,21 @@ def reference_reproducibility_floor(relTol, sD, mItr, res_out, ls_type=None, **k
     fx = ff = 0.0; di = 0
     for k in (2, 3):
         lsk, Gk = oracle_gmres_global(k, relTol, sD, mItr, res_out, ls_type=ls_type, **kw)
+        fx = max(fx, float(np.linalg.norm(Gk - G1) / np.linalg.norm(G1)))
+        ff = max(ff, abs(lsk.RI.fNorm - ls1.RI.fNorm) / ls1.RI.fNorm)
+        di = max(di, abs(lsk.RI.itr - ls1.RI.itr))
+    return fx, ff, di
+
+
+def rounding_floor(relTol, sD, mItr, res_out, ls_type=None, seeds=(1, 2, 3), **kw):
+    """Same idea as reference_reproducibility_floor but partition-independent: how far the
+    reference algorithm (oracle, 1 rank) moves when the assembled R / Val are perturbed by one
+    ulp of relative noise -- the size of the difference between any two correct FP64 evaluations
+    of the element loop.  Returns (floor on ||dX||/||X||, floor on |d fNorm|/fNorm, max |d itr|)."""
+    ls1, G1 = oracle_gmres_global(1, relTol, sD, mItr, res_out, ls_type=ls_type, **kw)
+    fx = ff = 0.0; di = 0
+    for sd in seeds:
+        lsk, Gk = oracle_gmres_global(1, relTol, sD, mItr, res_out, ls_type=ls_type, perturb=sd, **kw)
         fx = max(fx, float(np.linalg.norm(Gk - G1) / np.linalg.norm(G1)))
         ff = max(ff, abs(lsk.RI.fNorm - ls1.RI.fNorm) / ls1.RI.fNorm)
         di = max(di, abs(lsk.RI.itr - ls1.RI.itr))

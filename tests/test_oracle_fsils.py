@@ -186,3 +186,110 @@ def test_golden_two_rank_pipe():
         st = g[f"{tag}_stats"]
         assert (ls.RI.itr, ls.RI.suc) == (int(st[0]), int(st[1]))
         assert np.allclose(X[0], g[f"{tag}_X0"], rtol=0, atol=1e-9 * np.abs(g[f"{tag}_X0"]).max())
+
+
+# ---------------------------------------------------------------------------------------------
+# BICGSV/BICGSS (L/BICGS.f) and PRECONDRCS (L/PRECOND.f:150-368)
+def _rcs_reference(K, dir_mask, maxiter=10, tol=2.0):
+    """independent NumPy/SciPy restatement of PRECONDRCS on the scalar CSR expansion of the matrix:
+    returns (scaled matrix, W1, W2).  dir_mask[i] = True where dof i is a Dirichlet dof."""
+    n = K.shape[0]
+    keep = (~dir_mask).astype(float)
+    A = sp.diags(keep) @ K @ sp.diags(keep)
+    A = A.tolil()
+    for i in np.nonzero(dir_mask)[0]:
+        A[i, i] = 1.0
+    A = A.tocsr()
+    W1 = np.ones(n); W2 = np.ones(n)
+    it, flag = 0, True
+    while flag:
+        it += 1
+        if it >= maxiter:
+            flag = False
+        B = abs(A)
+        wr = np.asarray(B.max(axis=1).todense()).reshape(-1)
+        wc = np.asarray(B.max(axis=0).todense()).reshape(-1)
+        if np.abs(1 - wr).max() < tol and np.abs(1 - wc).max() < tol:
+            flag = False
+        wr = 1 / np.sqrt(wr); wc = 1 / np.sqrt(wc)
+        A = (sp.diags(wr) @ A @ sp.diags(wc)).tocsr()
+        W1 *= wr; W2 *= wc
+    return A, W1, W2
+
+
+@pytest.mark.parametrize("ls_type,prec,kw", [
+    (ora.LS_TYPE_BICGS, ora.PRECOND_FSILS, dict(relTol=1e-8, maxItr=400)),
+    (ora.LS_TYPE_BICGS, ora.PRECOND_RCS, dict(relTol=1e-8, maxItr=400)),
+    (ora.LS_TYPE_GMRES, ora.PRECOND_RCS, dict(relTol=1e-7, maxItr=10, dimKry=80)),
+])
+def test_bicgs_and_rcs_solve_the_unscaled_system(pipe, ls_type, prec, kw):
+    """x returned by FSILS_SOLVE solves K x = R on the free dofs whatever the preconditioner:
+    checked through the UNscaled matrix against a SciPy direct solve."""
+    import scipy.sparse.linalg as spl
+    m, p, R, V = pipe
+    w = cm.oracle_world([p], m.nNo)
+    ls = ora.ls_create(ls_type, absTol=1e-14, **kw)
+    X = R.copy()
+    Vs = V.copy()
+    w.solve(ls, 4, [X], [Vs], prec=prec, incL=[1, 1, 1], res=[0.0, 0.0, 0.0])
+    assert ls.RI.suc and ls.RI.itr > 3
+    free = _free_mask(p).reshape(-1)
+    assert np.abs(X.reshape(-1)[~free]).max() == 0.0
+    K = bsr(p, V, 4)
+    xs = np.zeros(free.size)
+    xs[free] = spl.spsolve(K[free][:, free].tocsc(), R.reshape(-1)[free])
+    assert np.linalg.norm(X.reshape(-1) - xs) / np.linalg.norm(xs) < 2e-5
+    if prec == ora.PRECOND_RCS:
+        # Val left behind = the equilibrated matrix: identity on the Dirichlet dofs, every row and
+        # column max within (1/3, 3) unless the 10-sweep cap hit; equals the SciPy restatement
+        A, W1, W2 = _rcs_reference(K, ~free)
+        S = bsr(p, Vs, 4)
+        # (the reference rewrites EVERY diagonal entry as Wr*(Val-1)+1, L/PRECOND.f:203-237: on free
+        #  dofs that is (Val-1)+1, an absolute 1e-16 perturbation of diagonals that may be ~1e-4)
+        assert abs(S - A).max() < 1e-10 * abs(A).max()
+
+
+def test_bicgs_scalar_heat_matches_direct_solve():
+    m, probs, _ = mesh.build_problem(6, 6, 8, nparts=1, L=2.0)
+    p = probs[0]
+    rng = np.random.default_rng(5)
+    par = ora.heat_par(1.0, 0.5, 1.0, 1e-2, cm.GA["af"], cm.GA["am"], cm.GA["gam"])
+    R, V = ora.construct_heats(par, p.rm.IEN, p.rm.x, rng.standard_normal(p.rm.nNo),
+                               rng.standard_normal(p.rm.nNo), p.rowPtr, p.colPtr)
+    import scipy.sparse.linalg as spl
+    A = sp.csr_matrix((V, p.colPtr - 1, p.rowPtr - 1), shape=(p.rm.nNo,) * 2)
+    free = np.ones(p.rm.nNo, bool); free[p.faces["inlet"]["gN"] - 1] = False
+    xs = np.zeros(p.rm.nNo)
+    xs[free] = spl.spsolve(A[free][:, free].tocsc(), R[free])
+    for prec in (ora.PRECOND_FSILS, ora.PRECOND_RCS):
+        w = ora.World(m.nNo, [p.rm.ltg], [p.rowPtr], [p.colPtr], 1)
+        w.bc_create(1, [p.faces["inlet"]["gN"]], 1, ora.BC_TYPE_Dir, None)
+        ls = ora.ls_create(ora.LS_TYPE_BICGS, relTol=1e-10, absTol=1e-14, maxItr=500)
+        X = R.copy()
+        w.solve(ls, 1, [X], [V.copy()], prec=prec, incL=[1], res=None)
+        assert ls.RI.suc
+        assert np.linalg.norm(X - xs) / np.linalg.norm(xs) < 1e-7
+
+
+@pytest.mark.parametrize("nparts", [2, 3])
+def test_bicgs_rcs_partition_independence(nparts):
+    """k simulated ranks == 1 rank for BICGS + RCS.  Shared rows see the SUM of the per-rank row
+    maxima (FSILS_COMMUV on Wr/Wc, L/PRECOND.f:320-321), so the scaling differs between
+    partitions but the un-scaled solution does not."""
+    dims, L = (4, 4, 12), 3.0
+    out = []
+    for k in (1, nparts):
+        m, probs, _ = mesh.build_problem(*dims, nparts=k, L=L)
+        Rs, Vs = cm.oracle_assemble(probs)
+        w = cm.oracle_world(probs, m.nNo)
+        Rc = cm.oracle_commu(w, probs, Rs)
+        ls = ora.ls_create(ora.LS_TYPE_BICGS, relTol=1e-9, absTol=1e-14, maxItr=400)
+        X = [r.copy() for r in Rc]
+        w.solve(ls, 4, X, [v.copy() for v in Vs], prec=ora.PRECOND_RCS, incL=[1, 1, 1],
+                res=np.array([0.0, 0.0, 0.0]))
+        assert ls.RI.suc
+        G = np.zeros((m.nNo, 4))
+        for p, x in zip(probs, X):
+            G[p.rm.ltg - 1] = x
+        out.append(G)
+    assert np.linalg.norm(out[0] - out[1]) / np.linalg.norm(out[0]) < 1e-5

@@ -1,0 +1,25 @@
+#!/usr/bin/env python
+"""Times the three kernels of the gather assembly (records / tangent gather / residual gather)
+for every kernel variant on the bench pipe (GPU box only):  python tools/time_asm_variants.py [nz]"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from svfsi_b200 import api, mesh  # noqa: E402
+
+nz = int(sys.argv[1]) if len(sys.argv) > 1 else 408
+api.init(device=0, rank=0, nranks=1)
+gnNo, p = bench.setup_rank(api, mesh, (64, 64, nz), 0, 1)
+api.state_upload(4, p.Ag, p.Yg, None)
+bench.newton_step_dev(api, api.ASM_GATHER)
+api.sync()
+out = dict(nEl=int(p.rm.nEl), nnz=int(p.colPtr.size))
+for part, name in ((1, "record"), (2, "gather_val"), (4, "gather_r")):
+    for tune in (0, 3):
+        api.time_kernel(5, 4, part, 2, tune)
+        out[f"{name}_v{1 if tune else 0}_ms"] = api.time_kernel(5, 4, part, 10, tune) / 10
+print(json.dumps(out))
+api.finalize()

@@ -338,7 +338,11 @@ def main():
     # SURVEY.md 8d, per launch, this rank (NS solver: mixed shapes -> bytes of the K (3x3) SpMV only approx.)
     alg_bytes = nnz * (8 * dof * dof + 4) + nNo * (8 + 16 * dof)
     peak, peak_src = measured_peak()
-    achieved = alg_bytes / (spmv_ms / max(spmv_n, 1) * 1e-3) / 1e9 if spmv_n else None
+    # with neighbours every FSILS_SPARMUL is TWO launches of the same kernel (boundary rows, then
+    # interior rows while the halo is in flight): the roofline unit is the whole SpMV (both launches)
+    per_op = 2 if world > 1 else 1
+    spmv_ops = spmv_n / per_op
+    achieved = alg_bytes / (spmv_ms / max(spmv_ops, 1) * 1e-3) / 1e9 if spmv_n else None
     asm_ms, asm_n = prof["asm"]
     melem = (nEl * world) / (asm_ms / max(asm_n, 1) * 1e-3) / 1e6 if asm_n else None
     scatter_bytes = nEl * (16 + 4 * 14 * 8 + 2048 + 128)        # element-scatter model, SURVEY.md 8d
@@ -357,7 +361,8 @@ def main():
                                  achieved=achieved, peak=peak, unit="GB/s",
                                  frac=(achieved / peak) if achieved else None, peak_source=peak_src,
                                  traffic=None, algorithmic_bytes_per_launch=int(alg_bytes),
-                                 avg_launch_ms=spmv_ms / max(spmv_n, 1), launches=int(spmv_n)),
+                                 avg_launch_ms=spmv_ms / max(spmv_ops, 1), launches=int(spmv_n),
+                                 launches_per_spmv=per_op),
                    detail=dict(nEl_rank0=int(nEl), nNo_rank0=int(nNo), nnz_rank0=int(nnz),
                                gmres_spmv_count=int(ls.RI.itr), gmres_suc=int(ls.RI.suc), gm_itr=int(ls.GM.itr), cg_itr=int(ls.CG.itr),
                                iNorm=ls.RI.iNorm, fNorm=ls.RI.fNorm,

@@ -312,6 +312,31 @@ int reduce_allreduce(const double *partial, int k, double *out, const int *done)
   return nccl_allreduce_sum(out, (size_t)k, c.stream);
 }
 
+// the same followed by the GMRES column step; fused into one kernel on the single-rank and the
+// peer-memory paths, separate kernels on the NCCL fallback
+int reduce_allreduce_column(const double *partial, int k, double *out, const ColArgs &col,
+                            const int *done) {
+  Ctx &c = ctx();
+  if (k <= kArMax) {
+    if (c.nranks > 1 && c.p2p.on) {
+      ProfScope ps(PROF_ALLREDUCE);
+      c.p2p.arSeq++;
+      launch_p2p_allreduce(c.stream, p2p_dev(), partial, multidot_nblk(), k, out, c.p2p.arSeq, &col);
+      return 0;
+    }
+    if (c.nranks == 1) {
+      ProfScope ps(PROF_SMALL);
+      launch_reduce_column(c.stream, partial, multidot_nblk(), k, out, col);
+      return 0;
+    }
+  }
+  if (int rc = reduce_allreduce(partial, k, out, done)) return rc;
+  ProfScope ps(PROF_SMALL);
+  launch_gmres_column(c.stream, col.ctl, col.i, col.sD, out, col.h, col.c, col.s, col.err, col.coef,
+                      col.pubFlag, col.pubProgress, col.seq);
+  return 0;
+}
+
 int host_allgather_i32(const int32_t *send, int32_t n, int32_t *recv) {
   Ctx &c = ctx();
   if (c.nranks == 1) {

@@ -23,6 +23,8 @@ int halo_sum(double *R, int dof, const int *done);
 int allreduce_dev(double *buf, size_t n);
 // out[j] = all-reduce(sum_b partial[j*nblk+b]), j < k (one kernel on the peer-memory path)
 int reduce_allreduce(const double *partial, int k, double *out, const int *done);
+int reduce_allreduce_column(const double *partial, int k, double *out, const ColArgs &col,
+                            const int *done);
 // peer-memory arena (IPC) set up after the halo schedule is known; falls back to NCCL
 int p2p_setup();
 void p2p_teardown();

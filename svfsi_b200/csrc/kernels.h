@@ -58,8 +58,20 @@ void launch_halo_recv_add(cudaStream_t st, const P2PDev &pd, int dof, int nNbr, 
                           int nUniq, const int *uniqNode, const int *uniqPtr, const int *uniqSlot,
                           double *R, int seq);
 // out[j] = sum over ranks (rank order) of (partial ? sum_b partial[j*nblk+b] : out[j]), j < k <= kArMax
+// arguments of the GMRES column step (Givens / Hessenberg / stop test, L/GMRES.f:342-366) when it
+// is fused into the tail of a reduction kernel; ctl == NULL: no column step
+struct ColArgs {
+  KrylovCtl *ctl;
+  int i, sD;
+  double *h, *c, *s, *err, *coef;
+  volatile int *pubFlag, *pubProgress;
+  int seq;
+};
 void launch_p2p_allreduce(cudaStream_t st, const P2PDev &pd, const double *partial, int nblk, int k,
-                          double *out, int seq);
+                          double *out, int seq, const ColArgs *col = nullptr);
+// single rank: out[j] = sum_b partial[j*nblk+b] and the column step, one kernel (k <= kArMax)
+void launch_reduce_column(cudaStream_t st, const double *partial, int nblk, int k, double *out,
+                          const ColArgs &col);
 
 // ---------------- vectors ----------------
 // partial[j*nblk + b] = sum over block b of U_j . w, j < k; U_j = U + j*stride. n doubles.

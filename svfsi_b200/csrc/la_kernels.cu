@@ -9,6 +9,7 @@
 // grids sized as multiples of the 148 SMs, reductions by warp shuffles, and no
 // host synchronisation inside the Krylov loop (kernels test a device flag).
 #include <cuda_runtime.h>
+#include <string.h>
 
 #include "ctx.h"
 #include "kernels.h"
@@ -286,13 +287,88 @@ void launch_halo_recv_add(cudaStream_t st, const P2PDev &pd, int dof, int nNbr, 
                                                         uniqSlot, R, seq);
 }
 
+// One column of the Arnoldi/Givens recurrence, L/GMRES.f:342-366 (scalar part), as the tail of
+// the reduction kernels below.  sh[0..i] = <u_j, u_{i+1}> (already summed over blocks and ranks)
+// in shared memory.  The rotations are a sequential recurrence: thread 0 runs it on shared memory
+// (c, s staged there by the whole block) instead of chasing global-memory latencies.
+__device__ void column_step_block(const ColArgs &a, double *sh, double *sc, double *ss, double *sv) {
+  const int i = a.i;
+  const bool active = (a.ctl->done == 0);
+  for (int j = threadIdx.x; j < i; j += blockDim.x) {
+    sv[j] = sh[j];
+    if (j < i - 1) { sc[j] = a.c[j]; ss[j] = a.s[j]; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && active) {
+    double hh = sh[i];
+    for (int j = 0; j < i; j++) hh = hh - sh[j] * sh[j];
+    hh = sqrt(fabs(hh));
+    a.ctl->inv = 1.0 / hh;
+    sh[i] = hh;
+    for (int j = 0; j < i - 1; j++) {
+      const double tmp = sc[j] * sh[j] + ss[j] * sh[j + 1];
+      sh[j + 1] = -ss[j] * sh[j] + sc[j] * sh[j + 1];
+      sh[j] = tmp;
+    }
+    const double tmp = sqrt(sh[i - 1] * sh[i - 1] + sh[i] * sh[i]);
+    const double ci = sh[i - 1] / tmp, si = sh[i] / tmp;
+    a.c[i - 1] = ci;
+    a.s[i - 1] = si;
+    sh[i - 1] = tmp;
+    sh[i] = 0.0;
+    const double e0 = a.err[i - 1];
+    a.err[i] = -si * e0;
+    a.err[i - 1] = ci * e0;
+    a.ctl->ilast = i;
+    a.ctl->itr += 1;
+    if (fabs(-si * e0) < a.ctl->eps) {
+      a.ctl->suc = 1;
+      a.ctl->done = 1;
+    }
+  }
+  __syncthreads();
+  if (active) {
+    double *hc = a.h + (size_t)(i - 1) * (a.sD + 1);  // h(:,i), 0-based rows
+    for (int j = threadIdx.x; j <= i; j += blockDim.x) {
+      hc[j] = sh[j];
+      if (j < i) a.coef[j] = sv[j];
+    }
+  }
+  // publish the stop flag AS OF THIS COLUMN to the host (mapped pinned memory), see solver_int.h
+  if (threadIdx.x == 0 && a.pubFlag) {
+    *a.pubFlag = a.ctl->done;
+    __threadfence_system();
+    *a.pubProgress = a.seq;
+    __threadfence_system();
+  }
+}
+
+// single rank: block sums of the multi-dot partials + the column step in ONE kernel
+__global__ void __launch_bounds__(512) reduce_column_kernel(const double *__restrict__ partial, int nblk,
+                                                            int k, double *__restrict__ out, ColArgs col) {
+  __shared__ double sh[kArMax], sc[kArMax], ss[kArMax], sv[kArMax];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (col.ctl->done == 0) {
+    for (int j = wid; j < k; j += nw) {
+      double v = 0.0;
+      for (int b = lane; b < nblk; b += 32) v += partial[(size_t)j * nblk + b];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) { sh[j] = v; out[j] = v; }
+    }
+  }
+  __syncthreads();
+  column_step_block(col, sh, sc, ss, sv);
+}
+
 // reduce the multi-dot partials (optional) and all-reduce k <= kArMax scalars in ONE kernel:
 // every rank stores its k values into every peer's mailbox, flags, waits for all peers, and sums
 // in rank order -- so all ranks obtain bit-identical results (the Krylov control flow depends on it).
 __global__ void __launch_bounds__(512) p2p_allreduce_kernel(P2PDev pd, const double *__restrict__ partial,
                                                             int nblk, int k, double *__restrict__ out,
-                                                            int seq) {
+                                                            int seq, ColArgs col) {
   __shared__ double mine[kArMax];
+  __shared__ double sc[kArMax], ss[kArMax], sv[kArMax];
   const int slot = seq & 1;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   if (partial) {
@@ -317,17 +393,30 @@ __global__ void __launch_bounds__(512) p2p_allreduce_kernel(P2PDev pd, const dou
   if (threadIdx.x < pd.nranks) wait_flag_sys(flag_ptr(pd.peer[pd.rank], 2 + slot, threadIdx.x), seq);
   __syncthreads();
   const double *mb = (const double *)(pd.peer[pd.rank] + pd.offMail) + (size_t)slot * pd.nranks * kArMax;
+  __syncthreads();   // everyone is done reading mine[] as the send buffer
   for (int j = threadIdx.x; j < k; j += blockDim.x) {
     double v = 0.0;
     for (int r = 0; r < pd.nranks; r++) v += __ldcv(mb + (size_t)r * kArMax + j);
     out[j] = v;
+    mine[j] = v;
+  }
+  if (col.ctl) {     // the Givens column step of GMRES rides on the same kernel
+    __syncthreads();
+    column_step_block(col, mine, sc, ss, sv);
   }
 }
 
 void launch_p2p_allreduce(cudaStream_t st, const P2PDev &pd, const double *partial, int nblk, int k,
-                          double *out, int seq) {
+                          double *out, int seq, const ColArgs *col) {
   count_launch();
-  p2p_allreduce_kernel<<<1, 512, 0, st>>>(pd, partial, nblk, k, out, seq);
+  ColArgs none;
+  memset(&none, 0, sizeof(none));
+  p2p_allreduce_kernel<<<1, 512, 0, st>>>(pd, partial, nblk, k, out, seq, col ? *col : none);
+}
+void launch_reduce_column(cudaStream_t st, const double *partial, int nblk, int k, double *out,
+                          const ColArgs &col) {
+  count_launch();
+  reduce_column_kernel<<<1, 512, 0, st>>>(partial, nblk, k, out, col);
 }
 
 // ---------------------------------------------------------------------------

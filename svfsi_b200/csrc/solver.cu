@@ -304,12 +304,12 @@ int arnoldi_cycle(int kind, int dof, const double *Val, double *u, size_t stride
       ProfScope ps(PROF_DOT);
       launch_multidot(c.stream, u, stride, ui, nOwned, i + 1, c.d_partial, done);
     }
-    if (int rc = reduce_allreduce(c.d_partial, i + 1, g.hcol, done)) return rc;
     const int seq = ++g_seq;
     {
-      ProfScope ps(PROF_SMALL);
-      launch_gmres_column(c.stream, g.ctl, i, sD, g.hcol, g.h, g.cc, g.ss, g.err, g.coef,
-                          &g_hm_dev->flag[seq & 63], &g_hm_dev->progress, seq);
+      // block sums + all-reduce + Givens column + stop test + flag publication: one kernel
+      ColArgs col{g.ctl, i, sD, g.h, g.cc, g.ss, g.err, g.coef, &g_hm_dev->flag[seq & 63],
+                  &g_hm_dev->progress, seq};
+      if (int rc = reduce_allreduce_column(c.d_partial, i + 1, g.hcol, col, done)) return rc;
     }
     {
       ProfScope ps(PROF_AXPY);

@@ -338,9 +338,10 @@ def main():
     # SURVEY.md 8d, per launch, this rank (NS solver: mixed shapes -> bytes of the K (3x3) SpMV only approx.)
     alg_bytes = nnz * (8 * dof * dof + 4) + nNo * (8 + 16 * dof)
     peak, peak_src = measured_peak()
-    # with neighbours every FSILS_SPARMUL is TWO launches of the same kernel (boundary rows, then
-    # interior rows while the halo is in flight): the roofline unit is the whole SpMV (both launches)
-    per_op = 2 if world > 1 else 1
+    # on the NCCL / unfused paths every FSILS_SPARMUL is TWO launches of the same kernel (boundary
+    # rows, then interior rows while the halo is in flight); the roofline unit is the whole SpMV
+    comm = api.comm_mode()
+    per_op = 2 if comm in (1, 2) else 1
     spmv_ops = spmv_n / per_op
     achieved = alg_bytes / (spmv_ms / max(spmv_ops, 1) * 1e-3) / 1e9 if spmv_n else None
     asm_ms, asm_n = prof["asm"]
@@ -355,8 +356,9 @@ def main():
                    e2e=dict(value=1e3 / (ms_e2e / args.steps), unit=unit,
                             h2d_bytes_per_step=int(Ag_h.nbytes + Yg_h.nbytes),
                             d2h_bytes_per_step=int(R_h.nbytes), ms_per_step=ms_e2e / args.steps),
-                   gpu_launches=int(launches),
-                   roofline=dict(bound="hbm", kernel=("spmv_vv4_kernel (FSILS_SPARMULVV dof=4)" if dof == 4 and SOLVER == "gmres"
+                   gpu_launches=int(launches), comm=api.COMM_MODES[comm],
+                   roofline=dict(bound="hbm", kernel=(("spmv_vv4_fused_kernel" if comm == 3 else "spmv_vv4_kernel") +
+                                         " (FSILS_SPARMULVV dof=4)" if dof == 4 and SOLVER == "gmres"
                                                     else "spmv kernels (mixed shapes; bytes of the dof x dof shape)"),
                                  achieved=achieved, peak=peak, unit="GB/s",
                                  frac=(achieved / peak) if achieved else None, peak_source=peak_src,

@@ -196,6 +196,10 @@ int32_t gpu_prof_reset_(void);
 int32_t gpu_prof_get_(double *ms /*[SVFSI_NTIMERS]*/, int64_t *launches /*[SVFSI_NTIMERS]*/);
 /* total number of kernels this library launched since gpu_init_ */
 int32_t gpu_launch_count_(int64_t *n);
+/* how the halo sums / all-reduces travel: 0 single rank, 1 NCCL send/recv + all-reduce,
+ * 2 peer-memory kernels (CUDA IPC over NVLink), 3 peer-memory with the halo send fused into the
+ * SpMV kernel (one launch per FSILS_SPARMUL*; replaces MPI_ISEND/IRECV of L/INCOMMU.f:91-96) */
+int32_t gpu_comm_mode_(int32_t *mode);
 /* cudaStream_t of the library (so a caller can record its own events on it) */
 int32_t gpu_get_stream_(void **stream);
 int32_t gpu_sync_(void);

@@ -68,7 +68,7 @@ EXPORTS = [
     "gpu_get_val_", "gpu_set_val_", "gpu_commu_", "gpu_commu_dev_", "gpu_solve_",
     "gpu_solve_dev_", "gpu_ls_create_", "gpu_sparmul_", "gpu_dot_", "gpu_time_kernel_",
     "gpu_prof_enable_", "gpu_prof_reset_", "gpu_prof_get_", "gpu_launch_count_",
-    "gpu_get_stream_", "gpu_sync_",
+    "gpu_get_stream_", "gpu_sync_", "gpu_comm_mode_",
 ]
 
 
@@ -398,6 +398,16 @@ def prof_get():
     ms = np.zeros(NTIMERS); n = np.zeros(NTIMERS, dtype=np.int64)
     _check(lib().gpu_prof_get_(_d(ms), n.ctypes.data_as(C.POINTER(C.c_int64))))
     return {name: (float(ms[i]), int(n[i])) for i, name in enumerate(PROF_SLOTS)}
+
+
+COMM_MODES = {0: "single rank", 1: "nccl", 2: "peer-memory kernels (CUDA IPC over NVLink)",
+              3: "peer-memory, halo send fused into the SpMV kernel"}
+
+
+def comm_mode():
+    m = C.c_int32()
+    _check(lib().gpu_comm_mode_(C.byref(m)))
+    return m.value
 
 
 def launch_count():

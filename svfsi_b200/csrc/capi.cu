@@ -722,6 +722,13 @@ int32_t gpu_launch_count_(int64_t *n) {
   *n = ctx().launches;
   return 0;
 }
+int32_t gpu_comm_mode_(int32_t *mode) {
+  Ctx &c = ctx();
+  if (c.nranks == 1) *mode = 0;
+  else if (!c.p2p.on) *mode = 1;
+  else *mode = c.p2p.fuse ? 3 : 2;
+  return 0;
+}
 int32_t gpu_get_stream_(void **stream) {
   *stream = (void *)ctx().stream;
   return 0;

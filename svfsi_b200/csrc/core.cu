@@ -151,6 +151,9 @@ void p2p_teardown() {
   if (p.d_nbrN) cudaFree(p.d_nbrN);
   if (p.d_slotNbr) cudaFree(p.d_slotNbr);
   if (p.d_counter) cudaFree(p.d_counter);
+  if (p.d_sendPtr) cudaFree(p.d_sendPtr);
+  if (p.d_sendRank) cudaFree(p.d_sendRank);
+  if (p.d_sendOff) cudaFree(p.d_sendOff);
   p = P2P();
 }
 
@@ -227,6 +230,35 @@ int p2p_setup() {
   if (int rc = upload_vec(&p.d_nbrPeerOff, nbrPeerOff)) return rc;
   if (int rc = upload_vec(&p.d_nbrN, nbrN)) return rc;
   if (int rc = upload_vec(&p.d_slotNbr, slotNbr)) return rc;
+  {
+    // destinations of every boundary row, for the SpMV kernels that send from inside the kernel
+    p.nBnd = c.shnNo + (c.nNo - c.mynNo);
+    std::vector<std::vector<std::pair<int, int>>> dst((size_t)p.nBnd);
+    bool ok2 = true;
+    for (size_t i = 0; i < c.nbr.size() && ok2; i++) {
+      const Neighbor &nb = c.nbr[i];
+      for (int t = 0; t < nb.n; t++) {
+        const int row = nb.ptr[t];
+        int b;
+        if (row < c.shnNo) b = row;
+        else if (row >= c.mynNo && row < c.nNo) b = c.shnNo + (row - c.mynNo);
+        else { ok2 = false; break; }
+        dst[b].push_back({nb.iP, nbrPeerOff[i] + t});
+      }
+    }
+    const char *ef = getenv("SVFSI_SPMV_FUSE");
+    p.fuse = ok2 && !(ef && atoi(ef) == 0);
+    if (p.fuse) {
+      std::vector<int> sp((size_t)p.nBnd + 1, 0), sr, so;
+      for (int b = 0; b < p.nBnd; b++) {
+        for (auto &d : dst[b]) { sr.push_back(d.first); so.push_back(d.second); }
+        sp[b + 1] = (int)sr.size();
+      }
+      if (int rc = upload_vec(&p.d_sendPtr, sp)) return rc;
+      if (int rc = upload_vec(&p.d_sendRank, sr)) return rc;
+      if (int rc = upload_vec(&p.d_sendOff, so)) return rc;
+    }
+  }
   CUDA_TRY(cudaMalloc((void **)&p.d_counter, sizeof(unsigned int)));
   CUDA_TRY(cudaMemset(p.d_counter, 0, sizeof(unsigned int)));
   p.arSeq = 0;
@@ -369,6 +401,23 @@ int sparmul(int kind, int dof, const double *K, const double *U, double *KU, con
   Ctx &c = ctx();
   if (kind == 3) dof = 1;
   const int rd = row_dof(kind, dof);
+  if (c.nranks > 1 && !c.nbr.empty() && c.p2p.on && c.p2p.fuse) {
+    // ONE kernel: boundary rows in the first CTAs, their results stored straight into the
+    // neighbours' receive buffers, flags raised by the last boundary CTA, interior rows behind
+    {
+      ProfScope ps(PROF_SPMV);
+      c.p2p.haloSeq++;
+      SpmvFuse f;
+      f.shnNo = c.shnNo; f.mynNo = c.mynNo; f.nNo = c.nNo;
+      f.nBnd = c.p2p.nBnd; f.bndCtas = 0;
+      f.sendPtr = c.p2p.d_sendPtr; f.sendRank = c.p2p.d_sendRank; f.sendOff = c.p2p.d_sendOff;
+      f.nbrRank = c.p2p.d_nbrRank; f.nNbr = (int)c.nbr.size();
+      f.pd = p2p_dev(); f.seq = c.p2p.haloSeq; f.counter = c.p2p.d_counter;
+      launch_spmv_fused(c.stream, kind, dof, f, c.d_rowPtr, c.d_col, K, U, KU, done);
+    }
+    ProfScope ps(PROF_HALO);
+    return halo_recv(KU, rd, done);
+  }
   if (c.nranks > 1 && !c.nbr.empty()) {
     // rows shared with other ranks first (the two contiguous slabs at the ends of the reordered
     // numbering, L/LHS.f:134-165), push them to the neighbours, then the interior rows while the

@@ -63,6 +63,10 @@ struct P2P {
   char **d_peer = nullptr;       // device copy of peer[]
   int *d_nbrRank = nullptr, *d_nbrOff = nullptr, *d_nbrPeerOff = nullptr, *d_nbrN = nullptr;
   int *d_slotNbr = nullptr;      // [nShared] neighbour index of every pack slot
+  // fused SpMV + send: destinations of every boundary row (CSR over boundary-row index)
+  bool fuse = false;
+  int nBnd = 0;
+  int *d_sendPtr = nullptr, *d_sendRank = nullptr, *d_sendOff = nullptr;
   unsigned int *d_counter = nullptr;
 };
 static constexpr int kArMax = 512;

@@ -51,6 +51,22 @@ struct P2PDev {
   size_t offMail, offHalo;
   int haloCap, rank, nranks;
 };
+// SpMV with the halo send fused into the kernel (la_kernels.cu: spmv_*_fused_kernel)
+struct SpmvFuse {
+  int shnNo, mynNo, nNo;   // row ranges of the reordered numbering (L/LHS.f:134-165)
+  int nBnd, bndCtas;       // boundary rows = shnNo + (nNo - mynNo); CTAs that hold them
+  const int *sendPtr;      // [nBnd+1] CSR over boundary rows -> destinations
+  const int *sendRank;     // peer rank of each destination
+  const int *sendOff;      // node offset inside that peer's receive slot
+  const int *nbrRank;
+  int nNbr;
+  P2PDev pd;
+  int seq;
+  unsigned int *counter;
+};
+void launch_spmv_fused(cudaStream_t st, int kind, int dof, SpmvFuse f, const int *rowPtr,
+                       const int *col, const double *K, const double *U, double *KU,
+                       const int *done);
 void launch_halo_send(cudaStream_t st, const P2PDev &pd, int dof, int nShared, int nNbr,
                       const int *packIdx, const int *slotNbr, const int *nbrRank, const int *nbrOff,
                       const int *nbrPeerOff, const double *R, int seq, unsigned int *counter);

@@ -26,6 +26,20 @@ __device__ __forceinline__ double2 ldg_stream2(const double2 *p) {
   return __ldcs(p);
 }
 
+// flag words of the peer-memory exchanges (see the halo kernels below)
+__device__ __forceinline__ void st_flag_sys(volatile int *p, int v) {
+  __threadfence_system();
+  *p = v;
+}
+__device__ __forceinline__ void wait_flag_sys(volatile int *p, int v) {
+  while (*p != v) { /* spin on a word in local memory that the peer writes */ }
+  __threadfence_system();
+}
+// flags live at the start of the arena: int[4][64]: 0 = halo slot0, 1 = halo slot1, 2 = ar slot0, 3 = ar slot1
+__device__ __forceinline__ volatile int *flag_ptr(char *base, int which, int src) {
+  return (volatile int *)base + which * 64 + src;
+}
+
 // ---------------------------------------------------------------------------
 // SPARMULVV, dof = 4 (L/SPARMUL.f:98-113).  8 lanes own one block row: lane q
 // loads the q-th 16-byte piece of every 128-byte block (one LDG.128 per lane,
@@ -34,22 +48,11 @@ __device__ __forceinline__ double2 ldg_stream2(const double2 *p) {
 // Column ids of 8 consecutive blocks are fetched by one coalesced load and
 // broadcast by shuffles, so the U gather does not wait on a dependent load per
 // block.
-__global__ void __launch_bounds__(256) spmv_vv4_kernel(int r0, int r1, int r2, int r3,
-                                                        const int *__restrict__ rowPtr,
-                                                        const int *__restrict__ col,
-                                                        const double2 *__restrict__ K,
-                                                        const double2 *__restrict__ U,
-                                                        double *__restrict__ KU,
-                                                        const int *done) {
-  DONE_GUARD(done);
-  const int lane = threadIdx.x & 31;
-  const int q = lane & 7;
-  const int h = q & 1;
-  const unsigned gmask = 0xFFu << (lane & 24);
-  // rows [r0,r1) followed by rows [r2, ...): the two boundary slabs go out in one launch
-  int row = r0 + (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 3);
-  if (row >= r1) row += r2 - r1;
-  if (row >= r3) return;  // whole 8-lane groups leave together
+__device__ __forceinline__ double spmv_vv4_row(int row, int q, int h, unsigned gmask,
+                                               const int *__restrict__ rowPtr,
+                                               const int *__restrict__ col,
+                                               const double2 *__restrict__ K,
+                                               const double2 *__restrict__ U) {
   const int s = __ldg(rowPtr + row), e = __ldg(rowPtr + row + 1);
   double acc = 0.0;
   for (int base = s; base < e; base += 8) {
@@ -68,29 +71,104 @@ __global__ void __launch_bounds__(256) spmv_vv4_kernel(int r0, int r1, int r2, i
     }
   }
   acc += __shfl_xor_sync(gmask, acc, 1, 8);
+  return acc;
+}
+
+__global__ void __launch_bounds__(256) spmv_vv4_kernel(int r0, int r1, int r2, int r3,
+                                                        const int *__restrict__ rowPtr,
+                                                        const int *__restrict__ col,
+                                                        const double2 *__restrict__ K,
+                                                        const double2 *__restrict__ U,
+                                                        double *__restrict__ KU,
+                                                        const int *done) {
+  DONE_GUARD(done);
+  const int lane = threadIdx.x & 31;
+  const int q = lane & 7;
+  const int h = q & 1;
+  const unsigned gmask = 0xFFu << (lane & 24);
+  // rows [r0,r1) followed by rows [r2, ...): the two boundary slabs go out in one launch
+  int row = r0 + (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 3);
+  if (row >= r1) row += r2 - r1;
+  if (row >= r3) return;  // whole 8-lane groups leave together
+  const double acc = spmv_vv4_row(row, q, h, gmask, rowPtr, col, K, U);
   if (h == 0) KU[(size_t)row * 4 + (q >> 1)] = acc;
+}
+
+// ---------------------------------------------------------------------------
+// SpMV + halo send in ONE kernel (peer-memory path, FSILS_SPARMUL* = product followed by
+// FSILS_COMMUV, L/SPARMUL.f:130).  The rows shared with other ranks -- the two slabs at the ends
+// of the reordered numbering -- are given to the FIRST CTAs of the grid; each of their results is
+// stored locally AND straight into the receive buffer of every rank sharing that node (NVLink
+// stores into the peer's IPC-mapped arena).  The last boundary CTA to finish raises the
+// neighbours' flags, so the transfer is in flight while the remaining CTAs stream the interior
+// rows.  A set `done` flag skips the arithmetic but never the flag protocol (the receiving
+// kernel of the same exchange waits on it).
+__device__ __forceinline__ bool fuse_map_row(const SpmvFuse &f, int rowsPerCta, int grp, int &row,
+                                             int &bidx) {
+  if ((int)blockIdx.x < f.bndCtas) {
+    bidx = blockIdx.x * rowsPerCta + grp;
+    if (bidx >= f.nBnd) return false;
+    row = bidx < f.shnNo ? bidx : f.mynNo + (bidx - f.shnNo);
+    return true;
+  }
+  bidx = -1;
+  row = f.shnNo + ((int)blockIdx.x - f.bndCtas) * rowsPerCta + grp;
+  return row < f.mynNo;
+}
+__device__ __forceinline__ void fuse_send(const SpmvFuse &f, int bidx, int rd, int comp, double v) {
+  const int slot = f.seq & 1;
+  for (int k = __ldg(f.sendPtr + bidx); k < __ldg(f.sendPtr + bidx + 1); k++) {
+    double *dst = (double *)(f.pd.peer[__ldg(f.sendRank + k)] + f.pd.offHalo) +
+                  (size_t)slot * f.pd.haloCap + (size_t)__ldg(f.sendOff + k) * rd + comp;
+    *dst = v;
+  }
+}
+__device__ __forceinline__ void fuse_publish(const SpmvFuse &f) {
+  if ((int)blockIdx.x >= f.bndCtas) return;   // block-uniform
+  __shared__ bool last;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(f.counter, 1u) == (unsigned)f.bndCtas - 1u);
+  __syncthreads();
+  if (last) {
+    if ((int)threadIdx.x < f.nNbr)
+      st_flag_sys(flag_ptr(f.pd.peer[f.nbrRank[threadIdx.x]], f.seq & 1, f.pd.rank), f.seq);
+    if (threadIdx.x == 0) *f.counter = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) spmv_vv4_fused_kernel(SpmvFuse f,
+                                                              const int *__restrict__ rowPtr,
+                                                              const int *__restrict__ col,
+                                                              const double2 *__restrict__ K,
+                                                              const double2 *__restrict__ U,
+                                                              double *__restrict__ KU,
+                                                              const int *done) {
+  const bool skip = (done != nullptr && *(volatile const int *)done != 0);
+  const int lane = threadIdx.x & 31, q = lane & 7, h = q & 1;
+  const unsigned gmask = 0xFFu << (lane & 24);
+  int row, bidx;
+  const bool have = fuse_map_row(f, 32, threadIdx.x >> 3, row, bidx);
+  if (have && !skip) {
+    const double acc = spmv_vv4_row(row, q, h, gmask, rowPtr, col, K, U);
+    if (h == 0) {
+      KU[(size_t)row * 4 + (q >> 1)] = acc;
+      if (bidx >= 0) fuse_send(f, bidx, 4, q >> 1, acc);
+    }
+  }
+  fuse_publish(f);
 }
 
 // Generic shapes (VV dof<=3, VS, SV, SS): 4 lanes per row, each lane takes blocks
 // q, q+4, ... of the row; partial results combined by shuffles.  BR x BC is the
 // block shape: VV d: (d,d); VS d: (1,d); SV d: (d,1); SS: (1,1).
 template <int BR, int BC>
-__global__ void __launch_bounds__(256) spmv_generic_kernel(int r0, int r1, int r2, int r3,
-                                                            const int *__restrict__ rowPtr,
-                                                            const int *__restrict__ col,
-                                                            const double *__restrict__ K,
-                                                            const double *__restrict__ U,
-                                                            double *__restrict__ KU,
-                                                            const int *done) {
-  DONE_GUARD(done);
-  const int lane = threadIdx.x & 31;
-  const int q = lane & 3;
-  const unsigned gmask = 0xFu << (lane & 28);
-  int row = r0 + (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 2);
-  if (row >= r1) row += r2 - r1;
-  if (row >= r3) return;
+__device__ __forceinline__ void spmv_generic_row(int row, int q, unsigned gmask,
+                                                 const int *__restrict__ rowPtr,
+                                                 const int *__restrict__ col,
+                                                 const double *__restrict__ K,
+                                                 const double *__restrict__ U, double (&acc)[BR]) {
   const int s = __ldg(rowPtr + row), e = __ldg(rowPtr + row + 1);
-  double acc[BR];
 #pragma unroll
   for (int l = 0; l < BR; l++) acc[l] = 0.0;
   for (int j = s + q; j < e; j += 4) {
@@ -109,10 +187,56 @@ __global__ void __launch_bounds__(256) spmv_generic_kernel(int r0, int r1, int r
     acc[l] += __shfl_xor_sync(gmask, acc[l], 1, 4);
     acc[l] += __shfl_xor_sync(gmask, acc[l], 2, 4);
   }
+}
+
+template <int BR, int BC>
+__global__ void __launch_bounds__(256) spmv_generic_kernel(int r0, int r1, int r2, int r3,
+                                                            const int *__restrict__ rowPtr,
+                                                            const int *__restrict__ col,
+                                                            const double *__restrict__ K,
+                                                            const double *__restrict__ U,
+                                                            double *__restrict__ KU,
+                                                            const int *done) {
+  DONE_GUARD(done);
+  const int lane = threadIdx.x & 31;
+  const int q = lane & 3;
+  const unsigned gmask = 0xFu << (lane & 28);
+  int row = r0 + (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 2);
+  if (row >= r1) row += r2 - r1;
+  if (row >= r3) return;
+  double acc[BR];
+  spmv_generic_row<BR, BC>(row, q, gmask, rowPtr, col, K, U, acc);
   if (q == 0) {
 #pragma unroll
     for (int l = 0; l < BR; l++) KU[(size_t)row * BR + l] = acc[l];
   }
+}
+
+template <int BR, int BC>
+__global__ void __launch_bounds__(256) spmv_generic_fused_kernel(SpmvFuse f,
+                                                                  const int *__restrict__ rowPtr,
+                                                                  const int *__restrict__ col,
+                                                                  const double *__restrict__ K,
+                                                                  const double *__restrict__ U,
+                                                                  double *__restrict__ KU,
+                                                                  const int *done) {
+  const bool skip = (done != nullptr && *(volatile const int *)done != 0);
+  const int lane = threadIdx.x & 31, q = lane & 3;
+  const unsigned gmask = 0xFu << (lane & 28);
+  int row, bidx;
+  const bool have = fuse_map_row(f, 64, threadIdx.x >> 2, row, bidx);
+  if (have && !skip) {
+    double acc[BR];
+    spmv_generic_row<BR, BC>(row, q, gmask, rowPtr, col, K, U, acc);
+    if (q == 0) {
+#pragma unroll
+      for (int l = 0; l < BR; l++) {
+        KU[(size_t)row * BR + l] = acc[l];
+        if (bidx >= 0) fuse_send(f, bidx, BR, l, acc[l]);
+      }
+    }
+  }
+  fuse_publish(f);
 }
 
 template <int BR, int BC>
@@ -149,6 +273,42 @@ void launch_spmv2(cudaStream_t st, int kind, int dof, int r0, int r1, int r2, in
     if (dof == 2) GEN(2, 1); else if (dof == 3) GEN(3, 1); else GEN(4, 1);
   }
 #undef GEN
+}
+
+template <int BR, int BC>
+static void launch_generic_fused(cudaStream_t st, const SpmvFuse &f, int blocks, const int *rowPtr,
+                                 const int *col, const double *K, const double *U, double *KU,
+                                 const int *done) {
+  spmv_generic_fused_kernel<BR, BC><<<blocks, 256, 0, st>>>(f, rowPtr, col, K, U, KU, done);
+}
+// all rows of this rank in one launch, boundary rows first, halo send fused (see above).
+// f.bndCtas is filled in here (it depends on the rows per CTA of the kernel shape).
+void launch_spmv_fused(cudaStream_t st, int kind, int dof, SpmvFuse f, const int *rowPtr,
+                       const int *col, const double *K, const double *U, double *KU,
+                       const int *done) {
+  count_launch();
+  const bool vv4 = (kind == 0 && dof == 4);
+  const int rpc = vv4 ? 32 : 64;
+  f.bndCtas = (f.nBnd + rpc - 1) / rpc;
+  const int inner = f.mynNo - f.shnNo;
+  const int blocks = f.bndCtas + (inner + rpc - 1) / rpc;
+  if (blocks <= 0) return;
+  if (vv4) {
+    spmv_vv4_fused_kernel<<<blocks, 256, 0, st>>>(f, rowPtr, col, (const double2 *)K,
+                                                  (const double2 *)U, KU, done);
+    return;
+  }
+#define GENF(BR, BC) launch_generic_fused<BR, BC>(st, f, blocks, rowPtr, col, K, U, KU, done)
+  if (kind == 3 || dof == 1) {
+    GENF(1, 1);
+  } else if (kind == 0) {
+    if (dof == 2) GENF(2, 2); else GENF(3, 3);
+  } else if (kind == 1) {
+    if (dof == 2) GENF(1, 2); else if (dof == 3) GENF(1, 3); else GENF(1, 4);
+  } else {
+    if (dof == 2) GENF(2, 1); else if (dof == 3) GENF(3, 1); else GENF(4, 1);
+  }
+#undef GENF
 }
 
 void launch_spmv(cudaStream_t st, int kind, int dof, int r0, int r1, const int *rowPtr,
@@ -208,19 +368,6 @@ void launch_unpack_add(cudaStream_t st, int dof, int nUniq, const int *uniqNode,
 // host).  Flags carry a sequence number; two alternating slots make back-to-back exchanges safe
 // (a rank can be at most one exchange ahead of a neighbour: it needs the neighbour's previous
 // message to get there).
-__device__ __forceinline__ void st_flag_sys(volatile int *p, int v) {
-  __threadfence_system();
-  *p = v;
-}
-__device__ __forceinline__ void wait_flag_sys(volatile int *p, int v) {
-  while (*p != v) { /* spin on a word in local memory that the peer writes */ }
-  __threadfence_system();
-}
-// flags live at the start of the arena: int[4][64]: 0 = halo slot0, 1 = halo slot1, 2 = ar slot0, 3 = ar slot1
-__device__ __forceinline__ volatile int *flag_ptr(char *base, int which, int src) {
-  return (volatile int *)base + which * 64 + src;
-}
-
 __global__ void __launch_bounds__(256) halo_send_kernel(P2PDev pd, int dof, int nShared, int nNbr,
                                                         const int *__restrict__ packIdx,
                                                         const int *__restrict__ slotNbr,

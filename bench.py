@@ -168,14 +168,15 @@ def newton_step_e2e(api, variant, Ag, Yg, Rout):
     return ls
 
 
-def cpu_newton_sample(nz_sample, threads_note="1 (scalar port, single simulated rank)"):
+def cpu_newton_sample(nz_sample, threads_note="1 (scalar port, single simulated rank)", rebuild=True):
     """Oracle port (-O3 -march=native, the reference's own flags) on a slice of the same pipe:
     one Newton iteration (assembly incl. the reference's per-element overheads + COMMU + GMRES
     with the bench's solver settings), scaled to the full mesh by element count."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle import oracle as ora
     from svfsi_b200 import mesh
-    ora.build(native=True, force=True)      # -march=native must be compiled on THIS host
+    if rebuild:
+        ora.build(native=True, force=True)  # -march=native must be compiled on THIS host
     dims = (DIMS[0], DIMS[1], nz_sample)
     Ls = L_PIPE * nz_sample / DIMS[2]
     gnNo, p = mesh.build_rank_problem(*dims, rank=0, nparts=1, R=R_PIPE, L=Ls)
@@ -199,6 +200,49 @@ def cpu_newton_sample(nz_sample, threads_note="1 (scalar port, single simulated 
                 t_full=(t_asm + t_sol) * scale, threads=threads_note)
 
 
+def _cpu_worker(args):
+    nz_sample, barrier = args
+    if barrier is not None:
+        barrier.wait()
+    t0 = time.perf_counter()
+    r = cpu_newton_sample(nz_sample, rebuild=False)
+    r["t_wall"] = time.perf_counter() - t0
+    return r
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_newton_parallel(nz_sample, procs=None):
+    """The CPU arm on ALL host cores: `procs` processes (one per core, like `mpiexec -np procs
+    svFSI`), each running one Newton iteration of the oracle port on its own slab of the pipe at
+    the same time (they contend for memory bandwidth as MPI ranks would; the halo exchange between
+    slabs is NOT included, which flatters the CPU).  Whole-mesh time = slowest process x
+    (slabs of the full mesh / procs)."""
+    import multiprocessing as mp
+    from oracle import oracle as ora
+    ora.build(native=True, force=True)      # -march=native must be compiled on THIS host
+    procs = procs or max(1, min(host_cores(), 64))
+    if procs == 1:
+        rs = [_cpu_worker((nz_sample, None))]
+    else:
+        ctx = mp.get_context("fork")
+        with ctx.Manager() as mgr:
+            bar = mgr.Barrier(procs)
+            with ctx.Pool(procs) as pool:
+                rs = pool.map(_cpu_worker, [(nz_sample, bar)] * procs, chunksize=1)
+    t_max = max(r["t_asm"] + r["t_sol"] for r in rs)
+    nEl_full = 6 * DIMS[0] * DIMS[1] * DIMS[2]
+    slabs = nEl_full / rs[0]["nEl"]
+    return dict(procs=procs, t_max=t_max, t_full=t_max * slabs / procs, nEl=rs[0]["nEl"],
+                itr=rs[0]["itr"], t_asm=max(r["t_asm"] for r in rs), t_sol=max(r["t_sol"] for r in rs),
+                slabs=slabs)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -208,6 +252,8 @@ def main():
     ap.add_argument("--nz", type=int, default=DIMS[2], help="axial cells (default = 10M-tet workload)")
     ap.add_argument("--variant", default="gather", choices=["atomic", "colored", "gather"])
     ap.add_argument("--cpu-nz", type=int, default=24, help="axial cells of the CPU-baseline slice")
+    ap.add_argument("--cpu-procs", type=int, default=None,
+                    help="processes of the CPU arm (default: all host cores, at most 64)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--solver", default="gmres", choices=["gmres", "ns"],
                     help="non-default: FSILS_NSSOLVER with FSILS defaults (BASELINE configs[4])")
@@ -244,19 +290,21 @@ def main():
             return 0
         times = []
         for _ in range(args.warmup + args.steps):
-            times.append(cpu_newton_sample(args.cpu_nz))
+            times.append(cpu_newton_parallel(args.cpu_nz, args.cpu_procs))
         times = times[args.warmup:] if len(times) > args.warmup else times
         t_full = float(np.mean([t["t_full"] for t in times]))
         s = times[-1]
-        sample = (f"one Newton iteration (faithful CONSTRUCT_FLUID + FSILS GMRES, same settings) on a "
-                  f"{dims[0]}x{dims[1]}x{args.cpu_nz} slice ({s['nEl']} tets, {s['itr']} SpMVs), time scaled by "
-                  f"nEl ratio {s['scale']:.1f}")
+        sample = (f"{s['procs']} processes at once (one per host core, as mpiexec -np {s['procs']} would; no "
+                  f"halo exchange between them), each one Newton iteration (faithful CONSTRUCT_FLUID + "
+                  f"FSILS GMRES, same settings) of the oracle port (-O3 -march=native) on a {dims[0]}x{dims[1]}x"
+                  f"{args.cpu_nz} slab ({s['nEl']} tets, {s['itr']} SpMVs; slowest: assembly {s['t_asm']:.2f}s, "
+                  f"GMRES {s['t_sol']:.2f}s); whole mesh = {s['slabs']:.0f} slabs / {s['procs']} at a time")
         val = 1.0 / t_full
         out = dict(metric=metric, value=val, unit=unit, n_gpus=args.gpus, steps=args.steps,
                    warmup=args.warmup, ms_per_step=t_full * 1e3, higher_is_better=True,
                    scaling="strong", vs_baseline=None, dtype="f64", data="synthetic", config=config,
                    impl="reference",
-                   cpu_baseline=dict(value=val, unit=unit, cores=1, kind="port", sample=sample),
+                   cpu_baseline=dict(value=val, unit=unit, cores=s["procs"], kind="port", sample=sample),
                    e2e=dict(value=val, unit=unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         print(json.dumps(out))
         return 0
@@ -344,6 +392,14 @@ def main():
     per_op = 2 if comm in (1, 2) else 1
     spmv_ops = spmv_n / per_op
     achieved = alg_bytes / (spmv_ms / max(spmv_ops, 1) * 1e-3) / 1e9 if spmv_n else None
+    # DRAM traffic of the same kernel from the committed ncu --set full capture (same mesh only)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_spmv_traffic.json")
+    if os.path.exists(tp) and dof == 4 and SOLVER == "gmres":
+        with open(tp) as fh:
+            tj = json.load(fh)
+        if tj.get("nnz") == int(nnz) and tj.get("nNo") == int(nNo):
+            traffic = int(tj["dram_bytes_read"] + tj["dram_bytes_write"])
     asm_ms, asm_n = prof["asm"]
     melem = (nEl * world) / (asm_ms / max(asm_n, 1) * 1e-3) / 1e6 if asm_n else None
     scatter_bytes = nEl * (16 + 4 * 14 * 8 + 2048 + 128)        # element-scatter model, SURVEY.md 8d
@@ -362,7 +418,7 @@ def main():
                                                     else "spmv kernels (mixed shapes; bytes of the dof x dof shape)"),
                                  achieved=achieved, peak=peak, unit="GB/s",
                                  frac=(achieved / peak) if achieved else None, peak_source=peak_src,
-                                 traffic=None, algorithmic_bytes_per_launch=int(alg_bytes),
+                                 traffic=traffic, algorithmic_bytes_per_launch=int(alg_bytes),
                                  avg_launch_ms=spmv_ms / max(spmv_ops, 1), launches=int(spmv_n),
                                  launches_per_spmv=per_op),
                    detail=dict(nEl_rank0=int(nEl), nNo_rank0=int(nNo), nnz_rank0=int(nnz),
@@ -375,12 +431,14 @@ def main():
                                profiled_pass_ms_per_step=ms_prof / args.steps,
                                setup_s=t_setup))
         if world == 1 and not args.no_cpu:
-            c = cpu_newton_sample(args.cpu_nz)
+            c = cpu_newton_parallel(args.cpu_nz, args.cpu_procs)
             out["cpu_baseline"] = dict(
-                value=1.0 / c["t_full"], unit=unit, cores=1, kind="port",
-                sample=(f"oracle port (-O3 -march=native), one Newton iteration on a {dims[0]}x{dims[1]}x"
-                        f"{args.cpu_nz} slice ({c['nEl']} tets; assembly {c['t_asm']:.2f}s, GMRES "
-                        f"{c['t_sol']:.2f}s / {c['itr']} SpMVs) scaled by nEl ratio {c['scale']:.1f}"))
+                value=1.0 / c["t_full"], unit=unit, cores=c["procs"], kind="port",
+                sample=(f"oracle port (-O3 -march=native), {c['procs']} processes at once (one per host "
+                        f"core, no halo exchange), each one Newton iteration on a {dims[0]}x{dims[1]}x"
+                        f"{args.cpu_nz} slab ({c['nEl']} tets; slowest: assembly {c['t_asm']:.2f}s, GMRES "
+                        f"{c['t_sol']:.2f}s / {c['itr']} SpMVs); whole mesh = {c['slabs']:.0f} slabs / "
+                        f"{c['procs']} at a time"))
         else:
             out["cpu_baseline"] = None
         print(json.dumps(out))

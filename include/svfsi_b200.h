@@ -195,6 +195,24 @@ int32_t gpu_prof_enable_(const int32_t *on);
 int32_t gpu_prof_reset_(void);
 int32_t gpu_prof_get_(double *ms /*[SVFSI_NTIMERS]*/, int64_t *launches /*[SVFSI_NTIMERS]*/);
 /* total number of kernels this library launched since gpu_init_ */
+/* ---- generalised-alpha time integration on the device --------------------
+ * Replaces, for the equation being solved, PICP / PICI / PICC (S/PIC.f:40-297), the strong
+ * Dirichlet overwrite SETBCDIR (S/SETBC.f:39-228, std / ustd profiles: the Fortran side still
+ * evaluates SETBCDIRL's tmpA/tmpY, :202-232) and the end-of-step copy Ao = An (S/MAIN.f:277-279).
+ * Host arrays are (tDof, tnNo) column-major in svFSI node order.  Do may be NULL (no
+ * displacement unknowns: fluid, heatS).  Between gpu_pici_ and gpu_picc_ the caller runs
+ * gpu_construct_*_dev_, gpu_commu_dev_ and gpu_solve_dev_: no nodal vector crosses PCIe. */
+int32_t gpu_pic_init_(const int32_t *tDof, const double *Ao, const double *Yo, const double *Do);
+int32_t gpu_pic_free_(void);
+int32_t gpu_picp_(const double *gam);                            /* S/PIC.f:82-126   */
+int32_t gpu_setbcdir_(const int32_t *faNo, const int32_t *gN, const int32_t *s,
+                      const int32_t *lDof, const double *tmpA,
+                      const double *tmpY);                       /* S/SETBC.f:118-123; s 1-based */
+int32_t gpu_pici_(const double *am, const double *af);           /* S/PIC.f:141-152  */
+int32_t gpu_picc_(const double *gam, const double *beta, const double *dt); /* S/PIC.f:203-207 */
+int32_t gpu_pic_advance_(void);                                  /* S/MAIN.f:277-279 */
+int32_t gpu_pic_get_(const int32_t *which, double *A, double *Y, double *D); /* 0 old, 1 new */
+
 int32_t gpu_launch_count_(int64_t *n);
 /* how the halo sums / all-reduces travel: 0 single rank, 1 NCCL send/recv + all-reduce,
  * 2 peer-memory kernels (CUDA IPC over NVLink), 3 peer-memory with the halo send fused into the

@@ -268,3 +268,57 @@ def ge(A, B):
     A = np.asfortranarray(A, dtype=np.float64); B = np.array(B, dtype=np.float64)
     ok = lib().ora_ge(A.shape[0], B.size, _d(A), _d(B))
     return bool(ok), B
+
+
+# ---------------------------------------------------------------------------------------------
+# Generalised-alpha predictor / initiator / corrector and the strong Dirichlet overwrite, for one
+# equation occupying dofs s..e of (tnNo, tDof) row-major arrays (NumPy restatement; arrays are the
+# transposes of the Fortran (tDof, tnNo) ones).
+def picp(Ao, Yo, gam, Do=None):
+    """S/PIC.f:82-126 (no IB / prestress / dFlag branches): An = Ao*(gam-1)/gam; Yn = Yo; Dn = Do"""
+    coef = (gam - 1.0) / gam
+    An = Ao * coef
+    Yn = Yo.copy()
+    return (An, Yn) if Do is None else (An, Yn, Do.copy())
+
+
+def setbcdir(lA, lY, gN, s, tmpA, tmpY):
+    """S/SETBC.f:118-123 (std/ustd Dirichlet, no eDrn, not impD): lA(s:e,Ac) = tmpA(:,a);
+    lY(s:e,Ac) = tmpY(:,a).  gN 1-based svFSI local ids; s 1-based first dof."""
+    tmpA = np.atleast_2d(np.asarray(tmpA, dtype=np.float64).T).T
+    tmpY = np.atleast_2d(np.asarray(tmpY, dtype=np.float64).T).T
+    lDof = tmpA.shape[1]
+    idx = np.asarray(gN, dtype=np.int64) - 1
+    if lA.ndim == 1:
+        lA[idx] = tmpA[:, 0]; lY[idx] = tmpY[:, 0]
+    else:
+        lA[idx, s - 1:s - 1 + lDof] = tmpA
+        lY[idx, s - 1:s - 1 + lDof] = tmpY
+
+
+def setbcdirl(g, gx, nV=None, lDof=3, dirA=0.0):
+    """S/SETBC.f:202-232 SETBCDIRL for a steady (std) profile: lA = dirA*gx*nV, lY = g*gx*nV when
+    lDof == nsd, else the scalar profile repeated over the dofs."""
+    gx = np.asarray(gx, dtype=np.float64)
+    if nV is not None and lDof == nV.shape[1]:
+        return dirA * gx[:, None] * nV, g * gx[:, None] * nV
+    return np.repeat((dirA * gx)[:, None], lDof, 1), np.repeat((g * gx)[:, None], lDof, 1)
+
+
+def pici(Ao, An, Yo, Yn, am, af, Do=None, Dn=None):
+    """S/PIC.f:141-152"""
+    c1, c2, c3, c4 = 1.0 - am, am, 1.0 - af, af
+    Ag = Ao * c1 + An * c2
+    Yg = Yo * c3 + Yn * c4
+    if Do is None:
+        return Ag, Yg
+    return Ag, Yg, Do * c3 + Dn * c4
+
+
+def picc(An, Yn, R, gam, beta, dt, Dn=None):
+    """S/PIC.f:203-207 (the non-sstEq branch), in place"""
+    c1, c2 = gam * dt, beta * dt * dt
+    An -= R
+    Yn -= R * c1
+    if Dn is not None:
+        Dn -= R * c2

@@ -69,6 +69,8 @@ EXPORTS = [
     "gpu_solve_dev_", "gpu_ls_create_", "gpu_sparmul_", "gpu_dot_", "gpu_time_kernel_",
     "gpu_prof_enable_", "gpu_prof_reset_", "gpu_prof_get_", "gpu_launch_count_",
     "gpu_get_stream_", "gpu_sync_", "gpu_comm_mode_",
+    "gpu_pic_init_", "gpu_pic_free_", "gpu_picp_", "gpu_setbcdir_", "gpu_pici_", "gpu_picc_",
+    "gpu_pic_advance_", "gpu_pic_get_",
 ]
 
 
@@ -398,6 +400,79 @@ def prof_get():
     ms = np.zeros(NTIMERS); n = np.zeros(NTIMERS, dtype=np.int64)
     _check(lib().gpu_prof_get_(_d(ms), n.ctypes.data_as(C.POINTER(C.c_int64))))
     return {name: (float(ms[i]), int(n[i])) for i, name in enumerate(PROF_SLOTS)}
+
+
+# ---------------------------------------------------------------------------------------------
+# generalised-alpha time integration on the device: PICP / SETBCDIR / PICI / PICC (S/PIC.f, S/SETBC.f)
+class EqState:
+    """the scalars of eqType that PICC's convergence decision reads (S/PIC.f:262-275, S/MOD.f)"""
+
+    def __init__(self, tol=1e-6, absTol=1e-12, minItr=1, maxItr=10):
+        self.tol, self.absTol, self.minItr, self.maxItr = tol, absTol, minItr, maxItr
+        self.itr, self.iNorm, self.pNorm, self.ok = 0, 0.0, 0.0, False
+
+
+def _iszero(x):
+    """ISZERO with one argument, S/UTIL.f:879-903"""
+    eps = np.finfo(np.float64).eps
+    a = abs(x)
+    return a / max(a, eps) < 10.0 * eps
+
+
+def pic_init(tDof, Ao, Yo, Do=None):
+    _check(lib().gpu_pic_init_(_ci(tDof), _d(_f64(Ao)), _d(_f64(Yo)),
+                               _d(_f64(Do)) if Do is not None else None))
+
+
+def PICP(gam):
+    _check(lib().gpu_picp_(_cd(gam)))
+
+
+def SETBCDIR(gN, s, tmpA, tmpY):
+    """tmpA / tmpY = (nNo_face, lDof) arrays as SETBCDIRL fills them (S/SETBC.f:202-232); s = first
+    dof (1-based) of the equation"""
+    gN = _i32(gN); tmpA = _f64(tmpA); tmpY = _f64(tmpY)
+    lDof = 1 if tmpA.ndim == 1 else tmpA.shape[1]
+    _check(lib().gpu_setbcdir_(_ci(gN.size), _i(gN), _ci(s), _ci(lDof), _d(tmpA), _d(tmpY)))
+
+
+def PICI(eq: EqState, am, af):
+    eq.itr += 1                       # S/PIC.f:139
+    _check(lib().gpu_pici_(_cd(am), _cd(af)))
+
+
+def PICC(eq: EqState, ls: "Ls", gam, beta, dt):
+    """corrector + the convergence decision of S/PIC.f:262-275 (single, uncoupled equation)"""
+    _check(lib().gpu_picc_(_cd(gam), _cd(beta), _cd(dt)))
+    eps = float(np.finfo(np.float64).eps)
+    if _iszero(ls.RI.iNorm):
+        ls.RI.iNorm = eps
+    if _iszero(eq.iNorm):
+        eq.iNorm = ls.RI.iNorm
+    if eq.itr == 1:
+        eq.pNorm = ls.RI.iNorm / eq.iNorm
+    r1 = ls.RI.iNorm / eq.iNorm
+    l1 = eq.iNorm <= eq.absTol
+    l2 = eq.itr >= eq.maxItr
+    l3 = r1 <= eq.tol
+    l4 = r1 <= eq.tol * eq.pNorm
+    l5 = eq.itr >= eq.minItr
+    if l1 or l2 or ((l3 or l4) and l5):
+        eq.ok = True
+    return eq.ok
+
+
+def pic_advance(eq: EqState | None = None):
+    _check(lib().gpu_pic_advance_())
+    if eq is not None:
+        eq.itr, eq.ok = 0, False      # S/MAIN.f:99-100
+
+
+def pic_get(which, tDof, nNo, withD=False):
+    shp = (nNo, tDof) if tDof > 1 else (nNo,)
+    A = np.zeros(shp); Y = np.zeros(shp); D = np.zeros(shp) if withD else None
+    _check(lib().gpu_pic_get_(_ci(which), _d(A), _d(Y), _d(D) if withD else None))
+    return (A, Y, D) if withD else (A, Y)
 
 
 COMM_MODES = {0: "single rank", 1: "nccl", 2: "peer-memory kernels (CUDA IPC over NVLink)",

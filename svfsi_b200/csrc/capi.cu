@@ -220,6 +220,7 @@ int32_t gpu_lhs_free_(void) {
   dev_free(&c.d_blkAdjPtr); dev_free(&c.d_blkAdj); dev_free(&c.d_nodeAdjPtr);
   dev_free(&c.d_nodeAdj); dev_free(&c.d_blkOrder); dev_free(&c.d_elemP);
   dev_free(&c.d_R); dev_free(&c.d_Val); dev_free(&c.d_Ag); dev_free(&c.d_Yg); dev_free(&c.d_Bf);
+  gpu_pic_free_();
   c.lhs = false;
   c.mesh = false;
   g_haveBf = false;

@@ -264,3 +264,81 @@ def test_heat_cg(prob):
                             api.BC_TYPE_Neu if fa["bc"] == "Neu" else api.BC_TYPE_Dir, fa["gN"],
                             fa["val"])
     api.mesh_create(p.rm.IEN, p.rm.x)
+
+
+def test_device_resident_time_loop(prob):
+    """two time steps of Newton iterations with PICP / SETBCDIR / PICI / PICC on the
+    device (no nodal vector crosses PCIe inside the loop) == the oracle's loop (NumPy PIC restatement
+    + C element loop + FSILS GMRES).  Inlet: steady parabolic Dirichlet profile along the inward
+    normal; wall: no-slip."""
+    m, p = prob
+    ga = cm.GA
+    nNo = p.rm.nNo
+    rng = np.random.default_rng(21)
+    Ao = 0.05 * rng.standard_normal((nNo, 4)); Ao[:, 3] = 0.0
+    Yo = p.Yg.copy()
+    # Dirichlet data as SETBCDIRL builds it (S/SETBC.f:202-232)
+    gin = p.faces["inlet"]["gN"]; gw = p.faces["wall"]["gN"]
+    xin = p.rm.x[gin - 1]
+    r2 = (xin[:, 0] ** 2 + xin[:, 1] ** 2) / (np.abs(p.rm.x[:, :2]).max() ** 2)
+    gx = np.clip(1.0 - r2, 0.0, None)
+    nV = np.tile(np.array([0.0, 0.0, -1.0]), (gin.size, 1))        # outward normal of the inlet cap
+    tA_in, tY_in = ora.setbcdirl(-12.0, gx, nV, 3)
+    tA_w, tY_w = np.zeros((gw.size, 3)), np.zeros((gw.size, 3))
+    lskw = dict(relTol=1e-6, absTol=1e-14, maxItr=10, dimKry=80)
+    nsteps, nnewton = 2, 3
+
+    # ---- oracle loop
+    w = cm.oracle_world([p], m.nNo)
+    par = cm.fluid_par()
+    oAo, oYo = Ao.copy(), Yo.copy()
+    o_norms = []
+    for ts in range(nsteps):
+        An, Yn = ora.picp(oAo, oYo, ga["gam"])
+        ora.setbcdir(An, Yn, gin, 1, tA_in, tY_in)
+        ora.setbcdir(An, Yn, gw, 1, tA_w, tY_w)
+        for it in range(nnewton):
+            Ag, Yg = ora.pici(oAo, An, oYo, Yn, ga["am"], ga["af"])
+            R, V = ora.construct_fluid(par, p.rm.IEN, p.rm.x, Ag, Yg, np.zeros((nNo, 3)), p.rowPtr,
+                                       p.colPtr)
+            ls_o = ora.ls_create(ora.LS_TYPE_GMRES, **lskw)
+            w.solve(ls_o, 4, [R], [V], incL=[1, 1, 1], res=[0.0, 0.0, 0.0])
+            o_norms.append((ls_o.RI.iNorm, ls_o.RI.itr))
+            ora.picc(An, Yn, R, ga["gam"], ga["beta"], cm.DT)
+        oAo, oYo = An, Yn
+
+    # ---- device loop
+    eq = api.EqState(tol=1e-30, maxItr=nnewton)
+    api.pic_init(4, Ao, Yo)
+    g_norms = []
+    for ts in range(nsteps):
+        api.PICP(ga["gam"])
+        api.SETBCDIR(gin, 1, tA_in, tY_in)
+        api.SETBCDIR(gw, 1, tA_w, tY_w)
+        while True:
+            api.PICI(eq, ga["am"], ga["af"])
+            api.construct_fluid_dev(cm.RHO, cm.MU, cm.F, cm.DT, ga["af"], ga["am"], ga["gam"],
+                                    api.ASM_GATHER)
+            api.commu_dev(4)
+            ls = api.FSILS_LS_CREATE(api.LS_TYPE_GMRES, **lskw)
+            api.solve_dev(ls, 4, incL=[1, 1, 1], res=[0.0, 0.0, 0.0])
+            g_norms.append((ls.RI.iNorm, ls.RI.itr))
+            if api.PICC(eq, ls, ga["gam"], ga["beta"], cm.DT):
+                break
+        assert eq.itr == nnewton
+        api.pic_advance(eq)
+    gA, gY = api.pic_get(0, 4, nNo)
+    assert len(g_norms) == len(o_norms) == nsteps * nnewton
+    for (gi, gitr), (oi, oitr) in zip(g_norms, o_norms):
+        assert abs(gitr - oitr) <= 1
+        # the first Newton residual of a step is O(1e3); later ones drop by orders: compare relative
+        assert abs(gi - oi) <= 1e-7 * max(oi, 1e-12 * o_norms[0][0]) + 1e-9 * o_norms[0][0]
+    assert np.linalg.norm(gY - oYo) / np.linalg.norm(oYo) <= TOL_SOL
+    assert np.linalg.norm(gA - oAo) / np.linalg.norm(oAo) <= 1e-6   # A = increments / (gam dt): amplified
+    # Dirichlet nodes hold exactly the imposed values
+    # (rim nodes belong to both faces: the wall, applied last, wins -- as in the reference's bc loop)
+    eA, eY = np.zeros((nNo, 4)), np.zeros((nNo, 4))
+    ora.setbcdir(eA, eY, gin, 1, tA_in, tY_in)
+    ora.setbcdir(eA, eY, gw, 1, tA_w, tY_w)
+    both = np.union1d(gin, gw) - 1
+    assert np.array_equal(gY[both, :3], eY[both, :3])

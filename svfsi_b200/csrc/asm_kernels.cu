@@ -529,6 +529,45 @@ __global__ void __launch_bounds__(256) fluid_gather_val_kernel(int nnz, double m
   __stcs((double2 *)(Val + (size_t)p * 16) + q, make_double2(acc0, acc1));
 }
 
+// Kernel B with tuning knobs (measured in profiles/r01_asm_variants.md): U2 = two contributions in
+// flight per lane, THREADS per CTA, MINB = minimum resident CTAs (register cap)
+template <bool U2, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) fluid_gather_val_t_kernel(
+    int nnz, double mu4, const int *__restrict__ blkOrder, const int *__restrict__ adjPtr,
+    const int *__restrict__ adj, const double *__restrict__ elemP, double *__restrict__ Val) {
+  const int lane = threadIdx.x & 31, q = lane & 7;
+  const unsigned gmask = 0xFFu << (lane & 24);
+  const int g = (int)((blockIdx.x * (unsigned)THREADS + threadIdx.x) >> 3);
+  if (g >= nnz) return;
+  const int p = blkOrder ? __ldg(blkOrder + g) : g;
+  const int s = __ldg(adjPtr + p), e = __ldg(adjPtr + p + 1);
+  double acc0 = 0.0, acc1 = 0.0;
+  for (int base = s; base < e; base += 8) {
+    const int mine = base + q;
+    const int cq = (mine < e) ? __ldg(adj + mine) : 0;
+    const int cnt = min(8, e - base);
+    int k = 0;
+    if (U2) {
+      for (; k + 1 < cnt; k += 2) {
+        const int pa = __shfl_sync(gmask, cq, k, 8), pb = __shfl_sync(gmask, cq, k + 1, 8);
+        double a0, a1, b0, b1;
+        tangent_pair<1>(elemP + (size_t)(pa >> 4) * F_COUNT, (pa >> 2) & 3, pa & 3, q, mu4, a0, a1);
+        tangent_pair<1>(elemP + (size_t)(pb >> 4) * F_COUNT, (pb >> 2) & 3, pb & 3, q, mu4, b0, b1);
+        acc0 += a0; acc1 += a1;
+        acc0 += b0; acc1 += b1;
+      }
+    }
+    for (; k < cnt; k++) {
+      const int pk = __shfl_sync(gmask, cq, k, 8);
+      double v0, v1;
+      tangent_pair<1>(elemP + (size_t)(pk >> 4) * F_COUNT, (pk >> 2) & 3, pk & 3, q, mu4, v0, v1);
+      acc0 += v0;
+      acc1 += v1;
+    }
+  }
+  __stcs((double2 *)(Val + (size_t)p * 16) + q, make_double2(acc0, acc1));
+}
+
 // Kernel A, second version: register budget capped at 128 (four CTAs of 128 threads per SM instead
 // of two) and the record staged through shared memory in two halves of 40 fields, so that the
 // staging buffer (41 KB per CTA) no longer limits residency.
@@ -653,12 +692,14 @@ void launch_fluid_asm(cudaStream_t st, const FluidPar &par, int n, int e0, const
 }
 
 // bit 0: record kernel v2 (128 registers, two-pass staging); bit 1: chunked gather kernel.
-// Default = 0 (both measured SLOWER on B200, profiles/r01_asm_variants.md); SVFSI_ASM_TUNE overrides (used by the kernel-variant timings in profiles/).
+// bits 2..4: knobs of the templated tangent-gather kernel (1 = two contributions in flight,
+// 2 = 128-thread CTAs, 4 = 32-register cap).  Default = 8 (128-thread CTAs, the only knob that measured
+// faster on B200: profiles/r01_asm_variants.md); SVFSI_ASM_TUNE overrides (used by the kernel-variant timings in profiles/).
 int asm_tune() {
   static int t = -1;
   if (t < 0) {
     const char *e = getenv("SVFSI_ASM_TUNE");
-    t = e ? atoi(e) : 0;
+    t = e ? atoi(e) : 8;
   }
   return t;
 }
@@ -685,9 +726,21 @@ void launch_fluid_gather_parts(cudaStream_t st, int parts, const FluidPar &par, 
   }
   if (parts & 2) {
     count_launch();
+    const size_t lanes = (size_t)nnz * 8;
+#define GV(U2, T, MB)                                                                          \
+  fluid_gather_val_t_kernel<U2, T, MB><<<(unsigned)((lanes + T - 1) / T), T, 0, st>>>(           \
+      nnz, 4.0 * par.mu, blkOrder, blkAdjPtr, blkAdj, elemP, Val)
+    const int knob = tune >> 2;   // bits 2..: 1 = U2, 2 = 128 threads, 4 = 32-register cap
     if (tune & 2)
       fluid_gather_val2_kernel<<<(unsigned)((nnz + GCH - 1) / GCH), 256, 0, st>>>(
           nnz, 4.0 * par.mu, blkOrder, blkAdjPtr, blkAdj, elemP, Val);
+    else if (knob == 1) GV(true, 256, 1);
+    else if (knob == 2) GV(false, 128, 1);
+    else if (knob == 3) GV(true, 128, 1);
+    else if (knob == 4) GV(false, 256, 8);
+    else if (knob == 5) GV(true, 256, 8);
+    else if (knob == 6) GV(false, 128, 16);
+    else if (knob == 7) GV(true, 128, 16);
     else
       fluid_gather_val_kernel<<<(unsigned)(((size_t)nnz * 8 + 255) / 256), 256, 0, st>>>(
           nnz, 4.0 * par.mu, blkOrder, blkAdjPtr, blkAdj, elemP, Val);

@@ -17,9 +17,10 @@ api.state_upload(4, p.Ag, p.Yg, None)
 bench.newton_step_dev(api, api.ASM_GATHER)
 api.sync()
 out = dict(nEl=int(p.rm.nEl), nnz=int(p.colPtr.size))
-for part, name in ((1, "record"), (2, "gather_val"), (4, "gather_r")):
-    for tune in (0, 3):
+for part, name, tunes in ((1, "record", (0, 1)), (2, "gather_val", (0, 2, 4, 8, 12, 16, 20, 24, 28)),
+                          (4, "gather_r", (0,))):
+    for tune in tunes:
         api.time_kernel(5, 4, part, 2, tune)
-        out[f"{name}_v{1 if tune else 0}_ms"] = api.time_kernel(5, 4, part, 10, tune) / 10
+        out[f"{name}_tune{tune}_ms"] = api.time_kernel(5, 4, part, 10, tune) / 10
 print(json.dumps(out))
 api.finalize()

@@ -213,6 +213,24 @@ int32_t gpu_picc_(const double *gam, const double *beta, const double *dt); /* S
 int32_t gpu_pic_advance_(void);                                  /* S/MAIN.f:277-279 */
 int32_t gpu_pic_get_(const int32_t *which, double *A, double *Y, double *D); /* 0 old, 1 new */
 
+/* ---- face integrals on the device ----------------------------------------
+ * gpu_face_create_: one mesh face (faceType: gN, IEN, gE of S/MOD.f) of TRI3 elements on a TET4
+ *   mesh; ids 1-based in svFSI's local numbering; call after gpu_mesh_create_.
+ * gpu_bassem_neu_fluid_: BASSEMNEUBC + BFLUID + GNNB + DOASSEM (S/EQASSEM.f:90-192,
+ *   S/FLUID.f:1279-1336, S/NN.f:1856-1996, S/LHSA.f:266-298) for one Neumann face: adds the
+ *   traction residual and the backflow-stabilisation tangent to the device-resident R / Val, reading
+ *   the device-resident Yg.  hgN(a) = hg(gN(a)) as SETBCNEUL builds it (S/SETBC.f:292-306).
+ * gpu_face_integ_v_: IntegV (S/ALLFUN.f:199-262) of dofs s..s+2 of Yg (which = 0) or of the
+ *   time integrator's Yn (which = 1), summed over ranks -- what a resistance BC multiplies by r. */
+int32_t gpu_face_create_(const int32_t *iFa, const int32_t *nNo, const int32_t *gN,
+                         const int32_t *nEl, const int32_t *eNoN, const int32_t *IEN,
+                         const int32_t *gE);
+int32_t gpu_face_free_(const int32_t *iFa);
+int32_t gpu_bassem_neu_fluid_(const int32_t *iFa, const double *hgN, const double *rho,
+                              const double *bfStab, const double *af, const double *gam,
+                              const double *dt);
+int32_t gpu_face_integ_v_(const int32_t *iFa, const int32_t *which, const int32_t *s, double *flux);
+
 int32_t gpu_launch_count_(int64_t *n);
 /* how the halo sums / all-reduces travel: 0 single rank, 1 NCCL send/recv + all-reduce,
  * 2 peer-memory kernels (CUDA IPC over NVLink), 3 peer-memory with the halo send fused into the

@@ -322,3 +322,98 @@ def picc(An, Yn, R, gam, beta, dt, Dn=None):
     Yn -= R * c1
     if Dn is not None:
         Dn -= R * c2
+
+
+# ---------------------------------------------------------------------------------------------
+# Face integrals (TRI3 faces of a TET4 mesh), NumPy restatement vectorised over face elements.
+_TRI3_W = 1.0 / 6.0                                             # S/NN.f:417
+
+
+def tri3_N(g):
+    """S/NN.f:416-422 (Gauss points) and :1100-1103 (shape functions)"""
+    s, t = 2.0 / 3.0, 1.0 / 6.0
+    x1 = s if g == 1 else t
+    x2 = s if g == 2 else t
+    return np.array([x1, x2, 1.0 - x1 - x2])
+
+
+def gnnb_tri3(x, fIEN, IEN, gE):
+    """GNNB, S/NN.f:1856-1996 for TRI3-in-TET4: n = CROSS(xXi) with xXi(:,i) = sum_a Nx(i,a) lX(:,ptr(a)),
+    Nx = [[1,0,-1],[0,1,-1]]; flipped so that n.(x_ptr(1) - x_offface) >= 0.  Ids 1-based.  Returns the
+    area-weighted normals (nEl, 3)."""
+    f = np.asarray(fIEN, dtype=np.int64) - 1
+    par = np.asarray(IEN, dtype=np.int64)[np.asarray(gE, dtype=np.int64) - 1] - 1     # (nEl, 4)
+    onface = (par[:, :, None] == f[:, None, :]).any(axis=2)
+    if not (onface.sum(axis=1) == 3).all():
+        raise ValueError("could not find matching face nodes")
+    opp = par[~onface]                                               # one per element
+    x0, x1, x2 = x[f[:, 0]], x[f[:, 1]], x[f[:, 2]]
+    a = (0.0 + 1.0 * x0 + 0.0 * x1) + (-1.0) * x2
+    b = (0.0 + 0.0 * x0 + 1.0 * x1) + (-1.0) * x2
+    n = np.cross(a, b)
+    v = x0 - x[opp]
+    flip = np.einsum("ij,ij->i", n, v) < 0.0
+    n[flip] = -n[flip]
+    return n
+
+
+def bassem_neu_fluid(x, IEN, fIEN, gE, hg, Yg, rowPtr, colPtr, R, Val, rho, bfStab, af, gam, dt):
+    """BASSEMNEUBC (S/EQASSEM.f:90-192) + BFLUID (S/FLUID.f:1279-1336, nsd = 3, no mesh motion) +
+    DOASSEM (S/LHSA.f:266-298), in place on R (tnNo, 4) and Val (nnz, 16).  hg: (tnNo,) nodal
+    Neumann values; Yg: (tnNo, 4).  rowPtr / colPtr 1-based CSR of svFSI."""
+    f = np.asarray(fIEN, dtype=np.int64) - 1
+    nEl = f.shape[0]
+    n = gnnb_tri3(x, fIEN, IEN, gE)
+    Jac = np.sqrt((n * n).sum(axis=1))
+    nV = n / Jac[:, None]
+    w = _TRI3_W * Jac
+    wl = w * af * gam * dt
+    hl = hg[f]                       # (nEl, 3)
+    yl = Yg[f][:, :, :3]             # (nEl, 3 nodes, 3)
+    lR = np.zeros((nEl, 3, 3)); lK = np.zeros((nEl, 3, 3))
+    for g in range(3):
+        N = tri3_N(g)
+        h = np.zeros(nEl); u = np.zeros((nEl, 3))
+        for a in range(3):
+            h = h + N[a] * hl[:, a]
+            u = u + N[a] * yl[:, a, :]
+        udn = np.zeros(nEl)
+        for i in range(3):
+            udn = udn + u[:, i] * nV[:, i]
+        udn = 0.5 * bfStab * rho * (udn - np.abs(udn))
+        hc = h[:, None] * nV + udn[:, None] * u
+        for a in range(3):
+            for i in range(3):
+                lR[:, a, i] = lR[:, a, i] - w * N[a] * hc[:, i]
+            for b in range(3):
+                lK[:, a, b] = lK[:, a, b] - wl * N[a] * N[b] * udn
+    rp = np.asarray(rowPtr, dtype=np.int64) - 1
+    cp = np.asarray(colPtr, dtype=np.int64) - 1
+    V = Val.reshape(-1, 16)
+    for e in range(nEl):             # element order = accumulation order of the reference
+        for a in range(3):
+            row = f[e, a]
+            R[row, :3] += lR[e, a]
+            for b in range(3):
+                seg = cp[rp[row]:rp[row + 1]]
+                p = rp[row] + int(np.searchsorted(seg, f[e, b]))
+                V[p, 0] += lK[e, a, b]; V[p, 5] += lK[e, a, b]; V[p, 10] += lK[e, a, b]
+    return lR, lK
+
+
+def integ_v(x, IEN, fIEN, gE, S):
+    """IntegV, S/ALLFUN.f:199-262: flux of the nodal vector S (tnNo, 3) through the face (one rank)"""
+    f = np.asarray(fIEN, dtype=np.int64) - 1
+    n = gnnb_tri3(x, fIEN, IEN, gE)
+    tot = 0.0
+    acc = np.zeros(f.shape[0])
+    for g in range(3):
+        N = tri3_N(g)
+        sHat = np.zeros(f.shape[0])
+        for a in range(3):
+            for i in range(3):
+                sHat = sHat + N[a] * S[f[:, a], i] * n[:, i]
+        acc = acc + _TRI3_W * sHat
+    for v in acc:
+        tot = tot + v
+    return tot

@@ -71,6 +71,7 @@ EXPORTS = [
     "gpu_get_stream_", "gpu_sync_", "gpu_comm_mode_",
     "gpu_pic_init_", "gpu_pic_free_", "gpu_picp_", "gpu_setbcdir_", "gpu_pici_", "gpu_picc_",
     "gpu_pic_advance_", "gpu_pic_get_",
+    "gpu_face_create_", "gpu_face_free_", "gpu_bassem_neu_fluid_", "gpu_face_integ_v_",
 ]
 
 
@@ -473,6 +474,29 @@ def pic_get(which, tDof, nNo, withD=False):
     A = np.zeros(shp); Y = np.zeros(shp); D = np.zeros(shp) if withD else None
     _check(lib().gpu_pic_get_(_ci(which), _d(A), _d(Y), _d(D) if withD else None))
     return (A, Y, D) if withD else (A, Y)
+
+
+# ---------------------------------------------------------------------------------------------
+# face integrals on the device: BASSEMNEUBC/BFLUID (S/EQASSEM.f:90-192, S/FLUID.f:1279-1336), IntegV
+def face_create(iFa, gN, IEN, gE):
+    """gN (nNo,), IEN (nEl, 3), gE (nEl,): 1-based ids in svFSI's local numbering (faceType)"""
+    gN = _i32(gN); IEN = _i32(IEN); gE = _i32(gE)
+    _check(lib().gpu_face_create_(_ci(iFa), _ci(gN.size), _i(gN), _ci(gE.size), _ci(3), _i(IEN), _i(gE)))
+
+
+def face_free(iFa):
+    _check(lib().gpu_face_free_(_ci(iFa)))
+
+
+def BASSEMNEUBC_FLUID(iFa, hgN, rho, bfStab, af, gam, dt):
+    hgN = _f64(hgN)
+    _check(lib().gpu_bassem_neu_fluid_(_ci(iFa), _d(hgN), _cd(rho), _cd(bfStab), _cd(af), _cd(gam), _cd(dt)))
+
+
+def IntegV(iFa, which=0, s=1):
+    out = C.c_double()
+    _check(lib().gpu_face_integ_v_(_ci(iFa), _ci(which), _ci(s), C.byref(out)))
+    return out.value
 
 
 COMM_MODES = {0: "single rank", 1: "nccl", 2: "peer-memory kernels (CUDA IPC over NVLink)",

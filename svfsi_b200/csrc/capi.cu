@@ -13,6 +13,7 @@
 using namespace svfsi;
 
 namespace svfsi {
+void faces_free_all();   // face.cu
 int solver_bcpre(int nsd, double *sS);
 }
 
@@ -221,6 +222,7 @@ int32_t gpu_lhs_free_(void) {
   dev_free(&c.d_nodeAdj); dev_free(&c.d_blkOrder); dev_free(&c.d_elemP);
   dev_free(&c.d_R); dev_free(&c.d_Val); dev_free(&c.d_Ag); dev_free(&c.d_Yg); dev_free(&c.d_Bf);
   gpu_pic_free_();
+  faces_free_all();
   c.lhs = false;
   c.mesh = false;
   g_haveBf = false;

@@ -85,6 +85,10 @@ __global__ void setbcdir_kernel(int faNo, int tDof, int s, int lDof, const int *
   lY[at] = tmpY[t];
 }
 
+const double *pic_state_Yn() {
+  return (g_pic.Yn && g_pic.gen == ctx().lhsGen && g_pic.tDof == 4) ? g_pic.Yn : nullptr;
+}
+
 static int pic_ready() {
   Ctx &c = ctx();
   if (!c.lhs) return fail(SVFSI_ERR_STATE, "gpu_pic_*: FSILS_LHS_CREATE has not been called");

@@ -110,3 +110,15 @@ def rounding_floor(relTol, sD, mItr, res_out, ls_type=None, seeds=(1, 2, 3), **k
         ff = max(ff, abs(lsk.RI.fNorm - ls1.RI.fNorm) / ls1.RI.fNorm)
         di = max(di, abs(lsk.RI.itr - ls1.RI.itr))
     return fx, ff, di
+
+
+def local_face(m, rm, name):
+    """One rank's share of mesh face `name` in svFSI's local numbering (faceType gN / IEN / gE,
+    1-based), as PARTFACE leaves it (S/DISTRIBUTE.f:1679-1698)."""
+    fa = m.faces[name]
+    sel = rm.faces[name]["tri_sel"]
+    gtl = np.zeros(m.nNo + 1, dtype=np.int64)
+    gtl[rm.ltg] = np.arange(1, rm.ltg.size + 1)
+    fIEN = gtl[fa.tri[sel].astype(np.int64)].astype(np.int32)
+    gE = (np.searchsorted(rm.elems, fa.parent[sel]) + 1).astype(np.int32)
+    return rm.faces[name]["gN"], fIEN, gE

@@ -342,3 +342,46 @@ def test_device_resident_time_loop(prob):
     ora.setbcdir(eA, eY, gw, 1, tA_w, tY_w)
     both = np.union1d(gin, gw) - 1
     assert np.array_equal(gY[both, :3], eY[both, :3])
+
+
+@pytest.mark.parametrize("name,h,flow", [("outlet", 7.5, 1.0), ("outlet", -2.0, -1.0), ("inlet", 3.0, 1.0)])
+def test_face_neumann_assembly_and_flux(prob, name, h, flow):
+    """BASSEMNEUBC + BFLUID + GNNB + DOASSEM and IntegV on the device == oracle.
+    flow = -1 reverses the velocity so that the backflow-stabilisation branch (udn < 0) and its
+    tangent are exercised on the outlet; on the inlet the physiological flow is already 'backflow'."""
+    m, p = prob
+    gN, fIEN, gE = cm.local_face(m, p.rm, name)
+    iFa = dict(inlet=1, wall=2, outlet=3)[name]
+    api.face_create(iFa, gN, fIEN, gE)
+    Yg = p.Yg.copy(); Yg[:, :3] *= flow
+    ga = cm.GA
+    # oracle: element loop, then the face
+    par = cm.fluid_par()
+    Ro, Vo = ora.construct_fluid(par, p.rm.IEN, p.rm.x, p.Ag, Yg, np.zeros((p.rm.nNo, 3)), p.rowPtr, p.colPtr)
+    R0, V0 = Ro.copy(), Vo.copy()
+    hg = np.zeros(p.rm.nNo); hg[gN - 1] = -h
+    ora.bassem_neu_fluid(p.rm.x, p.rm.IEN, fIEN, gE, hg, Yg, p.rowPtr, p.colPtr, Ro, Vo, cm.RHO, 0.2,
+                         ga["af"], ga["gam"], cm.DT)
+    # device
+    api.CONSTRUCT_FLUID(p.Ag, Yg, None, cm.RHO, cm.MU, cm.F, cm.DT, ga["af"], ga["am"], ga["gam"],
+                        api.ASM_GATHER)
+    api.BASSEMNEUBC_FLUID(iFa, hg[gN - 1], cm.RHO, 0.2, ga["af"], ga["gam"], cm.DT)
+    R, V = api.get_R(4), api.get_Val(4)
+    assert cm.rel_err(R, Ro) <= TOL_ASM
+    assert max(cm.block_class_errs(V, Vo).values()) <= TOL_ASM
+    # the face part alone, relative to its own size (it is small next to the volume terms)
+    dR, dRo = R - api_free_R(p, Yg), Ro - R0
+    assert np.abs(dR - dRo).max() <= 1e-9 * np.abs(dRo).max()
+    if flow * (1 if name == "outlet" else -1) < 0:
+        assert np.abs(Vo - V0).max() > 0           # the backflow tangent really was exercised
+    flux = api.IntegV(iFa, which=0, s=1)
+    ref = ora.integ_v(p.rm.x, p.rm.IEN, fIEN, gE, Yg[:, :3])
+    assert abs(flux - ref) <= 1e-12 * abs(ref)
+    api.face_free(iFa)
+
+
+def api_free_R(p, Yg):
+    ga = cm.GA
+    api.CONSTRUCT_FLUID(p.Ag, Yg, None, cm.RHO, cm.MU, cm.F, cm.DT, ga["af"], ga["am"], ga["gam"],
+                        api.ASM_GATHER)
+    return api.get_R(4)

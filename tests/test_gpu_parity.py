@@ -266,11 +266,14 @@ def test_heat_cg(prob):
     api.mesh_create(p.rm.IEN, p.rm.x)
 
 
-def test_device_resident_time_loop(prob):
-    """two time steps of Newton iterations with PICP / SETBCDIR / PICI / PICC on the
-    device (no nodal vector crosses PCIe inside the loop) == the oracle's loop (NumPy PIC restatement
-    + C element loop + FSILS GMRES).  Inlet: steady parabolic Dirichlet profile along the inward
-    normal; wall: no-slip."""
+@pytest.mark.parametrize("resist", [0.0, 40.0])
+def test_device_resident_time_loop(prob, resist):
+    """SURVEY.md 8f-1/8f-2 (the shape of BASELINE configs[0], 04-fluid/01-pipe3D_RCR): two time steps
+    of Newton iterations with PICP / SETBCDIR / PICI / element loop / Neumann face / COMMU / FSILS_SOLVE
+    / PICC all on the device (no nodal vector crosses PCIe inside the loop) == the oracle's loop (NumPy
+    PIC + face restatements, C element loop + FSILS GMRES).  Inlet: steady parabolic Dirichlet profile
+    along the inward normal; wall: no-slip; outlet: resistance BC h = r * IntegV(Yn) (S/SETBC.f:282-283)
+    whose rank-one tangent enters the linear solve as res = gam*dt*r (S/MAIN.f:186-192, ADDBCMUL)."""
     m, p = prob
     ga = cm.GA
     nNo = p.rm.nNo
@@ -285,14 +288,17 @@ def test_device_resident_time_loop(prob):
     nV = np.tile(np.array([0.0, 0.0, -1.0]), (gin.size, 1))        # outward normal of the inlet cap
     tA_in, tY_in = ora.setbcdirl(-12.0, gx, nV, 3)
     tA_w, tY_w = np.zeros((gw.size, 3)), np.zeros((gw.size, 3))
+    gout, fIEN, gE = cm.local_face(m, p.rm, "outlet")
     lskw = dict(relTol=1e-6, absTol=1e-14, maxItr=10, dimKry=80)
+    res = [0.0, 0.0, ga["gam"] * cm.DT * resist]
+    bf = 0.2                                                       # backflow_stab default
     nsteps, nnewton = 2, 3
 
     # ---- oracle loop
     w = cm.oracle_world([p], m.nNo)
     par = cm.fluid_par()
     oAo, oYo = Ao.copy(), Yo.copy()
-    o_norms = []
+    o_norms, o_flux = [], []
     for ts in range(nsteps):
         An, Yn = ora.picp(oAo, oYo, ga["gam"])
         ora.setbcdir(An, Yn, gin, 1, tA_in, tY_in)
@@ -301,8 +307,14 @@ def test_device_resident_time_loop(prob):
             Ag, Yg = ora.pici(oAo, An, oYo, Yn, ga["am"], ga["af"])
             R, V = ora.construct_fluid(par, p.rm.IEN, p.rm.x, Ag, Yg, np.zeros((nNo, 3)), p.rowPtr,
                                        p.colPtr)
+            if resist:
+                q = ora.integ_v(p.rm.x, p.rm.IEN, fIEN, gE, Yn[:, :3])
+                o_flux.append(q)
+                hg = np.zeros(nNo); hg[gout - 1] = -(resist * q) * 1.0
+                ora.bassem_neu_fluid(p.rm.x, p.rm.IEN, fIEN, gE, hg, Yg, p.rowPtr, p.colPtr, R, V,
+                                     cm.RHO, bf, ga["af"], ga["gam"], cm.DT)
             ls_o = ora.ls_create(ora.LS_TYPE_GMRES, **lskw)
-            w.solve(ls_o, 4, [R], [V], incL=[1, 1, 1], res=[0.0, 0.0, 0.0])
+            w.solve(ls_o, 4, [R], [V], incL=[1, 1, 1], res=res)
             o_norms.append((ls_o.RI.iNorm, ls_o.RI.itr))
             ora.picc(An, Yn, R, ga["gam"], ga["beta"], cm.DT)
         oAo, oYo = An, Yn
@@ -310,7 +322,9 @@ def test_device_resident_time_loop(prob):
     # ---- device loop
     eq = api.EqState(tol=1e-30, maxItr=nnewton)
     api.pic_init(4, Ao, Yo)
-    g_norms = []
+    if resist:
+        api.face_create(3, gout, fIEN, gE)
+    g_norms, g_flux = [], []
     for ts in range(nsteps):
         api.PICP(ga["gam"])
         api.SETBCDIR(gin, 1, tA_in, tY_in)
@@ -319,20 +333,29 @@ def test_device_resident_time_loop(prob):
             api.PICI(eq, ga["am"], ga["af"])
             api.construct_fluid_dev(cm.RHO, cm.MU, cm.F, cm.DT, ga["af"], ga["am"], ga["gam"],
                                     api.ASM_GATHER)
+            if resist:
+                q = api.IntegV(3, which=1, s=1)
+                g_flux.append(q)
+                api.BASSEMNEUBC_FLUID(3, np.full(gout.size, -(resist * q) * 1.0), cm.RHO, bf, ga["af"],
+                                      ga["gam"], cm.DT)
             api.commu_dev(4)
             ls = api.FSILS_LS_CREATE(api.LS_TYPE_GMRES, **lskw)
-            api.solve_dev(ls, 4, incL=[1, 1, 1], res=[0.0, 0.0, 0.0])
+            api.solve_dev(ls, 4, incL=[1, 1, 1], res=res)
             g_norms.append((ls.RI.iNorm, ls.RI.itr))
             if api.PICC(eq, ls, ga["gam"], ga["beta"], cm.DT):
                 break
         assert eq.itr == nnewton
         api.pic_advance(eq)
     gA, gY = api.pic_get(0, 4, nNo)
+    if resist:
+        api.face_free(3)
     assert len(g_norms) == len(o_norms) == nsteps * nnewton
     for (gi, gitr), (oi, oitr) in zip(g_norms, o_norms):
         assert abs(gitr - oitr) <= 1
         # the first Newton residual of a step is O(1e3); later ones drop by orders: compare relative
         assert abs(gi - oi) <= 1e-7 * max(oi, 1e-12 * o_norms[0][0]) + 1e-9 * o_norms[0][0]
+    for qg, qo in zip(g_flux, o_flux):
+        assert abs(qg - qo) <= 1e-8 * abs(qo)
     assert np.linalg.norm(gY - oYo) / np.linalg.norm(oYo) <= TOL_SOL
     assert np.linalg.norm(gA - oAo) / np.linalg.norm(oAo) <= 1e-6   # A = increments / (gam dt): amplified
     # Dirichlet nodes hold exactly the imposed values

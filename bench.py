@@ -138,7 +138,7 @@ def newton_step_dev(api, variant):
     """device-resident Newton iteration: R=0, Val=0, element loop, COMMU(R), FSILS_SOLVE"""
     if PHYSICS == "heat":
         api.construct_heats_dev(HEAT["nu"], HEAT["s"], HEAT["rho"], DT, GA["af"], GA["am"], GA["gam"],
-                                min(variant, 1))
+                                variant)
         api.commu_dev(1)
         ls = make_ls(api)
         api.solve_dev(ls, 1, incL=[1, 1])
@@ -154,7 +154,7 @@ def newton_step_e2e(api, variant, Ag, Yg, Rout):
     """same step through the reference-facing calls with HOST buffers"""
     if PHYSICS == "heat":
         api.CONSTRUCT_HEATS(Ag, Yg, HEAT["nu"], HEAT["s"], HEAT["rho"], DT, GA["af"], GA["am"],
-                            GA["gam"], min(variant, 1))
+                            GA["gam"], variant)
         api.commu_dev(1)
         ls = make_ls(api)
         api.solve_dev(ls, 1, incL=[1, 1])

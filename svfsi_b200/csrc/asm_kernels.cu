@@ -837,6 +837,119 @@ __global__ void __launch_bounds__(128) heat_asm_kernel(HeatPar par, int n, int e
   }
 }
 
+// Gather variant for heatS (dof = 1), same owner-computes scheme as the fluid one: kernel A writes
+// a 20-double record per element (lK(4,4) then lR(4)), kernel B gives every scalar Val entry to
+// one thread that sums the (element, a, b) triples around its edge in ascending element order,
+// kernel C does the same per node for R.  Deterministic, no atomics, no zero fill.
+static constexpr int HREC = 20;
+__global__ void __launch_bounds__(128) heat_record_kernel(HeatPar par, int n,
+                                                          const int *__restrict__ ien,
+                                                          const double *__restrict__ x,
+                                                          const double *__restrict__ Ag,
+                                                          const double *__restrict__ Yg,
+                                                          double *__restrict__ rec,
+                                                          int *__restrict__ badJac) {
+  __shared__ double sm[HREC][129];
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) {
+    Tet4Tab tab;
+    tet4_tab(tab);
+    int nd[4];
+    {
+      const int4 v = __ldg((const int4 *)ien + e);
+      nd[0] = v.x; nd[1] = v.y; nd[2] = v.z; nd[3] = v.w;
+    }
+    double xl[4][3], al[4], yl[4];
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      const double *xp = x + (size_t)nd[a] * 3;
+      xl[a][0] = __ldg(xp); xl[a][1] = __ldg(xp + 1); xl[a][2] = __ldg(xp + 2);
+      al[a] = __ldg(Ag + nd[a]);
+      yl[a] = __ldg(Yg + nd[a]);
+    }
+    double Nx[4][3], Jac, ks[3][3];
+    gnn_tet4(xl, Nx, Jac, ks);
+    if (iszero1(Jac)) atomicAdd(badJac, 1);
+    const double T1 = par.af * par.gam * par.dt;
+    const double amd = par.am * par.rho / T1;
+    const double w = (1.0 / 24.0) * Jac;
+    const double wl = w * T1;
+    double Tx[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int i = 0; i < 3; i++) Tx[i] = Tx[i] + Nx[a][i] * yl[a];
+    double lR[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+      double Td = -par.s;
+#pragma unroll
+      for (int a = 0; a < 4; a++) Td = Td + tab.N[g][a] * al[a];
+      Td = Td * par.rho;
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+        lR[a] = lR[a] + w * (tab.N[g][a] * Td +
+                             (Nx[a][0] * Tx[0] + Nx[a][1] * Tx[1] + Nx[a][2] * Tx[2]) * par.nu);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        double v = 0.0;
+#pragma unroll
+        for (int g = 0; g < 4; g++)
+          v = v + wl * (tab.N[g][a] * tab.N[g][b] * amd +
+                        par.nu * (Nx[a][0] * Nx[b][0] + Nx[a][1] * Nx[b][1] + Nx[a][2] * Nx[b][2]));
+        sm[a * 4 + b][threadIdx.x] = v;
+      }
+      sm[16 + a][threadIdx.x] = lR[a];
+    }
+  }
+  __syncthreads();
+  const int nHere = min(128, n - (int)blockIdx.x * 128);
+  double *out = rec + (size_t)blockIdx.x * 128 * HREC;
+  for (int t = threadIdx.x; t < nHere * HREC; t += 128) {
+    const int s = t / HREC, f = t - s * HREC;
+    out[t] = sm[f][s];
+  }
+}
+__global__ void __launch_bounds__(256) heat_gather_val_kernel(int nnz, const int *__restrict__ adjPtr,
+                                                              const int *__restrict__ adj,
+                                                              const double *__restrict__ rec,
+                                                              double *__restrict__ Val) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nnz) return;
+  double acc = 0.0;
+  for (int k = __ldg(adjPtr + p); k < __ldg(adjPtr + p + 1); k++) {
+    const int pk = __ldg(adj + k);
+    acc += __ldg(rec + (size_t)(pk >> 4) * HREC + (pk & 15));
+  }
+  Val[p] = acc;
+}
+__global__ void __launch_bounds__(256) heat_gather_r_kernel(int nNo, const int *__restrict__ adjPtr,
+                                                            const int *__restrict__ adj,
+                                                            const double *__restrict__ rec,
+                                                            double *__restrict__ R) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nNo) return;
+  double acc = 0.0;
+  for (int k = __ldg(adjPtr + t); k < __ldg(adjPtr + t + 1); k++) {
+    const int pk = __ldg(adj + k);
+    acc += __ldg(rec + (size_t)(pk >> 2) * HREC + 16 + (pk & 3));
+  }
+  R[t] = acc;
+}
+void launch_heat_gather(cudaStream_t st, const HeatPar &par, int nEl, int nNo, int nnz,
+                        const int *ien, const double *x, const double *Ag, const double *Yg,
+                        double *rec, const int *blkAdjPtr, const int *blkAdj, const int *nodeAdjPtr,
+                        const int *nodeAdj, double *R, double *Val, int *badJac) {
+  if (nEl <= 0) return;
+  count_launch(3);
+  heat_record_kernel<<<(nEl + 127) / 128, 128, 0, st>>>(par, nEl, ien, x, Ag, Yg, rec, badJac);
+  heat_gather_val_kernel<<<(nnz + 255) / 256, 256, 0, st>>>(nnz, blkAdjPtr, blkAdj, rec, Val);
+  heat_gather_r_kernel<<<(nNo + 255) / 256, 256, 0, st>>>(nNo, nodeAdjPtr, nodeAdj, rec, R);
+}
+
 void launch_heat_asm(cudaStream_t st, const HeatPar &par, int n, int e0, const int *elems,
                      const int *ien, const int *edest, const double *x, const double *Ag,
                      const double *Yg, double *R, double *Val, int atomic, int *badJac) {

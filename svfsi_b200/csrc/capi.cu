@@ -132,8 +132,10 @@ int run_heat_asm(const HeatPar &par, int variant) {
   Ctx &c = ctx();
   if (!c.mesh) return fail(SVFSI_ERR_STATE, "gpu_mesh_create_ has not been called");
   if (int rc = ensure_system(1)) return rc;
-  CUDA_TRY(cudaMemsetAsync(c.d_R, 0, sizeof(double) * (size_t)c.nNo, c.stream));
-  CUDA_TRY(cudaMemsetAsync(c.d_Val, 0, sizeof(double) * (size_t)c.nnz, c.stream));
+  if (variant != SVFSI_ASM_GATHER) {
+    CUDA_TRY(cudaMemsetAsync(c.d_R, 0, sizeof(double) * (size_t)c.nNo, c.stream));
+    CUDA_TRY(cudaMemsetAsync(c.d_Val, 0, sizeof(double) * (size_t)c.nnz, c.stream));
+  }
   CUDA_TRY(cudaMemsetAsync(c.d_flag, 0, sizeof(int), c.stream));
   {
     ProfScope ps(PROF_ASM);
@@ -145,6 +147,11 @@ int run_heat_asm(const HeatPar &par, int variant) {
         launch_heat_asm(c.stream, par, c.colorOff[k + 1] - c.colorOff[k], c.colorOff[k],
                         c.d_colorElems, c.d_ien, c.d_edest, c.d_x, c.d_Ag, c.d_Yg, c.d_R, c.d_Val, 0,
                         c.d_flag);
+    } else if (variant == SVFSI_ASM_GATHER) {
+      if (!c.d_elemP) CUDA_TRY(cudaMalloc(&c.d_elemP, sizeof(double) * 80 * (size_t)c.nEl));
+      launch_heat_gather(c.stream, par, c.nEl, c.nNo, c.nnz, c.d_ien, c.d_x, c.d_Ag, c.d_Yg,
+                         c.d_elemP, c.d_blkAdjPtr, c.d_blkAdj, c.d_nodeAdjPtr, c.d_nodeAdj, c.d_R,
+                         c.d_Val, c.d_flag);
     } else {
       return fail(SVFSI_ERR_ARG, "unknown assembly variant");
     }

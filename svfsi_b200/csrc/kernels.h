@@ -183,6 +183,11 @@ void launch_fluid_gather(cudaStream_t st, const FluidPar &par, int nEl, int nNo,
                          const double *Bf, double *elemP, const int *blkOrder,
                          const int *blkAdjPtr, const int *blkAdj, const int *nodeAdjPtr,
                          const int *nodeAdj, double *R, double *Val, int *badJac);
+// heatS gather variant; rec >= 20 doubles per element (the fluid record buffer is reused)
+void launch_heat_gather(cudaStream_t st, const HeatPar &par, int nEl, int nNo, int nnz,
+                        const int *ien, const double *x, const double *Ag, const double *Yg,
+                        double *rec, const int *blkAdjPtr, const int *blkAdj, const int *nodeAdjPtr,
+                        const int *nodeAdj, double *R, double *Val, int *badJac);
 // the three kernels separately (parts: 1 records, 2 tangent gather, 4 residual gather) with an
 // explicit kernel-variant mask (see asm_tune()); used by gpu_time_kernel_
 void launch_fluid_gather_parts(cudaStream_t st, int parts, const FluidPar &par, int nEl, int nNo,

@@ -134,6 +134,67 @@ def main():
         if (ls.GM.itr, ls.CG.itr) == (ls_o.GM.itr, ls_o.CG.itr):
             check(tag + " step", err <= 1e-8, f"err={err:.2e}")
 
+    # ---- BICGS and PRECONDRCS across ranks (RCS: the halo SUMS the per-rank row/col maxima, L/PRECOND.f:320)
+    for lst, prec, relTol in [("BICGS", "FSILS", 1e-4), ("GMRES", "RCS", 1e-4), ("BICGS", "RCS", 1e-2)]:
+        lst_o = dict(BICGS=ora.LS_TYPE_BICGS, GMRES=ora.LS_TYPE_GMRES)[lst]
+        lst_g = dict(BICGS=api.LS_TYPE_BICGS, GMRES=api.LS_TYPE_GMRES)[lst]
+        prec_o = dict(FSILS=ora.PRECOND_FSILS, RCS=ora.PRECOND_RCS)[prec]
+        prec_g = dict(FSILS=api.PRECOND_FSILS, RCS=api.PRECOND_RCS)[prec]
+        api.CONSTRUCT_FLUID(p.Ag, p.Yg, None, cm.RHO, cm.MU, cm.F, cm.DT, cm.GA["af"], cm.GA["am"],
+                            cm.GA["gam"], api.ASM_GATHER)
+        api.commu_dev(4)
+        ls = api.FSILS_LS_CREATE(lst_g, relTol=relTol, absTol=1e-14, maxItr=300, dimKry=60)
+        api.solve_dev(ls, 4, prec=prec_g, incL=[1, 1, 1], res=[0.0, 0.0, 0.0])
+        X = api.get_R(4)
+        ls_o, G = cm.oracle_gmres_global(world, relTol, 60, 300, 0.0, dims=dims, L=L, ls_type=lst_o,
+                                         prec=prec_o)
+        Xref = G[p.rm.ltg - 1]
+        num = torch.tensor([float(((X - Xref) ** 2).sum()), float((Xref ** 2).sum())],
+                           dtype=torch.float64, device="cuda")
+        dist.all_reduce(num)
+        err = float(torch.sqrt(num[0] / num[1]))
+        fx = 0.0; di = 0
+        for sd in (1, 2):
+            lp, Gp = cm.oracle_gmres_global(world, relTol, 60, 300, 0.0, dims=dims, L=L, ls_type=lst_o,
+                                            prec=prec_o, perturb=sd)
+            fx = max(fx, float(np.linalg.norm(Gp - G) / np.linalg.norm(G))); di = max(di, abs(lp.RI.itr - ls_o.RI.itr))
+        tag = f"{lst}/{prec} relTol={relTol}"
+        check(tag + " itr", abs(ls.RI.itr - ls_o.RI.itr) <= max(1, di), f"{ls.RI.itr} vs {ls_o.RI.itr} (floor {di})")
+        check(tag + " iNorm", abs(ls.RI.iNorm - ls_o.RI.iNorm) <= 1e-10 * ls_o.RI.iNorm)
+        if ls.RI.itr == ls_o.RI.itr:
+            check(tag + " step", err <= max(1e-8, 4 * fx), f"err={err:.2e} floor={fx:.2e}")
+
+    # ---- Neumann face + flux + device-resident PIC state across ranks
+    gout, fIEN, gE = cm.local_face(m, p.rm, "outlet")
+    api.face_create(3, gout, fIEN, gE)
+    ga = cm.GA
+    Ao = np.zeros((p.rm.nNo, 4)); Yo = p.Yg.copy()
+    api.pic_init(4, Ao, Yo)
+    api.PICP(ga["gam"])
+    eqs = api.EqState(maxItr=1)
+    api.PICI(eqs, ga["am"], ga["af"])
+    q = api.IntegV(3, which=1, s=1)
+    qref = 0.0
+    for r_ in range(world):
+        go, fI, gEr = cm.local_face(m, probs[r_].rm, "outlet")
+        if gEr.size:
+            qref += ora.integ_v(probs[r_].rm.x, probs[r_].rm.IEN, fI, gEr, probs[r_].Yg[:, :3])
+    check("IntegV(Yn) over ranks", abs(q - qref) <= 1e-12 * abs(qref), f"{q} {qref}")
+    An_o, Yn_o = ora.picp(Ao, Yo, ga["gam"])
+    Ag_o, Yg_o = ora.pici(Ao, An_o, Yo, Yn_o, ga["am"], ga["af"])
+    Ro, Vo = ora.construct_fluid(cm.fluid_par(), p.rm.IEN, p.rm.x, Ag_o, Yg_o, np.zeros((p.rm.nNo, 3)),
+                                 p.rowPtr, p.colPtr)
+    hg = np.zeros(p.rm.nNo); hg[gout - 1] = -25.0 * q
+    if gE.size:
+        ora.bassem_neu_fluid(p.rm.x, p.rm.IEN, fIEN, gE, hg, Yg_o, p.rowPtr, p.colPtr, Ro, Vo, cm.RHO, 0.2,
+                             ga["af"], ga["gam"], cm.DT)
+    api.construct_fluid_dev(cm.RHO, cm.MU, cm.F, cm.DT, ga["af"], ga["am"], ga["gam"], api.ASM_GATHER)
+    api.BASSEMNEUBC_FLUID(3, hg[gout - 1], cm.RHO, 0.2, ga["af"], ga["gam"], cm.DT)
+    check("PICP/PICI + element loop + Neumann face R", cm.rel_err(api.get_R(4), Ro) <= 1e-12)
+    check("PICP/PICI + element loop + Neumann face Val",
+          max(cm.block_class_errs(api.get_Val(4), Vo).values()) <= 1e-12)
+    api.face_free(3)
+
     # ---- heat / CG (dof = 1)
     api.FSILS_LHS_FREE()
     api.FSILS_LHS_CREATE(m.nNo, p.rm.nNo, p.colPtr.size, p.rm.ltg, p.rowPtr, p.colPtr, 2)
@@ -156,7 +217,7 @@ def main():
     wh.solve(ls_o, 1, Rhc, [v.copy() for v in Vh], incL=[1, 1], res=None)
     g = p.rm.ltg - 1
     api.CONSTRUCT_HEATS(Ad[g], Tg[g], 1.0, 0.0, 1.0, cm.DT, cm.GA["af"], cm.GA["am"], cm.GA["gam"],
-                        api.ASM_ATOMIC)
+                        api.ASM_GATHER)
     check("heat assembly", cm.rel_err(api.get_Val(1), Vh[rank]) <= 1e-12)
     api.commu_dev(1)
     ls = api.FSILS_LS_CREATE(api.LS_TYPE_CG, relTol=1e-8, absTol=1e-14, maxItr=500)

@@ -63,7 +63,7 @@ def test_heat_assembly(prob):
     Tg = rng.uniform(0, 1, p.rm.nNo); Ad = rng.uniform(-1, 1, p.rm.nNo)
     par = ora.heat_par(1.3, 0.2, 1.1, cm.DT, cm.GA["af"], cm.GA["am"], cm.GA["gam"])
     Rr, Vr = ora.construct_heats(par, p.rm.IEN, p.rm.x, Ad, Tg, p.rowPtr, p.colPtr)
-    for variant in (api.ASM_ATOMIC, api.ASM_COLORED):
+    for variant in (api.ASM_ATOMIC, api.ASM_COLORED, api.ASM_GATHER):
         api.CONSTRUCT_HEATS(Ad, Tg, 1.3, 0.2, 1.1, cm.DT, cm.GA["af"], cm.GA["am"], cm.GA["gam"],
                             variant)
         assert cm.rel_err(api.get_R(1), Rr) <= TOL_ASM

@@ -231,6 +231,9 @@ int32_t gpu_bassem_neu_fluid_(const int32_t *iFa, const double *hgN, const doubl
                               const double *dt);
 int32_t gpu_face_integ_v_(const int32_t *iFa, const int32_t *which, const int32_t *s, double *flux);
 
+/* algorithmic bytes (nnz*(8 BR BC + 4) + nNo*(8 + 8 BR + 8 BC)) and count of the
+ * FSILS_SPARMUL* operations issued since gpu_prof_reset_ while profiling was enabled */
+int32_t gpu_prof_spmv_(double *bytes, int64_t *ops);
 int32_t gpu_launch_count_(int64_t *n);
 /* how the halo sums / all-reduces travel: 0 single rank, 1 NCCL send/recv + all-reduce,
  * 2 peer-memory kernels (CUDA IPC over NVLink), 3 peer-memory with the halo send fused into the

@@ -72,6 +72,7 @@ EXPORTS = [
     "gpu_pic_init_", "gpu_pic_free_", "gpu_picp_", "gpu_setbcdir_", "gpu_pici_", "gpu_picc_",
     "gpu_pic_advance_", "gpu_pic_get_",
     "gpu_face_create_", "gpu_face_free_", "gpu_bassem_neu_fluid_", "gpu_face_integ_v_",
+    "gpu_prof_spmv_",
 ]
 
 
@@ -401,6 +402,12 @@ def prof_get():
     ms = np.zeros(NTIMERS); n = np.zeros(NTIMERS, dtype=np.int64)
     _check(lib().gpu_prof_get_(_d(ms), n.ctypes.data_as(C.POINTER(C.c_int64))))
     return {name: (float(ms[i]), int(n[i])) for i, name in enumerate(PROF_SLOTS)}
+
+
+def prof_spmv():
+    b = C.c_double(); n = C.c_int64()
+    _check(lib().gpu_prof_spmv_(C.byref(b), C.byref(n)))
+    return b.value, n.value
 
 
 # ---------------------------------------------------------------------------------------------

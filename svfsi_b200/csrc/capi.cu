@@ -720,12 +720,19 @@ int32_t gpu_prof_reset_(void) {
   Ctx &c = ctx();
   prof_collect();
   for (int i = 0; i < PROF_NSLOTS; i++) { c.profMs[i] = 0.0; c.profN[i] = 0; }
+  c.profSpmvBytes = 0.0;
+  c.profSpmvOps = 0;
   return 0;
 }
 int32_t gpu_prof_get_(double *ms, int64_t *launches) {
   Ctx &c = ctx();
   prof_collect();
   for (int i = 0; i < PROF_NSLOTS; i++) { ms[i] = c.profMs[i]; launches[i] = c.profN[i]; }
+  return 0;
+}
+int32_t gpu_prof_spmv_(double *bytes, int64_t *ops) {
+  *bytes = ctx().profSpmvBytes;
+  *ops = ctx().profSpmvOps;
   return 0;
 }
 int32_t gpu_launch_count_(int64_t *n) {

@@ -401,6 +401,11 @@ int sparmul(int kind, int dof, const double *K, const double *U, double *KU, con
   Ctx &c = ctx();
   if (kind == 3) dof = 1;
   const int rd = row_dof(kind, dof);
+  if (c.prof) {  // nnz*(8 BR BC + 4) + nNo*(8 + 8 BR + 8 BC), this rank
+    const int cd = col_dof(kind, dof);
+    c.profSpmvBytes += (double)c.nnz * (8.0 * rd * cd + 4.0) + (double)c.nNo * (8.0 + 8.0 * rd + 8.0 * cd);
+    c.profSpmvOps += 1;
+  }
   if (c.nranks > 1 && !c.nbr.empty() && c.p2p.on && c.p2p.fuse) {
     // ONE kernel: boundary rows in the first CTAs, their results stored straight into the
     // neighbours' receive buffers, flags raised by the last boundary CTA, interior rows behind

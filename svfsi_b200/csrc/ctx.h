@@ -150,6 +150,8 @@ struct Ctx {
   size_t evUsed = 0;
   double profMs[PROF_NSLOTS] = {0};
   int64_t profN[PROF_NSLOTS] = {0};
+  double profSpmvBytes = 0.0;   // algorithmic bytes of the SpMVs issued while profiling
+  int64_t profSpmvOps = 0;
 };
 
 Ctx &ctx();

@@ -9,6 +9,7 @@
 // grids sized as multiples of the 148 SMs, reductions by warp shuffles, and no
 // host synchronisation inside the Krylov loop (kernels test a device flag).
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "ctx.h"
@@ -239,6 +240,139 @@ __global__ void __launch_bounds__(256) spmv_generic_fused_kernel(SpmvFuse f,
   fuse_publish(f);
 }
 
+// ---------------------------------------------------------------------------
+// "Flat row" SpMV for the small block shapes of NSSOLVER / CG (3x3, 1x3, 3x1, 1x1, 2x2, 1x2, 2x1):
+// T lanes own one block row and read its values as ONE contiguous run of doubles -- lane t takes
+// flat entries t, t+T, ... of the row, so a warp instruction covers whole 128-byte lines (the
+// lane-per-block kernel above touches a different line per lane and is bound by L1 wavefronts,
+// 8.7 per 72-byte block).  T is a multiple of BR*BC, hence every lane keeps a fixed (l, m) entry
+// position and needs one U component; the T/BR partial sums of an output row meet in shared
+// memory and are added in a fixed order (deterministic).  32/T rows per warp.
+template <int BR, int BC, int T>
+struct FlatCfg {
+  static constexpr int BB = BR * BC;       // doubles per block
+  static constexpr int BPI = T / BB;       // blocks per iteration
+  static constexpr int RPW = 32 / T;       // rows per warp
+  static constexpr int RPC = RPW * 8;      // rows per 256-thread CTA
+  static_assert(T % BB == 0 && T <= 32, "T must be a multiple of the block size");
+};
+template <int BR, int BC, int T>
+__device__ __forceinline__ void spmv_flat_row(bool laneOk, bool have, int row, int sub, int t,
+                                              const int *__restrict__ rowPtr,
+                                              const int *__restrict__ col,
+                                              const double *__restrict__ K,
+                                              const double *__restrict__ U, double *smw,
+                                              double &out) {
+  using C = FlatCfg<BR, BC, T>;
+  const int lb = t / C::BB, e = t - lb * C::BB, m = e % BC;
+  double acc = 0.0;
+  if (have) {
+    const int s = __ldg(rowPtr + row), end = __ldg(rowPtr + row + 1);
+    for (int j = s + lb; j < end; j += C::BPI) {
+      const int c = __ldg(col + j);
+      acc = fma(__ldcs(K + (size_t)j * C::BB + e), __ldg(U + (size_t)c * BC + m), acc);
+    }
+  }
+  if (laneOk) smw[sub * T + t] = acc;   // lanes beyond RPW*T own no slot
+  __syncwarp();
+  out = 0.0;
+  if (have && t < BR) {        // lane t adds the partials of output row l = t: blocks, then m
+#pragma unroll
+    for (int b = 0; b < C::BPI; b++)
+#pragma unroll
+      for (int mm = 0; mm < BC; mm++) out += smw[sub * T + b * C::BB + t * BC + mm];
+  }
+  __syncwarp();
+}
+
+template <int BR, int BC, int T>
+__global__ void __launch_bounds__(256) spmv_flat_kernel(int r0, int r1, int r2, int r3,
+                                                        const int *__restrict__ rowPtr,
+                                                        const int *__restrict__ col,
+                                                        const double *__restrict__ K,
+                                                        const double *__restrict__ U,
+                                                        double *__restrict__ KU, const int *done) {
+  DONE_GUARD(done);
+  using C = FlatCfg<BR, BC, T>;
+  __shared__ double sm[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int sub = lane / T, t = lane - sub * T;
+  int row = r0 + ((int)blockIdx.x * 8 + w) * C::RPW + sub;
+  if (row >= r1) row += r2 - r1;
+  const bool have = (sub < C::RPW) && (row < r3);
+  double out;
+  spmv_flat_row<BR, BC, T>(sub < C::RPW, have, row, sub, t, rowPtr, col, K, U, sm[w], out);
+  if (have && t < BR) KU[(size_t)row * BR + t] = out;
+}
+
+template <int BR, int BC, int T>
+__global__ void __launch_bounds__(256) spmv_flat_fused_kernel(SpmvFuse f,
+                                                              const int *__restrict__ rowPtr,
+                                                              const int *__restrict__ col,
+                                                              const double *__restrict__ K,
+                                                              const double *__restrict__ U,
+                                                              double *__restrict__ KU,
+                                                              const int *done) {
+  using C = FlatCfg<BR, BC, T>;
+  __shared__ double sm[8][32];
+  const bool skip = (done != nullptr && *(volatile const int *)done != 0);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int sub = lane / T, t = lane - sub * T;
+  int row = 0, bidx = -1;
+  bool have = false;
+  if (sub < C::RPW) have = fuse_map_row(f, C::RPC, w * C::RPW + sub, row, bidx);
+  have = have && !skip;
+  double out;
+  spmv_flat_row<BR, BC, T>(sub < C::RPW, have, row, sub, t, rowPtr, col, K, U, sm[w], out);
+  if (have && t < BR) {
+    KU[(size_t)row * BR + t] = out;
+    if (bidx >= 0) fuse_send(f, bidx, BR, t, out);
+  }
+  fuse_publish(f);
+}
+
+template <int BR, int BC, int T>
+static void launch_flat(cudaStream_t st, int r0, int r1, int r2, int r3, const int *rowPtr,
+                        const int *col, const double *K, const double *U, double *KU,
+                        const int *done) {
+  const int rows = (r1 - r0) + (r3 - r2);
+  const int rpc = FlatCfg<BR, BC, T>::RPC;
+  spmv_flat_kernel<BR, BC, T><<<(rows + rpc - 1) / rpc, 256, 0, st>>>(r0, r1, r2, r3, rowPtr, col, K,
+                                                                      U, KU, done);
+}
+template <int BR, int BC, int T>
+static void launch_flat_fused(cudaStream_t st, SpmvFuse f, const int *rowPtr, const int *col,
+                              const double *K, const double *U, double *KU, const int *done) {
+  const int rpc = FlatCfg<BR, BC, T>::RPC;
+  f.bndCtas = (f.nBnd + rpc - 1) / rpc;
+  const int inner = f.mynNo - f.shnNo;
+  const int blocks = f.bndCtas + (inner + rpc - 1) / rpc;
+  if (blocks <= 0) return;
+  spmv_flat_fused_kernel<BR, BC, T><<<blocks, 256, 0, st>>>(f, rowPtr, col, K, U, KU, done);
+}
+// shape -> kernel.  MEASURED SLOWER than the lane-per-block kernels on B200 (10M tets: NSSOLVER step
+// 12.8 vs 9.5 ms of SpMV, heat CG 7.1 vs 2.8 ms; profiles/r01_spmv_shapes.md): with ~15 blocks per row
+// the per-row overhead (row pointers, shared-memory meeting point, serial tail) outweighs the
+// coalescing gain.  Kept behind SVFSI_SPMV_FLAT=1 as a measured negative result; default off.
+static bool use_flat() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("SVFSI_SPMV_FLAT");
+    v = (e && atoi(e) == 1) ? 1 : 0;
+  }
+  return v != 0;
+}
+#define FLAT_DISPATCH(CALL)                                              \
+  do {                                                                   \
+    if (kind == 3 || dof == 1) { CALL(1, 1, 16); return; }               \
+    if (kind == 0 && dof == 3) { CALL(3, 3, 27); return; }               \
+    if (kind == 0 && dof == 2) { CALL(2, 2, 16); return; }               \
+    if (kind == 1 && dof == 3) { CALL(1, 3, 15); return; }               \
+    if (kind == 2 && dof == 3) { CALL(3, 1, 15); return; }               \
+    if (kind == 1 && dof == 2) { CALL(1, 2, 16); return; }               \
+    if (kind == 2 && dof == 2) { CALL(2, 1, 16); return; }               \
+  } while (0)
+
 template <int BR, int BC>
 static void launch_generic(cudaStream_t st, int r0, int r1, int r2, int r3, const int *rowPtr,
                            const int *col, const double *K, const double *U, double *KU,
@@ -261,6 +395,11 @@ void launch_spmv2(cudaStream_t st, int kind, int dof, int r0, int r1, int r2, in
     spmv_vv4_kernel<<<blocks, 256, 0, st>>>(r0, r1, r2, r3, rowPtr, col, (const double2 *)K,
                                             (const double2 *)U, KU, done);
     return;
+  }
+  if (use_flat()) {
+#define FL(BR, BC, T) launch_flat<BR, BC, T>(st, r0, r1, r2, r3, rowPtr, col, K, U, KU, done)
+    FLAT_DISPATCH(FL);
+#undef FL
   }
 #define GEN(BR, BC) launch_generic<BR, BC>(st, r0, r1, r2, r3, rowPtr, col, K, U, KU, done)
   if (kind == 3 || dof == 1) {
@@ -288,6 +427,11 @@ void launch_spmv_fused(cudaStream_t st, int kind, int dof, SpmvFuse f, const int
                        const int *done) {
   count_launch();
   const bool vv4 = (kind == 0 && dof == 4);
+  if (!vv4 && use_flat()) {
+#define FLF(BR, BC, T) launch_flat_fused<BR, BC, T>(st, f, rowPtr, col, K, U, KU, done)
+    FLAT_DISPATCH(FLF);
+#undef FLF
+  }
   const int rpc = vv4 ? 32 : 64;
   f.bndCtas = (f.nBnd + rpc - 1) / rpc;
   const int inner = f.mynNo - f.shnNo;

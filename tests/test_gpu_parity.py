@@ -408,3 +408,80 @@ def api_free_R(p, Yg):
     api.CONSTRUCT_FLUID(p.Ag, Yg, None, cm.RHO, cm.MU, cm.F, cm.DT, ga["af"], ga["am"], ga["gam"],
                         api.ASM_GATHER)
     return api.get_R(4)
+
+
+def test_mesh_files_and_restart_continuity(prob, tmp_path):
+    """the formats either side of the path.  (i) the case written as a svFSI-Tests
+    style `mesh-complete` directory and read back gives the same arrays and therefore the same CSR
+    pattern the device was set up with; (ii) two time steps on the device, state written as a
+    WRITERESTART record (S/OUTPUT.f:204-205) + a results .vtu, read back (INITFROMBIN,
+    S/INITIALIZE.f:512-620), third step run from the restored state == the third step of the
+    uninterrupted run, bit for bit (gather assembly and the single-GPU Krylov loop are deterministic)."""
+    from svfsi_b200 import vtkio
+    m, p = prob
+    d = str(tmp_path / "case")
+    # the case in the numbering the device was set up with (one rank's local ids)
+    case = mesh.Mesh(x=p.rm.x, IEN=p.rm.IEN)
+    for name in cm.FACE_ORDER:
+        gN, fIEN, gE = cm.local_face(m, p.rm, name)
+        case.faces[name] = mesh.Face(name, gN, fIEN, gE - 1)
+    vtkio.write_mesh_complete(case, d, compress=True)
+    x, IEN, faces = vtkio.read_mesh_complete(d)
+    assert np.array_equal(x, p.rm.x) and np.array_equal(IEN, p.rm.IEN)
+    rowPtr, colPtr = mesh.csr_pattern(x.shape[0], IEN)
+    assert np.array_equal(rowPtr, p.rowPtr) and np.array_equal(colPtr, p.colPtr)
+    for name in cm.FACE_ORDER:
+        assert np.array_equal(faces[name]["gN"], p.faces[name]["gN"])
+
+    ga = cm.GA
+    nNo = p.rm.nNo
+    rng = np.random.default_rng(5)
+    Ao = 0.05 * rng.standard_normal((nNo, 4)); Ao[:, 3] = 0.0
+    Yo = p.Yg.copy()
+    gw = faces["wall"]["gN"]
+    tz = np.zeros((gw.size, 3))
+    lskw = dict(relTol=1e-6, absTol=1e-14, maxItr=10, dimKry=80)
+
+    def steps(n, eq):
+        for _ in range(n):
+            api.PICP(ga["gam"])
+            api.SETBCDIR(gw, 1, tz, tz)
+            while True:
+                api.PICI(eq, ga["am"], ga["af"])
+                api.construct_fluid_dev(cm.RHO, cm.MU, cm.F, cm.DT, ga["af"], ga["am"], ga["gam"],
+                                        api.ASM_GATHER)
+                api.commu_dev(4)
+                ls = api.FSILS_LS_CREATE(api.LS_TYPE_GMRES, **lskw)
+                api.solve_dev(ls, 4, incL=[0, 0, 0], res=[0.0, 0.0, 0.0])
+                if api.PICC(eq, ls, ga["gam"], ga["beta"], cm.DT):
+                    break
+            api.pic_advance(eq)
+
+    eq = api.EqState(tol=1e-30, maxItr=2)
+    api.pic_init(4, Ao, Yo)
+    steps(3, eq)
+    A3, Y3 = api.pic_get(0, 4, nNo)
+
+    eq = api.EqState(tol=1e-30, maxItr=2)
+    api.pic_init(4, Ao, Yo)
+    steps(2, eq)
+    A2, Y2 = api.pic_get(0, 4, nNo)
+    stamp = [1, 1, 1, nNo, 0, 4, 0]
+    recLn = vtkio.restart_reclen(1, 0, 4, nNo)
+    rst = str(tmp_path / "stFile_last.bin")
+    vtkio.write_restart(rst, 1, recLn, stamp, cTS=2, time=2 * cm.DT, timeP=0.0, iNorm=[eq.iNorm], xn=[],
+                        Yn=Y2, An=A2)
+    out = str(tmp_path / "result_002.vtu")
+    vtkio.write_vtu(out, x, IEN, point_data={"Velocity": Y2[:, :3], "Pressure": Y2[:, 3]}, compress=True)
+    _, _, piece = vtkio.read_vtu(out)
+    assert np.array_equal(piece.point_data["Velocity"], Y2[:, :3])
+    assert np.array_equal(piece.point_data["Pressure"], Y2[:, 3])
+
+    got = vtkio.read_restart(rst, 1, recLn, 1, 0, 4, nNo, expect_stamp=stamp)
+    assert got["cTS"] == 2
+    eq = api.EqState(tol=1e-30, maxItr=2)
+    eq.iNorm = float(got["iNorm"][0])
+    api.pic_init(4, got["Ao"], got["Yo"])
+    steps(1, eq)
+    A3r, Y3r = api.pic_get(0, 4, nNo)
+    assert np.array_equal(Y3r, Y3) and np.array_equal(A3r, A3)

@@ -662,6 +662,146 @@ __global__ void __launch_bounds__(256) fluid_gather_r_kernel(int nNo, const int 
   R[t] = acc;
 }
 
+// ---------------------------------------------------------------------------
+// Kernels B + C, row-owner version: ONE WARP PER BLOCK ROW.  The warp walks the (element, a) pairs
+// around its node in ascending element order; at every visit lane group b = lane>>3 expands the
+// tangent block (a, b) (two entries per lane, q = lane&7) and adds it to the row's block
+// (row, ien[e][b]) held in shared memory; lanes 0..3 carry the residual.  The finished row leaves
+// as ONE coalesced streaming store of nblk*128 bytes.
+//  * b and q are lane constants, so the four cases of tangent_pair (momentum / continuity row,
+//    velocity / pressure column pair) become lane-constant COEFFICIENTS of one expression
+//        v = wl * ( P (A bi) + Q (x1 B) + T de )
+//    (coefficients 0 / 1 select exactly: 1*x and x+0 do not round), and all lane-dependent record
+//    offsets are loop invariant.  ~55 instructions and ~9 L1 wavefronts of operands per visit of four
+//    contributions; the block-owner kernel needs ~85 and ~25 (every 8-lane group reads its own two
+//    node records).
+//  * the slot of block (row, ien[e][b]) inside the row comes from nodeSlots (four 8-bit slots per
+//    visit, built once per pattern), read coalesced next to the visit list.
+//  * the four blocks of a visit are distinct (four distinct nodes of a tet), so lanes never collide
+//    inside a visit; successive visits may hit the same block from another lane group: __syncwarp.
+//  * every block still receives its contributions in ascending element order starting from 0.0:
+//    deterministic, the accumulation order of the reference's element loop.
+struct VisitOps {
+  double2 A, B, S;
+  double ai, bi, de;
+  int slot;
+};
+template <bool U2, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) fluid_gather_rows_kernel(
+    int nNo, int maxRow, double mu4, const int *__restrict__ rowPtr,
+    const int *__restrict__ nodeAdjPtr, const int *__restrict__ nodeAdj,
+    const int *__restrict__ nodeSlots, const double *__restrict__ elemP, double *__restrict__ Val,
+    double *__restrict__ R) {
+  extern __shared__ double2 smrow[];   // [WARPS][maxRow * 8]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.x * WARPS + warp;
+  if (row >= nNo) return;
+  double2 *acc = smrow + (size_t)warp * maxRow * 8 + (lane & 7);
+  const int b = lane >> 3, q = lane & 7;
+  const int i = q >> 1, j0 = (q & 1) * 2;
+  const bool row3 = (i == 3), col2 = (j0 == 2), momc0 = !row3 && !col2, byConst = col2 && !row3;
+  // lane-constant coefficients (S/FLUID.f:482-557 momentum rows, :1052-1081 continuity row)
+  const double P0 = row3 ? 1.0 : mu4;
+  const double P1 = row3 ? (col2 ? 0.0 : 1.0) : (col2 ? 1.0 : mu4);
+  const double Q1c = (row3 && col2) ? 0.0 : 1.0;
+  const double T0 = (!row3 && i == j0) ? 1.0 : 0.0;
+  const double T1 = row3 ? (col2 ? 1.0 : 0.0) : ((!col2 && i == 1) ? 1.0 : 0.0);
+  const double nsNb = -sN_of(b);
+  // lane-constant record offsets: A, ai, de relative to node record a; B, bi to the element record
+  const int oA = j0, oAi = row3 ? 0 : i, oDE = F_DE + b * 2 + (row3 ? 1 : 0);
+  const int oB = b * 8 + j0, oBi = b * 8 + (row3 ? N_R2 : i);
+  const int shift = b * 8;
+  const int rp0 = __ldg(rowPtr + row), nblk = __ldg(rowPtr + row + 1) - rp0;
+  for (int t = lane; t < nblk * 8; t += 32) smrow[(size_t)warp * maxRow * 8 + t] = make_double2(0.0, 0.0);
+  __syncwarp();
+  const int s = __ldg(nodeAdjPtr + row), e = __ldg(nodeAdjPtr + row + 1);
+  double r = 0.0;
+
+  auto load = [&](int pk, int sl, VisitOps &o, double &lr) {
+    const int a = pk & 3;
+    const double *rec = elemP + (size_t)(pk >> 2) * F_COUNT, *ra = rec + a * 8;
+    o.slot = (sl >> shift) & 0xff;
+    o.A = __ldg((const double2 *)(ra + oA));
+    o.B = __ldg((const double2 *)(rec + oB));
+    o.S = __ldg((const double2 *)(ra + N_STC));
+    o.ai = __ldg(ra + oAi);
+    o.bi = __ldg(rec + oBi);
+    o.de = __ldg(ra + oDE);
+    lr = (lane < 4) ? __ldg(rec + F_LR + a * 4 + lane) : 0.0;
+  };
+  auto apply = [&](int pk, const VisitOps &o, double lr) {
+    const double x1 = row3 ? sN_of(pk & 3) : o.ai;
+    const double Q0 = row3 ? 1.0 : o.S.x;
+    const double Q1 = momc0 ? o.S.x : Q1c;
+    const double By = byConst ? nsNb : o.B.y;
+    const double v0 = fma(T0, o.de, fma(Q0, x1 * o.B.x, P0 * (o.A.x * o.bi)));
+    const double v1 = fma(T1, o.de, fma(Q1, x1 * By, P1 * (o.A.y * o.bi)));
+    double2 c = acc[o.slot * 8];
+    c.x += v0 * o.S.y;
+    c.y += v1 * o.S.y;
+    acc[o.slot * 8] = c;
+    r += lr;
+    __syncwarp();
+  };
+
+  for (int base = s; base < e; base += 32) {
+    const bool have = base + lane < e;
+    const int mine = have ? __ldg(nodeAdj + base + lane) : 0;
+    const int mysl = have ? __ldg(nodeSlots + base + lane) : 0;
+    const int cnt = min(32, e - base);
+    int k = 0;
+    if (U2) {
+      for (; k + 1 < cnt; k += 2) {
+        const int pa = __shfl_sync(0xffffffffu, mine, k), pb = __shfl_sync(0xffffffffu, mine, k + 1);
+        const int sa = __shfl_sync(0xffffffffu, mysl, k), sb = __shfl_sync(0xffffffffu, mysl, k + 1);
+        VisitOps oa, ob;
+        double la, lb;
+        load(pa, sa, oa, la);
+        load(pb, sb, ob, lb);
+        apply(pa, oa, la);
+        apply(pb, ob, lb);
+      }
+    }
+    for (; k < cnt; k++) {
+      const int pk = __shfl_sync(0xffffffffu, mine, k);
+      const int sl = __shfl_sync(0xffffffffu, mysl, k);
+      VisitOps o;
+      double lr;
+      load(pk, sl, o, lr);
+      apply(pk, o, lr);
+    }
+  }
+  double2 *out = (double2 *)(Val + (size_t)rp0 * 16);
+  const double2 *fin = smrow + (size_t)warp * maxRow * 8;
+  for (int t = lane; t < nblk * 8; t += 32) __stcs(out + t, fin[t]);
+  if (lane < 4) R[(size_t)row * 4 + lane] = r;
+}
+
+// nodeSlots[k] for visit k = nodeAdj entry (element e, local node a) of row r: the positions inside
+// row r of the four blocks (r, ien[e][b]), 8 bits each (rows longer than 255 blocks do not use
+// the row-owner kernel)
+__global__ void build_node_slots_kernel(int nNo, const int *__restrict__ rowPtr,
+                                        const int *__restrict__ nodeAdjPtr,
+                                        const int *__restrict__ nodeAdj,
+                                        const int *__restrict__ edest, int *__restrict__ slots) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= nNo) return;
+  const int rp0 = rowPtr[row];
+  for (int k = nodeAdjPtr[row]; k < nodeAdjPtr[row + 1]; k++) {
+    const int pk = nodeAdj[k];
+    int v = 0;
+    for (int b = 0; b < 4; b++)
+      v |= ((edest[(size_t)(pk >> 2) * 16 + (pk & 3) * 4 + b] - rp0) & 0xff) << (8 * b);
+    slots[k] = v;
+  }
+}
+void launch_build_node_slots(cudaStream_t st, int nNo, const int *rowPtr, const int *nodeAdjPtr,
+                             const int *nodeAdj, const int *edest, int *slots) {
+  if (nNo <= 0) return;
+  build_node_slots_kernel<<<(nNo + 127) / 128, 128, 0, st>>>(nNo, rowPtr, nodeAdjPtr, nodeAdj, edest,
+                                                           slots);
+}
+
 static void fluid_attr_once() {
   static bool attr = false;
   if (attr) return;
@@ -709,9 +849,12 @@ void launch_fluid_gather_parts(cudaStream_t st, int parts, const FluidPar &par, 
                                const double *Yg, const double *Bf, double *elemP,
                                const int *blkOrder, const int *blkAdjPtr, const int *blkAdj,
                                const int *nodeAdjPtr, const int *nodeAdj, double *R, double *Val,
-                               int *badJac, int tune) {
+                               int *badJac, int tune, const int *rowPtr, const int *nodeSlots,
+                               int maxRow) {
   if (nEl <= 0) return;
   fluid_attr_once();
+  // bit 5: row-owner kernel (B and C in one launch); needs the row's blocks in shared memory
+  const bool rows = (tune & 32) && rowPtr && nodeSlots && maxRow > 0 && maxRow <= 64;
   if (parts & 1) {
     count_launch();
     if (tune & 1) {
@@ -723,6 +866,19 @@ void launch_fluid_gather_parts(cudaStream_t st, int parts, const FluidPar &par, 
       fluid_record_kernel<<<(nEl + NE - 1) / NE, NE, smem, st>>>(par, nEl, ien, x, Ag, Yg, Bf,
                                                                  elemP, badJac);
     }
+  }
+  if (rows && (parts & 6)) {
+    // parts 2 and 4 are one kernel here (timed under either bit)
+    count_launch();
+    constexpr int W = 4;
+    const size_t smem = (size_t)W * maxRow * 128;
+    if (tune & 64)
+      fluid_gather_rows_kernel<true, W><<<(nNo + W - 1) / W, W * 32, smem, st>>>(
+          nNo, maxRow, 4.0 * par.mu, rowPtr, nodeAdjPtr, nodeAdj, nodeSlots, elemP, Val, R);
+    else
+      fluid_gather_rows_kernel<false, W><<<(nNo + W - 1) / W, W * 32, smem, st>>>(
+          nNo, maxRow, 4.0 * par.mu, rowPtr, nodeAdjPtr, nodeAdj, nodeSlots, elemP, Val, R);
+    return;
   }
   if (parts & 2) {
     count_launch();
@@ -756,9 +912,11 @@ void launch_fluid_gather(cudaStream_t st, const FluidPar &par, int nEl, int nNo,
                          const int *ien, const double *x, const double *Ag, const double *Yg,
                          const double *Bf, double *elemP, const int *blkOrder,
                          const int *blkAdjPtr, const int *blkAdj, const int *nodeAdjPtr,
-                         const int *nodeAdj, double *R, double *Val, int *badJac) {
+                         const int *nodeAdj, double *R, double *Val, int *badJac,
+                         const int *rowPtr, const int *nodeSlots, int maxRow) {
   launch_fluid_gather_parts(st, 7, par, nEl, nNo, nnz, ien, x, Ag, Yg, Bf, elemP, blkOrder,
-                            blkAdjPtr, blkAdj, nodeAdjPtr, nodeAdj, R, Val, badJac, asm_tune());
+                            blkAdjPtr, blkAdj, nodeAdjPtr, nodeAdj, R, Val, badJac, asm_tune(),
+                            rowPtr, nodeSlots, maxRow);
 }
 
 // ---------------------------------------------------------------------------

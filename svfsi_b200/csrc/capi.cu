@@ -120,7 +120,7 @@ int run_fluid_asm(const FluidPar &par, int variant) {
       if (!c.d_elemP) CUDA_TRY(cudaMalloc(&c.d_elemP, sizeof(double) * 80 * (size_t)c.nEl));
       launch_fluid_gather(c.stream, par, c.nEl, c.nNo, c.nnz, c.d_ien, c.d_x, c.d_Ag, c.d_Yg, bf,
                           c.d_elemP, c.d_blkOrder, c.d_blkAdjPtr, c.d_blkAdj, c.d_nodeAdjPtr,
-                          c.d_nodeAdj, c.d_R, c.d_Val, c.d_flag);
+                          c.d_nodeAdj, c.d_R, c.d_Val, c.d_flag, c.d_rowPtr, c.d_nodeSlots, c.maxRowLen);
     } else {
       return fail(SVFSI_ERR_ARG, "unknown assembly variant");
     }
@@ -226,7 +226,7 @@ int32_t gpu_lhs_free_(void) {
   dev_free(&c.d_uniqPtr); dev_free(&c.d_uniqSlot); dev_free(&c.d_sbuf); dev_free(&c.d_rbuf);
   dev_free(&c.d_ien); dev_free(&c.d_edest); dev_free(&c.d_x); dev_free(&c.d_colorElems);
   dev_free(&c.d_blkAdjPtr); dev_free(&c.d_blkAdj); dev_free(&c.d_nodeAdjPtr);
-  dev_free(&c.d_nodeAdj); dev_free(&c.d_blkOrder); dev_free(&c.d_elemP);
+  dev_free(&c.d_nodeAdj); dev_free(&c.d_blkOrder); dev_free(&c.d_elemP); dev_free(&c.d_nodeSlots);
   dev_free(&c.d_R); dev_free(&c.d_Val); dev_free(&c.d_Ag); dev_free(&c.d_Yg); dev_free(&c.d_Bf);
   gpu_pic_free_();
   faces_free_all();
@@ -319,6 +319,8 @@ int32_t gpu_lhs_create_(const int32_t *gnNo_, const int32_t *nNo_, const int32_t
     if (diag[r] < 0) return fail(SVFSI_ERR_ARG, "row without a diagonal entry");
   }
   c.rowPtrDev = rp;
+  c.maxRowLen = 0;
+  for (int r = 0; r < nNo; r++) c.maxRowLen = std::max(c.maxRowLen, rp[r + 1] - rp[r]);
   if (int rc = dev_upload(&c.d_perm, c.map)) return rc;
   if (int rc = dev_upload(&c.d_rowPtr, rp)) return rc;
   if (int rc = dev_upload(&c.d_col, col)) return rc;
@@ -478,11 +480,17 @@ int32_t gpu_mesh_create_(const int32_t *nEl_, const int32_t *eNoN, const int32_t
   c.ncolors = (int)c.colorOff.size() - 1;
   if (int rc = dev_upload(&c.d_colorElems, colorElems)) return rc;
   dev_free(&c.d_blkAdjPtr); dev_free(&c.d_blkAdj); dev_free(&c.d_nodeAdjPtr);
-  dev_free(&c.d_nodeAdj); dev_free(&c.d_blkOrder); dev_free(&c.d_elemP);
+  dev_free(&c.d_nodeAdj); dev_free(&c.d_blkOrder); dev_free(&c.d_elemP); dev_free(&c.d_nodeSlots);
   if (int rc = build_gather_adjacency(c.stream, nEl, c.nNo, c.nnz, c.d_ien, c.d_edest,
                                       &c.d_blkAdjPtr, &c.d_blkAdj, &c.d_nodeAdjPtr, &c.d_nodeAdj,
                                       &c.d_blkOrder))
     return rc;
+  dev_free(&c.d_nodeSlots);
+  if (c.maxRowLen <= 64) {
+    CUDA_TRY(cudaMalloc(&c.d_nodeSlots, sizeof(int) * (size_t)nEl * 4));
+    launch_build_node_slots(c.stream, c.nNo, c.d_rowPtr, c.d_nodeAdjPtr, c.d_nodeAdj, c.d_edest,
+                            c.d_nodeSlots);
+  }
   CUDA_TRY(cudaStreamSynchronize(c.stream));
   // every (a,b) of every element must exist in the pattern
   c.mesh = true;
@@ -698,7 +706,8 @@ int32_t gpu_time_kernel_(const int32_t *what, const int32_t *dof, const int32_t 
     for (int r = 0; r < *reps; r++)
       launch_fluid_gather_parts(c.stream, *k, par, c.nEl, c.nNo, c.nnz, c.d_ien, c.d_x, c.d_Ag,
                                 c.d_Yg, nullptr, c.d_elemP, c.d_blkOrder, c.d_blkAdjPtr, c.d_blkAdj,
-                                c.d_nodeAdjPtr, c.d_nodeAdj, c.d_R, c.d_Val, c.d_flag, *variant);
+                                c.d_nodeAdjPtr, c.d_nodeAdj, c.d_R, c.d_Val, c.d_flag, *variant,
+                                c.d_rowPtr, c.d_nodeSlots, c.maxRowLen);
     CUDA_TRY(cudaEventRecord(b, c.stream));
   } else {
     return fail(SVFSI_ERR_ARG, "gpu_time_kernel_: unknown kernel id");

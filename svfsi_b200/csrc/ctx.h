@@ -92,6 +92,7 @@ struct Ctx {
   int gnNo = 0, nNo = 0, nnz = 0, nFaces = 0, mynNo = 0, shnNo = 0;
   std::vector<int> map;       // [nNo] svFSI local id (0-based) -> reordered id (0-based)
   std::vector<int> rowPtrDev; // host copy of device rowPtr (0-based, nNo+1)
+  int maxRowLen = 0;          // longest block row (sizes the row-owner assembly's shared memory)
   std::vector<Neighbor> nbr;
   std::vector<Face> face;
   int *d_perm = nullptr;     // [nNo] = map
@@ -124,6 +125,7 @@ struct Ctx {
   int *d_blkAdj = nullptr;      // [16*nEl] (e<<4 | a<<2 | b)
   int *d_nodeAdjPtr = nullptr;  // [nNo+1]
   int *d_nodeAdj = nullptr;     // [4*nEl] (e<<2 | a)
+  int *d_nodeSlots = nullptr;   // [4*nEl] row-local slots of the visit's four blocks (8 bits each)
   double *d_elemP = nullptr;    // [nEl][64] per-element compact records (gather variant)
   int *d_blkOrder = nullptr;    // [nnz padded] block processing order (length-sorted chunks)
 

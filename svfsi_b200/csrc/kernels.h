@@ -182,7 +182,8 @@ void launch_fluid_gather(cudaStream_t st, const FluidPar &par, int nEl, int nNo,
                          const int *ien, const double *x, const double *Ag, const double *Yg,
                          const double *Bf, double *elemP, const int *blkOrder,
                          const int *blkAdjPtr, const int *blkAdj, const int *nodeAdjPtr,
-                         const int *nodeAdj, double *R, double *Val, int *badJac);
+                         const int *nodeAdj, double *R, double *Val, int *badJac,
+                         const int *rowPtr = nullptr, const int *nodeSlots = nullptr, int maxRow = 0);
 // heatS gather variant; rec >= 20 doubles per element (the fluid record buffer is reused)
 void launch_heat_gather(cudaStream_t st, const HeatPar &par, int nEl, int nNo, int nnz,
                         const int *ien, const double *x, const double *Ag, const double *Yg,
@@ -195,7 +196,11 @@ void launch_fluid_gather_parts(cudaStream_t st, int parts, const FluidPar &par, 
                                const double *Yg, const double *Bf, double *elemP,
                                const int *blkOrder, const int *blkAdjPtr, const int *blkAdj,
                                const int *nodeAdjPtr, const int *nodeAdj, double *R, double *Val,
-                               int *badJac, int tune);
+                               int *badJac, int tune, const int *rowPtr = nullptr,
+                               const int *nodeSlots = nullptr, int maxRow = 0);
+// row-owner gather: positions of the four blocks of every (node, element) visit inside the row
+void launch_build_node_slots(cudaStream_t st, int nNo, const int *rowPtr, const int *nodeAdjPtr,
+                             const int *nodeAdj, const int *edest, int *slots);
 int asm_tune();
 // adjacency lists for the gather variant (built once at gpu_mesh_create_)
 int build_gather_adjacency(cudaStream_t st, int nEl, int nNo, int nnz, const int *ien,

@@ -833,13 +833,15 @@ void launch_fluid_asm(cudaStream_t st, const FluidPar &par, int n, int e0, const
 
 // bit 0: record kernel v2 (128 registers, two-pass staging); bit 1: chunked gather kernel.
 // bits 2..4: knobs of the templated tangent-gather kernel (1 = two contributions in flight,
-// 2 = 128-thread CTAs, 4 = 32-register cap).  Default = 8 (128-thread CTAs, the only knob that measured
-// faster on B200: profiles/r01_asm_variants.md); SVFSI_ASM_TUNE overrides (used by the kernel-variant timings in profiles/).
+// 2 = 128-thread CTAs, 4 = 32-register cap).  bit 5 (32): row-owner kernel for B + C (one warp per block
+// row, accumulation in shared memory); bit 6 (64): two visits in flight in it.
+// Default = 40 (row-owner kernel; 8 = the block-owner kernel with 128-thread CTAs is what runs when a
+// row is longer than 64 blocks); SVFSI_ASM_TUNE overrides (kernel-variant timings in profiles/).
 int asm_tune() {
   static int t = -1;
   if (t < 0) {
     const char *e = getenv("SVFSI_ASM_TUNE");
-    t = e ? atoi(e) : 8;
+    t = e ? atoi(e) : 40;
   }
   return t;
 }

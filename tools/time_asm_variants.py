@@ -17,8 +17,8 @@ api.state_upload(4, p.Ag, p.Yg, None)
 bench.newton_step_dev(api, api.ASM_GATHER)
 api.sync()
 out = dict(nEl=int(p.rm.nEl), nnz=int(p.colPtr.size))
-for part, name, tunes in ((1, "record", (0, 1)), (2, "gather_val", (0, 2, 4, 8, 12, 16, 20, 24, 28)),
-                          (4, "gather_r", (0,))):
+tunes_val = tuple(int(t) for t in os.environ.get("ASM_TUNES", "8,40,104").split(","))
+for part, name, tunes in ((1, "record", (0,)), (2, "gather_val", tunes_val), (4, "gather_r", (0,))):
     for tune in tunes:
         api.time_kernel(5, 4, part, 2, tune)
         out[f"{name}_tune{tune}_ms"] = api.time_kernel(5, 4, part, 10, tune) / 10

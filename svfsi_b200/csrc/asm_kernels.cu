@@ -74,7 +74,9 @@ __device__ __forceinline__ void tet4_tab(Tet4Tab &t) {
   for (int a = 0; a < 4; a++) t.sN[a] = t.N[0][a] + t.N[1][a] + t.N[2][a] + t.N[3][a];
 }
 
-// GNN for TET4, S/NN.f:1515-1561: Jacobian, inverse, metric ks, Nx
+// GNN for TET4, S/NN.f:1515-1561: Jacobian, inverse, metric ks, Nx.  FAST: one reciprocal of Jac
+// instead of nine divisions (1 ulp differences; parity tolerance is 1e-12).
+template <bool FAST = false>
 __device__ __forceinline__ void gnn_tet4(const double xl[4][3], double Nx[4][3], double &Jac,
                                          double ks[3][3]) {
   double X[3][3], XI[3][3];
@@ -84,15 +86,20 @@ __device__ __forceinline__ void gnn_tet4(const double xl[4][3], double Nx[4][3],
     for (int c = 0; c < 3; c++) X[r][c] = xl[c][r] - xl[3][r];
   Jac = X[0][0] * X[1][1] * X[2][2] + X[0][1] * X[1][2] * X[2][0] + X[0][2] * X[1][0] * X[2][1] -
         X[0][0] * X[1][2] * X[2][1] - X[0][1] * X[1][0] * X[2][2] - X[0][2] * X[1][1] * X[2][0];
-  XI[0][0] = (X[1][1] * X[2][2] - X[1][2] * X[2][1]) / Jac;
-  XI[0][1] = (X[2][1] * X[0][2] - X[2][2] * X[0][1]) / Jac;
-  XI[0][2] = (X[0][1] * X[1][2] - X[0][2] * X[1][1]) / Jac;
-  XI[1][0] = (X[1][2] * X[2][0] - X[1][0] * X[2][2]) / Jac;
-  XI[1][1] = (X[2][2] * X[0][0] - X[2][0] * X[0][2]) / Jac;
-  XI[1][2] = (X[0][2] * X[1][0] - X[0][0] * X[1][2]) / Jac;
-  XI[2][0] = (X[1][0] * X[2][1] - X[1][1] * X[2][0]) / Jac;
-  XI[2][1] = (X[2][0] * X[0][1] - X[2][1] * X[0][0]) / Jac;
-  XI[2][2] = (X[0][0] * X[1][1] - X[0][1] * X[1][0]) / Jac;
+  XI[0][0] = (X[1][1] * X[2][2] - X[1][2] * X[2][1]);
+  XI[0][1] = (X[2][1] * X[0][2] - X[2][2] * X[0][1]);
+  XI[0][2] = (X[0][1] * X[1][2] - X[0][2] * X[1][1]);
+  XI[1][0] = (X[1][2] * X[2][0] - X[1][0] * X[2][2]);
+  XI[1][1] = (X[2][2] * X[0][0] - X[2][0] * X[0][2]);
+  XI[1][2] = (X[0][2] * X[1][0] - X[0][0] * X[1][2]);
+  XI[2][0] = (X[1][0] * X[2][1] - X[1][1] * X[2][0]);
+  XI[2][1] = (X[2][0] * X[0][1] - X[2][1] * X[0][0]);
+  XI[2][2] = (X[0][0] * X[1][1] - X[0][1] * X[1][0]);
+  const double rJ = FAST ? 1.0 / Jac : 0.0;
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) XI[r][c] = FAST ? XI[r][c] * rJ : XI[r][c] / Jac;
   ks[0][0] = XI[0][0] * XI[0][0] + XI[1][0] * XI[1][0] + XI[2][0] * XI[2][0];
   ks[0][1] = XI[0][1] * XI[0][0] + XI[1][1] * XI[1][0] + XI[2][1] * XI[2][0];
   ks[0][2] = XI[0][2] * XI[0][0] + XI[1][2] * XI[1][0] + XI[2][2] * XI[2][0];
@@ -124,6 +131,7 @@ struct ElemAcc {
   double w, wl, wr;
 };
 
+template <bool FAST = false>
 __device__ __forceinline__ void fluid_elem_compute(const FluidPar &par, int e,
                                                    const int *__restrict__ ien,
                                                    const double *__restrict__ x,
@@ -157,7 +165,7 @@ __device__ __forceinline__ void fluid_elem_compute(const FluidPar &par, int e,
       }
     }
     double Nx[4][3], Jac, ks[3][3];
-    gnn_tet4(xl, Nx, Jac, ks);
+    gnn_tet4<FAST>(xl, Nx, Jac, ks);
     if (iszero1(Jac)) atomicAdd(badJac, 1);
 
     const double rho = par.rho, mu = par.mu;
@@ -201,6 +209,9 @@ __device__ __forceinline__ void fluid_elem_compute(const FluidPar &par, int e,
     tq = mu / rho;
     kS = 36.0 * kS * (tq * tq);
     const double trks = ks[0][0] + ks[1][1] + ks[2][2];
+    // FAST: tauM = rsqrt(.)/rho, tauC = rho sqrt(.)/tr(ks), tauB = rho rsqrt(.) -- two rsqrt per
+    // Gauss point instead of two sqrt + three divisions (S/FLUID.f:376-412 up to 1-2 ulp)
+    const double irho = FAST ? 1.0 / rho : 0.0, rho_itrks = FAST ? rho / trks : 0.0;
 
     // accumulators over the Gauss points
     double A[4][4], c2[4], r2[4], sTC = 0.0, sTM = 0.0;
@@ -243,21 +254,23 @@ __device__ __forceinline__ void fluid_elem_compute(const FluidPar &par, int e,
       for (int i = 0; i < 3; i++)
 #pragma unroll
         for (int j = 0; j < 3; j++) kU = kU + u[j] * u[i] * ks[j][i];
-      const double tauM = 1.0 / (rho * sqrt(kT + kU + kS));
+      const double kSum = kT + kU + kS;
+      const double rsK = FAST ? rsqrt(kSum) : 0.0;
+      const double tauM = FAST ? rsK * irho : 1.0 / (rho * sqrt(kSum));
       double rV[3], up[3], ua[3];
 #pragma unroll
       for (int i = 0; i < 3; i++) {
         rV[i] = ud[i] + u[0] * ux[0][i] + u[1] * ux[1][i] + u[2] * ux[2][i];
         up[i] = -tauM * (rho * rV[i] + px[i]);
       }
-      const double tauC = 1.0 / (tauM * trks);
+      const double tauC = FAST ? (kSum * rsK) * rho_itrks : 1.0 / (tauM * trks);
       double tauB = 0.0;
 #pragma unroll
       for (int i = 0; i < 3; i++)
 #pragma unroll
         for (int j = 0; j < 3; j++) tauB = tauB + up[j] * up[i] * ks[j][i];
       if (iszero1(tauB)) tauB = DBL_EPSILON;
-      tauB = rho / sqrt(tauB);
+      tauB = FAST ? rho * rsqrt(tauB) : rho / sqrt(tauB);
 #pragma unroll
       for (int i = 0; i < 3; i++) ua[i] = u[i] + up[i];
       const double pa = p - tauC * divU;
@@ -602,6 +615,77 @@ __global__ void __launch_bounds__(NE, 4) fluid_record2_kernel(FluidPar par, int 
   }
 }
 
+// Kernel A, third version (default): same one-thread-per-element reduction with
+//  * the FAST arithmetic of fluid_elem_compute (one reciprocal of Jac, two rsqrt per Gauss point instead
+//    of two sqrt + three divisions: ~600 fewer instructions per element),
+//  * the record staged as 40 (field 2k, field 2k+1) PAIRS: sm2[k][slot] double2 -> 40 conflict-free
+//    STS.128 per thread instead of 80 STS.64, and a copy-out of 40 LDS.128 + STG.128 per thread with
+//    incremental (slot, pair) indices (the 80-iteration loop with a division by 80 was ~20% of the
+//    kernel's instructions),
+//  * the ten distinct Nx_a.Nx_b products computed once.
+__device__ __forceinline__ void fluid_elem_store_pairs(const FluidPar &par, const ElemAcc &acc,
+                                                       double2 *rec2) {
+  const double rho = par.rho, mu = par.mu;
+  double nn[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = a; b < 4; b++) {
+      nn[a][b] = acc.Nx[a][0] * acc.Nx[b][0] + acc.Nx[a][1] * acc.Nx[b][1] + acc.Nx[a][2] * acc.Nx[b][2];
+      nn[b][a] = nn[a][b];
+    }
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    rec2[(a * 4 + 0) * NEP] = make_double2(acc.Nx[a][0], acc.Nx[a][1]);
+    rec2[(a * 4 + 1) * NEP] = make_double2(acc.Nx[a][2], rho * acc.c2[a]);
+    rec2[(a * 4 + 2) * NEP] = make_double2(acc.sTC, acc.wl);
+    rec2[(a * 4 + 3) * NEP] = make_double2(acc.sTM, rho * acc.r2[a]);
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+      rec2[(F_DE / 2 + a * 4 + b) * NEP] =
+          make_double2(4.0 * (mu * nn[a][b]) + acc.A[a][b], acc.sTM * nn[a][b]);
+    double lr[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+      lr[i] = acc.wr * acc.sNrV[a][i] +
+              acc.w * (acc.Nx[a][0] * acc.sRM[0][i] + acc.Nx[a][1] * acc.sRM[1][i] +
+                       acc.Nx[a][2] * acc.sRM[2][i]);
+    rec2[(F_LR / 2 + a * 2 + 0) * NEP] = make_double2(lr[0], lr[1]);
+    rec2[(F_LR / 2 + a * 2 + 1) * NEP] = make_double2(lr[2], acc.w * acc.lR4[a]);
+  }
+}
+__global__ void __launch_bounds__(NE) fluid_record3_kernel(FluidPar par, int n,
+                                                           const int *__restrict__ ien,
+                                                           const double *__restrict__ x,
+                                                           const double *__restrict__ Ag,
+                                                           const double *__restrict__ Yg,
+                                                           const double *__restrict__ Bf,
+                                                           double *__restrict__ elemP,
+                                                           int *__restrict__ badJac) {
+  extern __shared__ double2 sm2[];  // [F_COUNT / 2][NEP]
+  constexpr int NP = F_COUNT / 2;   // 40 pairs per element
+  const int slot = threadIdx.x;
+  const int e = blockIdx.x * NE + slot;
+  int nodes[4];
+  if (e < n) {
+    ElemAcc acc;
+    fluid_elem_compute<true>(par, e, ien, x, Ag, Yg, Bf, acc, nodes, badJac);
+    fluid_elem_store_pairs(par, acc, sm2 + slot);
+  }
+  __syncthreads();
+  const int nHere = min(NE, n - blockIdx.x * NE);
+  double2 *out = (double2 *)(elemP + (size_t)blockIdx.x * NE * F_COUNT);
+  // thread t copies pairs t, t + NE, ...: (slot, pair) advance by (NE / NP, NE % NP) with carry
+  int s = threadIdx.x / NP, k = threadIdx.x - s * NP;
+#pragma unroll 4
+  for (int t = threadIdx.x; t < nHere * NP; t += NE) {
+    __stcg(out + t, sm2[k * NEP + s]);
+    s += NE / NP;
+    k += NE % NP;
+    if (k >= NP) { k -= NP; s++; }
+  }
+}
+
 // Kernel B, second version: one CTA walks a whole chunk of GCH = 512 consecutive (length-sorted)
 // blocks in 16 rounds of 32 groups, so that the ~34 block rows of a chunk -- whose element records
 // overlap 16-fold -- are gathered through ONE SM's L1; two contributions are in flight per lane.
@@ -686,7 +770,7 @@ struct VisitOps {
   double ai, bi, de;
   int slot;
 };
-template <bool U2, int WARPS>
+template <int U, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) fluid_gather_rows_kernel(
     int nNo, int maxRow, double mu4, const int *__restrict__ rowPtr,
     const int *__restrict__ nodeAdjPtr, const int *__restrict__ nodeAdj,
@@ -750,16 +834,20 @@ __global__ void __launch_bounds__(WARPS * 32) fluid_gather_rows_kernel(
     const int mysl = have ? __ldg(nodeSlots + base + lane) : 0;
     const int cnt = min(32, e - base);
     int k = 0;
-    if (U2) {
-      for (; k + 1 < cnt; k += 2) {
-        const int pa = __shfl_sync(0xffffffffu, mine, k), pb = __shfl_sync(0xffffffffu, mine, k + 1);
-        const int sa = __shfl_sync(0xffffffffu, mysl, k), sb = __shfl_sync(0xffffffffu, mysl, k + 1);
-        VisitOps oa, ob;
-        double la, lb;
-        load(pa, sa, oa, la);
-        load(pb, sb, ob, lb);
-        apply(pa, oa, la);
-        apply(pb, ob, lb);
+    if (U > 1) {
+      // U visits in flight: all loads issued before the first accumulation (still applied in
+      // ascending visit order)
+      for (; k + U <= cnt; k += U) {
+        int pk[U];
+        VisitOps o[U];
+        double lr[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          pk[u] = __shfl_sync(0xffffffffu, mine, k + u);
+          load(pk[u], __shfl_sync(0xffffffffu, mysl, k + u), o[u], lr[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) apply(pk[u], o[u], lr[u]);
       }
     }
     for (; k < cnt; k++) {
@@ -811,6 +899,7 @@ static void fluid_attr_once() {
   cudaFuncSetAttribute(fluid_record_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaFuncSetAttribute(fluid_record2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)((size_t)40 * NEP * sizeof(double)));
+  cudaFuncSetAttribute(fluid_record3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   attr = true;
 }
 
@@ -859,7 +948,11 @@ void launch_fluid_gather_parts(cudaStream_t st, int parts, const FluidPar &par, 
   const bool rows = (tune & 32) && rowPtr && nodeSlots && maxRow > 0 && maxRow <= 64;
   if (parts & 1) {
     count_launch();
-    if (tune & 1) {
+    if (tune & 128) {
+      const size_t smem = (size_t)F_COUNT * NEP * sizeof(double);
+      fluid_record3_kernel<<<(nEl + NE - 1) / NE, NE, smem, st>>>(par, nEl, ien, x, Ag, Yg, Bf,
+                                                                  elemP, badJac);
+    } else if (tune & 1) {
       const size_t smem = (size_t)40 * NEP * sizeof(double);
       fluid_record2_kernel<<<(nEl + NE - 1) / NE, NE, smem, st>>>(par, nEl, ien, x, Ag, Yg, Bf,
                                                                   elemP, badJac);
@@ -872,14 +965,17 @@ void launch_fluid_gather_parts(cudaStream_t st, int parts, const FluidPar &par, 
   if (rows && (parts & 6)) {
     // parts 2 and 4 are one kernel here (timed under either bit)
     count_launch();
-    constexpr int W = 4;
-    const size_t smem = (size_t)W * maxRow * 128;
-    if (tune & 64)
-      fluid_gather_rows_kernel<true, W><<<(nNo + W - 1) / W, W * 32, smem, st>>>(
-          nNo, maxRow, 4.0 * par.mu, rowPtr, nodeAdjPtr, nodeAdj, nodeSlots, elemP, Val, R);
-    else
-      fluid_gather_rows_kernel<false, W><<<(nNo + W - 1) / W, W * 32, smem, st>>>(
-          nNo, maxRow, 4.0 * par.mu, rowPtr, nodeAdjPtr, nodeAdj, nodeSlots, elemP, Val, R);
+    // bit 6 (64): two visits in flight; bit 9 (512): four; bit 8 (256): 8 warps per CTA instead of 4
+#define GR(U, W)                                                                                 \
+  fluid_gather_rows_kernel<U, W><<<(nNo + W - 1) / W, W * 32, (size_t)W * maxRow * 128, st>>>(     \
+      nNo, maxRow, 4.0 * par.mu, rowPtr, nodeAdjPtr, nodeAdj, nodeSlots, elemP, Val, R)
+    const int u = (tune & 512) ? 4 : ((tune & 64) ? 2 : 1);
+    if (tune & 256) {
+      if (u == 4) GR(4, 8); else if (u == 2) GR(2, 8); else GR(1, 8);
+    } else {
+      if (u == 4) GR(4, 4); else if (u == 2) GR(2, 4); else GR(1, 4);
+    }
+#undef GR
     return;
   }
   if (parts & 2) {

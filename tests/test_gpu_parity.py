@@ -2,6 +2,8 @@
 seeded synthetic pipe.  Tolerances are the north_star's: assembled residual / tangent within
 1e-12 relative (max|diff|/max|ref| per array and per block class), GMRES iteration count
 (RI%itr = SpMV count, L/GMRES.f:315,328) within +-1, Newton-step solution within 1e-8 relative."""
+import os
+
 import numpy as np
 import pytest
 
@@ -55,6 +57,29 @@ def test_deterministic_assembly_variants_are_bitwise_repeatable(prob, variant):
     R2, V2 = gpu_assemble(p, variant)
     assert np.array_equal(R1, R2) and np.array_equal(V1, V2)
     assert api.mesh_ncolors() >= 24          # interior node valence of the Kuhn lattice
+
+
+# every kernel variant of the gather assembly behind SVFSI_ASM_TUNE (asm_kernels.cu asm_tune()):
+# records v1 / v2 / v3 x block-owner / row-owner gather (1, 2, 4 visits in flight; 4 or 8 warps)
+@pytest.mark.parametrize("tune", [0, 1, 8, 40, 104, 296, 552, 808, 128 + 8, 128 + 40, 128 + 104,
+                                  128 + 808])
+def test_gather_kernel_variants(prob, tune):
+    m, p = prob
+    Rs, Vs = cm.oracle_assemble([p])
+    gpu_assemble(p, api.ASM_GATHER)              # state resident, lists built
+    gpu_assemble(p, api.ASM_ATOMIC)              # scribble over R / Val
+    api.time_kernel(5, 4, 7, 1, tune)            # records + tangent gather + residual gather
+    R, V = api.get_R(4), api.get_Val(4)
+    assert cm.rel_err(R[:, :3], Rs[0][:, :3]) <= TOL_ASM
+    assert cm.rel_err(R[:, 3], Rs[0][:, 3]) <= TOL_ASM
+    errs = cm.block_class_errs(V, Vs[0])
+    assert max(errs.values()) <= TOL_ASM, (tune, errs)
+    api.time_kernel(5, 4, 7, 1, tune)
+    assert np.array_equal(R, api.get_R(4)) and np.array_equal(V, api.get_Val(4))   # deterministic
+    ok = os.environ.get("SVFSI_VARIANT_OK_FILE")   # tools/gpu_session.sh picks the default among these
+    if ok:
+        with open(ok, "a") as fh:
+            fh.write(f"{tune}\n")
 
 
 def test_heat_assembly(prob):

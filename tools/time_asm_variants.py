@@ -17,8 +17,12 @@ api.state_upload(4, p.Ag, p.Yg, None)
 bench.newton_step_dev(api, api.ASM_GATHER)
 api.sync()
 out = dict(nEl=int(p.rm.nEl), nnz=int(p.colPtr.size))
-tunes_val = tuple(int(t) for t in os.environ.get("ASM_TUNES", "8,40,104").split(","))
-for part, name, tunes in ((1, "record", (0,)), (2, "gather_val", tunes_val), (4, "gather_r", (0,))):
+# tune bits: asm_kernels.cu asm_tune().  8 = block-owner gather (128-thread CTAs); 32 = row-owner gather
+# (B + C in one launch), +64 / +512 = two / four visits in flight, +256 = 8 warps per CTA;
+# records: 0 = v1, 128 = v3 (pair staging, rsqrt arithmetic)
+tunes_val = tuple(int(t) for t in os.environ.get("ASM_TUNES", "8,40,104,296,360,552,808").split(","))
+tunes_rec = tuple(int(t) for t in os.environ.get("ASM_TUNES_REC", "0,128").split(","))
+for part, name, tunes in ((1, "record", tunes_rec), (2, "gather_val", tunes_val), (4, "gather_r", (0,))):
     for tune in tunes:
         api.time_kernel(5, 4, part, 2, tune)
         out[f"{name}_tune{tune}_ms"] = api.time_kernel(5, 4, part, 10, tune) / 10

@@ -41,8 +41,16 @@ _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
 
 
+# error codes of include/svfsi_b200.h
+(OK, ERR_CUDA, ERR_STATE, ERR_ARG, ERR_JAC, ERR_COMM, ERR_UNSUPPORTED) = range(7)
+
+
 class SvfsiError(RuntimeError):
-    pass
+    """A non-zero return code of the C-ABI (the reference would PRINT + STOP); `.code` holds it."""
+
+    def __init__(self, msg, code=None):
+        super().__init__(msg)
+        self.code = code
 
 
 class SubLs(C.Structure):
@@ -129,7 +137,7 @@ def _check(rc):
     if rc != 0:
         buf = C.create_string_buffer(512)
         lib().gpu_last_error_(buf, _ci(512))
-        raise SvfsiError(f"svfsi_b200 error {rc}: {buf.value.decode(errors='replace')}")
+        raise SvfsiError(f"svfsi_b200 error {rc}: {buf.value.decode(errors='replace')}", rc)
 
 
 # --------------------------------------------------------------------------- life cycle

@@ -46,23 +46,70 @@ GA = gen_alpha(RHO_INF)
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and clock-event (throttle) reasons sampled DURING the timed region (B200_PROFILING.md).
+    NVML in a thread (one sample every ~5 ms; the main thread sits in ctypes calls that release the
+    GIL), so even a 200 ms timed region gets tens of samples; `nvidia-smi -lms` as the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device):
-        self.device = device
+    def __init__(self, device, uuid=None):
+        self.device, self.uuid = device, uuid
         self.proc = None
         self.lines = []
+        self.samples = []          # (sm_mhz, reasons bitmask)
+        self.nv = None
+        self.handle = None
+        self.stop_flag = threading.Event()
+        self.t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if uuid:
+                try:
+                    u = str(uuid)
+                    h = pynvml.nvmlDeviceGetHandleByUUID(u if u.startswith("GPU-") else "GPU-" + u)
+                except Exception:
+                    h = None
+            if h is None:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                idx = device
+                if vis:
+                    ent = vis.split(",")[device].strip()
+                    if ent.isdigit():
+                        idx = int(ent)
+                    else:
+                        h = pynvml.nvmlDeviceGetHandleByUUID(ent)
+                if h is None:
+                    h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv, self.handle = pynvml, h
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        nv, h = self.nv, self.handle
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
+                                     int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        if self.nv is not None:
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            time.sleep(1.0)        # nvidia-smi needs ~0.5 s before its first sample
         except Exception:
             self.proc = None
 
@@ -71,12 +118,26 @@ class ClockSampler:
             self.lines.append(ln.strip())
 
     def stop(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        if self.nv is not None:
+            self.stop_flag.set()
+            if self.t:
+                self.t.join(timeout=1.0)
+            nv = self.nv
+            bits = dict(hw_slowdown=nv.nvmlClocksEventReasonHwSlowdown,
+                        hw_thermal_slowdown=nv.nvmlClocksEventReasonHwThermalSlowdown,
+                        sw_thermal_slowdown=nv.nvmlClocksEventReasonSwThermalSlowdown,
+                        sw_power_cap=nv.nvmlClocksEventReasonSwPowerCap,
+                        hw_power_brake=nv.nvmlClocksEventReasonHwPowerBrakeSlowdown)
+            sm = [x[0] for x in self.samples]
+            reasons = sorted(k for k, b in bits.items() if any(x[1] & b for x in self.samples))
+            return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_min_mhz=min(sm) if sm else None,
+                        sm_max_mhz=self.max_mhz, reasons=reasons, samples=len(sm), source="nvml")
         if not self.proc:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
@@ -89,7 +150,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=mx,
-                    reasons=sorted(reasons), samples=len(sm))
+                    reasons=sorted(reasons), samples=len(sm), source="nvidia-smi")
 
 
 def measured_peak():
@@ -360,7 +421,11 @@ def main():
     for _ in range(args.warmup):
         ls = newton_step_dev(api, variant)
     l0 = api.launch_count()
-    sampler = ClockSampler(local)
+    try:
+        dev_uuid = torch.cuda.get_device_properties(local).uuid
+    except Exception:
+        dev_uuid = None
+    sampler = ClockSampler(local, dev_uuid)
     if rank == 0:
         sampler.start()
     ms_dev, ls = timed(lambda: newton_step_dev(api, variant), args.steps)

@@ -77,6 +77,61 @@ static int build_lists(cudaStream_t st, size_t nItems, const int *key, int nseg,
   return 0;
 }
 
+// Pair lists for the pair-owner gather: position g of the processing order holds block p = (r,c);
+// it is kept if c >= r (or if the pattern has no (c,r) entry, which an element-built pattern never
+// does), together with the position of (c,r).
+__global__ void pair_flag_kernel(int nnz, const int *__restrict__ blkOrder,
+                                 const int *__restrict__ rowOf, const int *__restrict__ col,
+                                 const int *__restrict__ rowPtr, int *__restrict__ flag,
+                                 int *__restrict__ tposOut) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nnz) return;
+  const int p = blkOrder[g];
+  const int r = rowOf[p], c = col[p];
+  int l = -1;
+  if (r == c) l = p;
+  else
+    for (int j = rowPtr[c]; j < rowPtr[c + 1]; j++)
+      if (col[j] == r) { l = j; break; }
+  tposOut[g] = l;
+  flag[g] = (c >= r || l < 0) ? 1 : 0;
+}
+__global__ void pair_fill_kernel(int nnz, const int *__restrict__ blkOrder,
+                                 const int *__restrict__ flag, const int *__restrict__ pos,
+                                 const int *__restrict__ tpos, int *__restrict__ pairList,
+                                 int *__restrict__ pairT) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nnz || !flag[g]) return;
+  pairList[pos[g]] = blkOrder[g];
+  pairT[pos[g]] = tpos[g];
+}
+int build_pair_lists(cudaStream_t st, int nnz, const int *blkOrder, const int *rowOf, const int *col,
+                     const int *rowPtr, int **pairList, int **pairT, int *nPair) {
+  *pairList = *pairT = nullptr;
+  *nPair = 0;
+  if (nnz <= 0) return 0;
+  int *flag = nullptr, *pos = nullptr, *tp = nullptr;
+  CUDA_TRY(cudaMalloc(&flag, sizeof(int) * (size_t)nnz));
+  CUDA_TRY(cudaMalloc(&pos, sizeof(int) * (size_t)nnz));
+  CUDA_TRY(cudaMalloc(&tp, sizeof(int) * (size_t)nnz));
+  const unsigned blocks = (unsigned)((nnz + 255) / 256);
+  pair_flag_kernel<<<blocks, 256, 0, st>>>(nnz, blkOrder, rowOf, col, rowPtr, flag, tp);
+  thrust::exclusive_scan(thrust::cuda::par.on(st), flag, flag + nnz, pos);
+  int lastPos = 0, lastFlag = 0;
+  CUDA_TRY(cudaMemcpyAsync(&lastPos, pos + nnz - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(&lastFlag, flag + nnz - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  const int n = lastPos + lastFlag;
+  CUDA_TRY(cudaMalloc(pairList, sizeof(int) * (size_t)(n ? n : 1)));
+  CUDA_TRY(cudaMalloc(pairT, sizeof(int) * (size_t)(n ? n : 1)));
+  pair_fill_kernel<<<blocks, 256, 0, st>>>(nnz, blkOrder, flag, pos, tp, *pairList, *pairT);
+  count_launch(3);
+  CUDA_TRY(cudaStreamSynchronize(st));
+  cudaFree(flag); cudaFree(pos); cudaFree(tp);
+  *nPair = n;
+  return 0;
+}
+
 int build_gather_adjacency(cudaStream_t st, int nEl, int nNo, int nnz, const int *ien,
                            const int *edest, int **blkAdjPtr, int **blkAdj, int **nodeAdjPtr,
                            int **nodeAdj, int **blkOrder) {

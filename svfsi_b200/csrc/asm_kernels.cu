@@ -747,6 +747,89 @@ __global__ void __launch_bounds__(256) fluid_gather_r_kernel(int nNo, const int 
 }
 
 // ---------------------------------------------------------------------------
+// Kernels B + C, pair-owner version (default).  The tangent blocks (a,b) and (b,a) of one element
+// are built from the SAME operands with the roles of the two nodes exchanged (S/FLUID.f:482-557,
+// :1052-1081): Nx_a, Nx_b, C2, R2, the element-wide (sum tauC, wl), and only the (D,E) pair differs.
+// So 8 lanes own the PAIR of blocks {(r,c), (c,r)}, c > r: they walk the (element, a, b) list of (r,c)
+// once -- which is also the list of (c,r) with a and b swapped -- load 7 operands instead of 2 x 6,
+// evaluate both blocks and write each ONCE.  Diagonal blocks (r,r) are single; their list is the list
+// of elements around node r in ascending order, i.e. exactly what the residual gather walks, so
+// lanes 0..3 of a diagonal group also sum lR(:,a) and write R(:,r): kernel C disappears.
+// Every block still receives its contributions in ascending element order starting from 0.0
+// (deterministic; the accumulation order of the reference's element loop, S/LHSA.f:275-295).
+__device__ __forceinline__ void tangent_eval(double2 A, double2 B, double2 S, double ai, double bi,
+                                             double de, double sNa, double sNb, int i, int j0,
+                                             bool row3, bool col2, double mu4, double &v0, double &v1) {
+  const double wl = S.y, sTC = S.x;
+  // momentum rows, velocity columns (ai = Nx_i of a, bi = Nx_i of b)
+  const double m0 = (mu4 * (A.x * bi) + sTC * (ai * B.x) + ((i == j0) ? de : 0.0)) * wl;
+  const double m1 = (mu4 * (A.y * bi) + sTC * (ai * B.y) + ((i == 1) ? de : 0.0)) * wl;
+  const double mp = -wl * (ai * sNb - bi * A.y);               // pressure column (A.y = C2_a)
+  // continuity row (bi = R2_b)
+  const double c0 = wl * (sNa * B.x + A.x * bi);
+  const double c1 = wl * (sNa * B.y + A.y * bi);
+  const double cp = wl * de;                                   // de = sum tauM Nx_a.Nx_b
+  v0 = row3 ? c0 : m0;
+  v1 = row3 ? (col2 ? cp : c1) : (col2 ? mp : m1);
+}
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) fluid_gather_pairs_kernel(
+    int nPair, double mu4, const int *__restrict__ pairList, const int *__restrict__ pairT,
+    const int *__restrict__ rowOf, const int *__restrict__ adjPtr, const int *__restrict__ adj,
+    const double *__restrict__ elemP, double *__restrict__ Val, double *__restrict__ R) {
+  const int lane = threadIdx.x & 31, q = lane & 7;
+  const unsigned gmask = 0xFFu << (lane & 24);
+  const int g = (int)((blockIdx.x * (unsigned)THREADS + threadIdx.x) >> 3);
+  if (g >= nPair) return;   // whole 8-lane groups leave together
+  const int p = __ldg(pairList + g), pt = __ldg(pairT + g);
+  const bool diag = (pt == p), both = (pt >= 0) && !diag;
+  const int s = __ldg(adjPtr + p), e = __ldg(adjPtr + p + 1);
+  const int i = q >> 1, j0 = (q & 1) * 2;
+  const bool row3 = (i == 3), col2 = (j0 == 2);
+  // lane-constant offsets inside a node record: (Nx_j0, Nx_j0+1 | C2); Nx_i on a momentum row, R2
+  // on the continuity row (where Nx_i of the ROW node is not used)
+  const int oI = row3 ? N_R2 : i, oDE = row3 ? 1 : 0;
+  double acc0 = 0.0, acc1 = 0.0, t0 = 0.0, t1 = 0.0, r = 0.0;
+  for (int base = s; base < e; base += 8) {
+    const int mine = base + q;
+    const int cq = (mine < e) ? __ldg(adj + mine) : 0;
+    const int cnt = min(8, e - base);
+    for (int k = 0; k < cnt; k++) {
+      const int pk = __shfl_sync(gmask, cq, k, 8);
+      const int a = (pk >> 2) & 3, b = pk & 3;
+      const double *rec = elemP + (size_t)(pk >> 4) * F_COUNT;
+      const double *ra = rec + a * 8, *rb = rec + b * 8;
+      const double2 A = __ldg((const double2 *)(ra + j0));
+      const double2 S = __ldg((const double2 *)(ra + N_STC));
+      const double ai = __ldg(ra + oI);
+      const double de = __ldg(rec + F_DE + (a * 4 + b) * 2 + oDE);
+      const double sNa = sN_of(a), sNb = sN_of(b);
+      double v0, v1;
+      if (diag) {   // group-uniform: a == b
+        tangent_eval(A, A, S, ai, ai, de, sNa, sNa, i, j0, row3, col2, mu4, v0, v1);
+        if (q < 4) r += __ldg(rec + F_LR + a * 4 + q);
+      } else {
+        const double2 B = __ldg((const double2 *)(rb + j0));
+        const double bi = __ldg(rb + oI);
+        tangent_eval(A, B, S, ai, bi, de, sNa, sNb, i, j0, row3, col2, mu4, v0, v1);
+        if (both) {
+          const double de2 = __ldg(rec + F_DE + (b * 4 + a) * 2 + oDE);
+          double w0, w1;
+          tangent_eval(B, A, S, bi, ai, de2, sNb, sNa, i, j0, row3, col2, mu4, w0, w1);
+          t0 += w0;
+          t1 += w1;
+        }
+      }
+      acc0 += v0;
+      acc1 += v1;
+    }
+  }
+  __stcs((double2 *)(Val + (size_t)p * 16) + q, make_double2(acc0, acc1));
+  if (both) __stcs((double2 *)(Val + (size_t)pt * 16) + q, make_double2(t0, t1));
+  if (diag && q < 4) R[(size_t)__ldg(rowOf + p) * 4 + q] = r;
+}
+
+// ---------------------------------------------------------------------------
 // Kernels B + C, row-owner version: ONE WARP PER BLOCK ROW.  The warp walks the (element, a) pairs
 // around its node in ascending element order; at every visit lane group b = lane>>3 expands the
 // tangent block (a, b) (two entries per lane, q = lane&7) and adds it to the row's block
@@ -924,13 +1007,15 @@ void launch_fluid_asm(cudaStream_t st, const FluidPar &par, int n, int e0, const
 // bits 2..4: knobs of the templated tangent-gather kernel (1 = two contributions in flight,
 // 2 = 128-thread CTAs, 4 = 32-register cap).  bit 5 (32): row-owner kernel for B + C (one warp per block
 // row, accumulation in shared memory); bit 6 (64): two visits in flight in it.
-// Default = 40 (row-owner kernel; 8 = the block-owner kernel with 128-thread CTAs is what runs when a
-// row is longer than 64 blocks); SVFSI_ASM_TUNE overrides (kernel-variant timings in profiles/).
+// bit 7 (128): record kernel v3.  bits 10..13: pair-owner kernel for B + C (see the dispatch below).
+// Default = 136: record kernel v3 + block-owner gather with 128-thread CTAs, the fastest measured
+// combination (profiles/r01_asm_variants.md: the row-owner kernel measured SLOWER, 6.9 vs 6.15 + 0.32 ms);
+// SVFSI_ASM_TUNE overrides (kernel-variant timings in profiles/).
 int asm_tune() {
   static int t = -1;
   if (t < 0) {
     const char *e = getenv("SVFSI_ASM_TUNE");
-    t = e ? atoi(e) : 40;
+    t = e ? atoi(e) : 136;
   }
   return t;
 }
@@ -941,7 +1026,7 @@ void launch_fluid_gather_parts(cudaStream_t st, int parts, const FluidPar &par, 
                                const int *blkOrder, const int *blkAdjPtr, const int *blkAdj,
                                const int *nodeAdjPtr, const int *nodeAdj, double *R, double *Val,
                                int *badJac, int tune, const int *rowPtr, const int *nodeSlots,
-                               int maxRow) {
+                               int maxRow, PairLists pairs) {
   if (nEl <= 0) return;
   fluid_attr_once();
   // bit 5: row-owner kernel (B and C in one launch); needs the row's blocks in shared memory
@@ -961,6 +1046,25 @@ void launch_fluid_gather_parts(cudaStream_t st, int parts, const FluidPar &par, 
       fluid_record_kernel<<<(nEl + NE - 1) / NE, NE, smem, st>>>(par, nEl, ien, x, Ag, Yg, Bf,
                                                                  elemP, badJac);
     }
+  }
+  // bit 10 (1024): pair-owner kernel (B and C in one launch); bit 11 (2048): 256-thread CTAs
+  if ((tune & 1024) && pairs.list && pairs.n > 0 && (parts & 6)) {
+    count_launch();
+    const size_t lanes = (size_t)pairs.n * 8;
+#define GP(T, MB)                                                                              \
+  fluid_gather_pairs_kernel<T, MB><<<(unsigned)((lanes + T - 1) / T), T, 0, st>>>(                 \
+      pairs.n, 4.0 * par.mu, pairs.list, pairs.tpos, pairs.rowOf, blkAdjPtr, blkAdj, elemP, Val, R)
+    // bit 11 (2048): 256-thread CTAs; bit 12 (4096) / bit 13 (8192): register cap for 1280 / 1024
+    // resident threads per SM (48 / 64 registers; uncapped: 77)
+    if (tune & 4096) {
+      if (tune & 2048) GP(256, 5); else GP(128, 10);
+    } else if (tune & 8192) {
+      if (tune & 2048) GP(256, 4); else GP(128, 8);
+    } else {
+      if (tune & 2048) GP(256, 1); else GP(128, 1);
+    }
+#undef GP
+    return;
   }
   if (rows && (parts & 6)) {
     // parts 2 and 4 are one kernel here (timed under either bit)
@@ -984,7 +1088,7 @@ void launch_fluid_gather_parts(cudaStream_t st, int parts, const FluidPar &par, 
 #define GV(U2, T, MB)                                                                          \
   fluid_gather_val_t_kernel<U2, T, MB><<<(unsigned)((lanes + T - 1) / T), T, 0, st>>>(           \
       nnz, 4.0 * par.mu, blkOrder, blkAdjPtr, blkAdj, elemP, Val)
-    const int knob = tune >> 2;   // bits 2..: 1 = U2, 2 = 128 threads, 4 = 32-register cap
+    const int knob = (tune >> 2) & 7;   // bits 2..4: 1 = U2, 2 = 128 threads, 4 = 32-register cap
     if (tune & 2)
       fluid_gather_val2_kernel<<<(unsigned)((nnz + GCH - 1) / GCH), 256, 0, st>>>(
           nnz, 4.0 * par.mu, blkOrder, blkAdjPtr, blkAdj, elemP, Val);
@@ -1011,10 +1115,10 @@ void launch_fluid_gather(cudaStream_t st, const FluidPar &par, int nEl, int nNo,
                          const double *Bf, double *elemP, const int *blkOrder,
                          const int *blkAdjPtr, const int *blkAdj, const int *nodeAdjPtr,
                          const int *nodeAdj, double *R, double *Val, int *badJac,
-                         const int *rowPtr, const int *nodeSlots, int maxRow) {
+                         const int *rowPtr, const int *nodeSlots, int maxRow, PairLists pairs) {
   launch_fluid_gather_parts(st, 7, par, nEl, nNo, nnz, ien, x, Ag, Yg, Bf, elemP, blkOrder,
                             blkAdjPtr, blkAdj, nodeAdjPtr, nodeAdj, R, Val, badJac, asm_tune(),
-                            rowPtr, nodeSlots, maxRow);
+                            rowPtr, nodeSlots, maxRow, pairs);
 }
 
 // ---------------------------------------------------------------------------

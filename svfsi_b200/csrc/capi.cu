@@ -94,6 +94,12 @@ void color_elements(int nEl, int nNo, const std::vector<int> &ien, std::vector<i
   for (int e = 0; e < nEl; e++) colorElems[pos[color[e]]++] = e;
 }
 
+static PairLists pair_lists(const Ctx &c) {
+  PairLists pl;
+  pl.list = c.d_pairList; pl.tpos = c.d_pairT; pl.rowOf = c.d_rowOf; pl.n = c.nPair;
+  return pl;
+}
+
 int run_fluid_asm(const FluidPar &par, int variant) {
   Ctx &c = ctx();
   if (!c.mesh) return fail(SVFSI_ERR_STATE, "gpu_mesh_create_ has not been called");
@@ -120,7 +126,8 @@ int run_fluid_asm(const FluidPar &par, int variant) {
       if (!c.d_elemP) CUDA_TRY(cudaMalloc(&c.d_elemP, sizeof(double) * 80 * (size_t)c.nEl));
       launch_fluid_gather(c.stream, par, c.nEl, c.nNo, c.nnz, c.d_ien, c.d_x, c.d_Ag, c.d_Yg, bf,
                           c.d_elemP, c.d_blkOrder, c.d_blkAdjPtr, c.d_blkAdj, c.d_nodeAdjPtr,
-                          c.d_nodeAdj, c.d_R, c.d_Val, c.d_flag, c.d_rowPtr, c.d_nodeSlots, c.maxRowLen);
+                          c.d_nodeAdj, c.d_R, c.d_Val, c.d_flag, c.d_rowPtr, c.d_nodeSlots, c.maxRowLen,
+                          pair_lists(c));
     } else {
       return fail(SVFSI_ERR_ARG, "unknown assembly variant");
     }
@@ -227,6 +234,7 @@ int32_t gpu_lhs_free_(void) {
   dev_free(&c.d_ien); dev_free(&c.d_edest); dev_free(&c.d_x); dev_free(&c.d_colorElems);
   dev_free(&c.d_blkAdjPtr); dev_free(&c.d_blkAdj); dev_free(&c.d_nodeAdjPtr);
   dev_free(&c.d_nodeAdj); dev_free(&c.d_blkOrder); dev_free(&c.d_elemP); dev_free(&c.d_nodeSlots);
+  dev_free(&c.d_pairList); dev_free(&c.d_pairT); c.nPair = 0;
   dev_free(&c.d_R); dev_free(&c.d_Val); dev_free(&c.d_Ag); dev_free(&c.d_Yg); dev_free(&c.d_Bf);
   gpu_pic_free_();
   faces_free_all();
@@ -481,6 +489,7 @@ int32_t gpu_mesh_create_(const int32_t *nEl_, const int32_t *eNoN, const int32_t
   if (int rc = dev_upload(&c.d_colorElems, colorElems)) return rc;
   dev_free(&c.d_blkAdjPtr); dev_free(&c.d_blkAdj); dev_free(&c.d_nodeAdjPtr);
   dev_free(&c.d_nodeAdj); dev_free(&c.d_blkOrder); dev_free(&c.d_elemP); dev_free(&c.d_nodeSlots);
+  dev_free(&c.d_pairList); dev_free(&c.d_pairT); c.nPair = 0;
   if (int rc = build_gather_adjacency(c.stream, nEl, c.nNo, c.nnz, c.d_ien, c.d_edest,
                                       &c.d_blkAdjPtr, &c.d_blkAdj, &c.d_nodeAdjPtr, &c.d_nodeAdj,
                                       &c.d_blkOrder))
@@ -491,6 +500,9 @@ int32_t gpu_mesh_create_(const int32_t *nEl_, const int32_t *eNoN, const int32_t
     launch_build_node_slots(c.stream, c.nNo, c.d_rowPtr, c.d_nodeAdjPtr, c.d_nodeAdj, c.d_edest,
                             c.d_nodeSlots);
   }
+  if (int rc = build_pair_lists(c.stream, c.nnz, c.d_blkOrder, c.d_rowOf, c.d_col, c.d_rowPtr,
+                                &c.d_pairList, &c.d_pairT, &c.nPair))
+    return rc;
   CUDA_TRY(cudaStreamSynchronize(c.stream));
   // every (a,b) of every element must exist in the pattern
   c.mesh = true;
@@ -707,7 +719,7 @@ int32_t gpu_time_kernel_(const int32_t *what, const int32_t *dof, const int32_t 
       launch_fluid_gather_parts(c.stream, *k, par, c.nEl, c.nNo, c.nnz, c.d_ien, c.d_x, c.d_Ag,
                                 c.d_Yg, nullptr, c.d_elemP, c.d_blkOrder, c.d_blkAdjPtr, c.d_blkAdj,
                                 c.d_nodeAdjPtr, c.d_nodeAdj, c.d_R, c.d_Val, c.d_flag, *variant,
-                                c.d_rowPtr, c.d_nodeSlots, c.maxRowLen);
+                                c.d_rowPtr, c.d_nodeSlots, c.maxRowLen, pair_lists(c));
     CUDA_TRY(cudaEventRecord(b, c.stream));
   } else {
     return fail(SVFSI_ERR_ARG, "gpu_time_kernel_: unknown kernel id");

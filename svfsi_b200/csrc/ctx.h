@@ -128,6 +128,9 @@ struct Ctx {
   int *d_nodeSlots = nullptr;   // [4*nEl] row-local slots of the visit's four blocks (8 bits each)
   double *d_elemP = nullptr;    // [nEl][64] per-element compact records (gather variant)
   int *d_blkOrder = nullptr;    // [nnz padded] block processing order (length-sorted chunks)
+  int *d_pairList = nullptr;    // [nPair] blocks (r,c), c >= r, in processing order (pair-owner gather)
+  int *d_pairT = nullptr;       // [nPair] position of the transposed block (c,r)
+  int nPair = 0;
 
   // ---- system ----
   int dof = 0;                // dof of the resident R/Val

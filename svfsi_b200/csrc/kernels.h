@@ -177,13 +177,23 @@ void launch_fluid_asm(cudaStream_t st, const FluidPar &par, int n, int e0, const
 void launch_heat_asm(cudaStream_t st, const HeatPar &par, int n, int e0, const int *elems,
                      const int *ien, const int *edest, const double *x, const double *Ag,
                      const double *Yg, double *R, double *Val, int atomic, int *badJac);
+// pair-owner gather (asm_kernels.cu fluid_gather_pairs_kernel): the blocks (r,c) with c >= r in the
+// length-sorted processing order, and for each the position of the transposed block (c,r)
+// (== itself on the diagonal, -1 if the pattern has no transposed entry)
+struct PairLists {
+  const int *list = nullptr, *tpos = nullptr, *rowOf = nullptr;
+  int n = 0;
+};
+int build_pair_lists(cudaStream_t st, int nnz, const int *blkOrder, const int *rowOf, const int *col,
+                     const int *rowPtr, int **pairList, int **pairT, int *nPair);
 // gather variant: element records + owner-computes accumulation (deterministic, no atomics)
 void launch_fluid_gather(cudaStream_t st, const FluidPar &par, int nEl, int nNo, int nnz,
                          const int *ien, const double *x, const double *Ag, const double *Yg,
                          const double *Bf, double *elemP, const int *blkOrder,
                          const int *blkAdjPtr, const int *blkAdj, const int *nodeAdjPtr,
                          const int *nodeAdj, double *R, double *Val, int *badJac,
-                         const int *rowPtr = nullptr, const int *nodeSlots = nullptr, int maxRow = 0);
+                         const int *rowPtr = nullptr, const int *nodeSlots = nullptr, int maxRow = 0,
+                         PairLists pairs = PairLists());
 // heatS gather variant; rec >= 20 doubles per element (the fluid record buffer is reused)
 void launch_heat_gather(cudaStream_t st, const HeatPar &par, int nEl, int nNo, int nnz,
                         const int *ien, const double *x, const double *Ag, const double *Yg,
@@ -197,7 +207,8 @@ void launch_fluid_gather_parts(cudaStream_t st, int parts, const FluidPar &par, 
                                const int *blkOrder, const int *blkAdjPtr, const int *blkAdj,
                                const int *nodeAdjPtr, const int *nodeAdj, double *R, double *Val,
                                int *badJac, int tune, const int *rowPtr = nullptr,
-                               const int *nodeSlots = nullptr, int maxRow = 0);
+                               const int *nodeSlots = nullptr, int maxRow = 0,
+                               PairLists pairs = PairLists());
 // row-owner gather: positions of the four blocks of every (node, element) visit inside the row
 void launch_build_node_slots(cudaStream_t st, int nNo, const int *rowPtr, const int *nodeAdjPtr,
                              const int *nodeAdj, const int *edest, int *slots);

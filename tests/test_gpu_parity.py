@@ -61,8 +61,10 @@ def test_deterministic_assembly_variants_are_bitwise_repeatable(prob, variant):
 
 # every kernel variant of the gather assembly behind SVFSI_ASM_TUNE (asm_kernels.cu asm_tune()):
 # records v1 / v2 / v3 x block-owner / row-owner gather (1, 2, 4 visits in flight; 4 or 8 warps)
+# x pair-owner gather (128 / 256-thread CTAs, uncapped / 48 / 64 registers)
 @pytest.mark.parametrize("tune", [0, 1, 8, 40, 104, 296, 552, 808, 128 + 8, 128 + 40, 128 + 104,
-                                  128 + 808])
+                                  128 + 808, 1024, 3072, 5120, 7168, 9216, 11264, 128 + 1024,
+                                  128 + 9216])
 def test_gather_kernel_variants(prob, tune):
     m, p = prob
     Rs, Vs = cm.oracle_assemble([p])

@@ -76,7 +76,7 @@ def test_gpu_assembly_and_solve_on_irregular_mesh(gpu_lib, name):
             errs = cm.block_class_errs(V, Vr)
             assert max(errs.values()) <= TOL_ASM, (name, variant, errs)
         # every gather-kernel variant (row-owner ones fall back to block-owner on the fan)
-        for tune in (0, 8, 40, 104, 808, 128 + 40):
+        for tune in (0, 8, 40, 104, 808, 128 + 40, 1024, 128 + 1024, 128 + 11264):
             api.time_kernel(5, 4, 7, 1, tune)
             assert cm.rel_err(api.get_R(4), Rr) <= TOL_ASM, (name, tune)
             assert max(cm.block_class_errs(api.get_Val(4), Vr).values()) <= TOL_ASM, (name, tune)
@@ -91,11 +91,11 @@ def test_gpu_assembly_and_solve_on_irregular_mesh(gpu_lib, name):
         api.CONSTRUCT_FLUID(Ag, Yg, None, cm.RHO, cm.MU, cm.F, cm.DT, cm.GA["af"], cm.GA["am"],
                             cm.GA["gam"], api.ASM_GATHER)
         ls = api.FSILS_LS_CREATE(api.LS_TYPE_GMRES, relTol=1e-6, absTol=1e-14, maxItr=10, dimKry=60)
-        api.solve_dev(ls, 4, incL=[], res=[])
+        api.solve_dev(ls, 4)
         X = api.get_R(4)
         ls_o = ora.ls_create(ora.LS_TYPE_GMRES, relTol=1e-6, absTol=1e-14, maxItr=10, dimKry=60)
         Xo = Rr.copy()
-        w.solve(ls_o, 4, [Xo], [Vr.copy()], incL=[], res=[])
+        w.solve(ls_o, 4, [Xo], [Vr.copy()])
         assert abs(ls.RI.itr - ls_o.RI.itr) <= 1
         assert np.linalg.norm(X - Xo) / np.linalg.norm(Xo) <= 1e-8
     finally:

@@ -21,5 +21,4 @@ timeout 400 ncu --set full --clock-control none --import-source on \
     -k regex:"fluid_record|fluid_gather" -c 4 -f -o $O/${TAG}_prof_asm \
     python bench.py --nz 104 --steps 1 --warmup 1 --no-cpu > $O/${TAG}_prof_asm.log 2>&1
 ncu -i $O/${TAG}_prof_asm.ncu-rep --page raw --csv > $O/${TAG}_prof_asm_raw.csv 2>/dev/null
-SVFSI_ASM_TUNE=8 timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu > $O/${TAG}_bench_tune8.json 2> $O/${TAG}_bench_tune8.err
 tail -3 $O/${TAG}_pytest.log; cat $O/${TAG}_best_tune.txt; cat $O/${TAG}_asm_variants.json; cut -c1-600 $O/${TAG}_bench.json

@@ -16,6 +16,10 @@ gat = {int(k[len("gather_val_tune"):-3]): v for k, v in j.items() if k.startswit
 REC_BITS = 1 | 128
 rec_ok = {r: v for r, v in rec.items() if any((t & REC_BITS) == r for t in ok)} or {0: rec.get(0, 0.0)}
 gat_ok = {g: v for g, v in gat.items() if any((t & ~REC_BITS) == g for t in ok)} or {8: gat.get(8, 0.0)}
+# the row-owner (32) and pair-owner (1024) kernels also do the residual gather; the block-owner
+# ones need kernel C on top
+c_ms = j.get("gather_r_tune0_ms", 0.0)
+gat_ok = {g: v + (0.0 if g & (32 | 1024) else c_ms) for g, v in gat_ok.items()}
 r = min(rec_ok, key=rec_ok.get)
 g = min(gat_ok, key=gat_ok.get)
 print(r | g)

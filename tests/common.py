@@ -97,18 +97,22 @@ def reference_reproducibility_floor(relTol, sD, mItr, res_out, ls_type=None, **k
     return fx, ff, di
 
 
-def rounding_floor(relTol, sD, mItr, res_out, ls_type=None, seeds=(1, 2, 3), **kw):
+def rounding_floor(relTol, sD, mItr, res_out, ls_type=None, seeds=(1, 2, 3), with_range=False, **kw):
     """Same idea as reference_reproducibility_floor but partition-independent: how far the
     reference algorithm (oracle, 1 rank) moves when the assembled R / Val are perturbed by one
     ulp of relative noise -- the size of the difference between any two correct FP64 evaluations
     of the element loop.  Returns (floor on ||dX||/||X||, floor on |d fNorm|/fNorm, max |d itr|)."""
     ls1, G1 = oracle_gmres_global(1, relTol, sD, mItr, res_out, ls_type=ls_type, **kw)
     fx = ff = 0.0; di = 0
+    lo = hi = ls1.RI.itr
     for sd in seeds:
         lsk, Gk = oracle_gmres_global(1, relTol, sD, mItr, res_out, ls_type=ls_type, perturb=sd, **kw)
         fx = max(fx, float(np.linalg.norm(Gk - G1) / np.linalg.norm(G1)))
         ff = max(ff, abs(lsk.RI.fNorm - ls1.RI.fNorm) / ls1.RI.fNorm)
         di = max(di, abs(lsk.RI.itr - ls1.RI.itr))
+        lo, hi = min(lo, lsk.RI.itr), max(hi, lsk.RI.itr)
+    if with_range:      # the spread of the reference algorithm's own iteration count under that noise
+        return fx, ff, di, (lo, hi)
     return fx, ff, di
 
 

@@ -153,13 +153,16 @@ def main():
                            dtype=torch.float64, device="cuda")
         dist.all_reduce(num)
         err = float(torch.sqrt(num[0] / num[1]))
-        fx = 0.0; di = 0
-        for sd in (1, 2):
+        # spread of the reference algorithm's own iteration count / step under one ulp of noise on the
+        # assembled system (BiCGStab is not monotone: 8 samples, not 2, or the spread is under-estimated)
+        fx = 0.0; lo = hi = ls_o.RI.itr
+        for sd in range(1, 9):
             lp, Gp = cm.oracle_gmres_global(world, relTol, 60, 300, 0.0, dims=dims, L=L, ls_type=lst_o,
                                             prec=prec_o, perturb=sd)
-            fx = max(fx, float(np.linalg.norm(Gp - G) / np.linalg.norm(G))); di = max(di, abs(lp.RI.itr - ls_o.RI.itr))
+            fx = max(fx, float(np.linalg.norm(Gp - G) / np.linalg.norm(G)))
+            lo, hi = min(lo, lp.RI.itr), max(hi, lp.RI.itr)
         tag = f"{lst}/{prec} relTol={relTol}"
-        check(tag + " itr", abs(ls.RI.itr - ls_o.RI.itr) <= max(1, di), f"{ls.RI.itr} vs {ls_o.RI.itr} (floor {di})")
+        check(tag + " itr", lo - 1 <= ls.RI.itr <= hi + 1, f"{ls.RI.itr} vs {ls_o.RI.itr} (oracle spread {lo}..{hi})")
         check(tag + " iNorm", abs(ls.RI.iNorm - ls_o.RI.iNorm) <= 1e-10 * ls_o.RI.iNorm)
         if ls.RI.itr == ls_o.RI.itr:
             check(tag + " step", err <= max(1e-8, 4 * fx), f"err={err:.2e} floor={fx:.2e}")

@@ -61,7 +61,7 @@ def test_deterministic_assembly_variants_are_bitwise_repeatable(prob, variant):
 
 # every kernel variant of the gather assembly behind SVFSI_ASM_TUNE (asm_kernels.cu asm_tune()):
 # records v1 / v2 / v3 x block-owner / row-owner gather (1, 2, 4 visits in flight; 4 or 8 warps)
-# x pair-owner gather (128 / 256-thread CTAs, uncapped / 48 / 64 registers)
+# x pair-owner gather (128 / 256-thread CTAs, uncapped / 48 / 64 registers) x lean block-owner gather
 @pytest.mark.parametrize("tune", [0, 1, 8, 40, 104, 296, 552, 808, 128 + 8, 128 + 40, 128 + 104,
                                   128 + 808, 1024, 3072, 5120, 7168, 9216, 11264, 128 + 1024,
                                   128 + 9216])
@@ -214,9 +214,13 @@ def test_bicgs_and_rcs_newton_step(prob, lst, prec, relTol, mItr):
     ls = api.FSILS_LS_CREATE(lst_g, relTol=relTol, absTol=1e-14, maxItr=mItr, dimKry=60)
     api.solve_dev(ls, 4, prec=prec_g, incL=[1, 1, 1], res=[0.0, 0.0, 0.0])
     X = api.get_R(4)
-    fx, ff, di = cm.rounding_floor(relTol, 60, mItr, 0.0, ls_type=lst_o, prec=prec_o)
-    print(f"{lst}/{prec} relTol={relTol}: itr {ls.RI.itr}/{ls_o.RI.itr} floor(dx={fx:.1e}, df={ff:.1e}, di={di})")
-    assert abs(ls.RI.itr - ls_o.RI.itr) <= max(1, di), (ls.RI.itr, ls_o.RI.itr, di)
+    # 12 noise samples: BICGS + RCS at relTol 1e-4 takes 84..91 iterations under one ulp of noise
+    # (90 without), so three samples under-estimate the spread
+    fx, ff, di, (lo, hi) = cm.rounding_floor(relTol, 60, mItr, 0.0, ls_type=lst_o, prec=prec_o,
+                                             seeds=range(1, 13), with_range=True)
+    print(f"{lst}/{prec} relTol={relTol}: itr {ls.RI.itr}/{ls_o.RI.itr} floor(dx={fx:.1e}, df={ff:.1e}, "
+          f"itr range {lo}..{hi})")
+    assert lo - 1 <= ls.RI.itr <= hi + 1, (ls.RI.itr, ls_o.RI.itr, lo, hi)
     assert bool(ls.RI.suc) == bool(ls_o.RI.suc)
     assert abs(ls.RI.iNorm - ls_o.RI.iNorm) <= 1e-10 * ls_o.RI.iNorm
     if ls.RI.itr == ls_o.RI.itr:

@@ -1,4 +1,6 @@
 #!/usr/bin/env python
+# NOTE: the deterministic-repeatability part of the variant test (second run bitwise equal) holds for
+# every variant; variants differ from each other in the last bits (different FMA contraction).
 """Picks the fastest records-kernel and gather-kernel variants out of tools/time_asm_variants.py's
 JSON, restricted to the variants whose parity test passed (one tune per line in the ok file).
 Prints the combined SVFSI_ASM_TUNE value.  Usage: pick_asm_tune.py variants.json ok.txt"""

@@ -542,9 +542,34 @@ __global__ void __launch_bounds__(256) fluid_gather_val_kernel(int nnz, double m
   __stcs((double2 *)(Val + (size_t)p * 16) + q, make_double2(acc0, acc1));
 }
 
+// Record prefetch for kernel B.  The gather is latency bound (1560 SM cycles per warp step of four
+// contributions at 36 resident warps: ncu, profiles/r01_ncu_asm_summary.md): every step waits for its six
+// operand loads, 44% of which miss L2 (the records were just streamed to DRAM by kernel A).  A group
+// knows its next eight contributions as soon as it has read its slice of the list, so lane q
+// prefetches the three 64..128-byte pieces contribution q will read (node record a, node record b,
+// the (D,E) pair) before the group walks the eight contributions in order: eight records in
+// flight per group instead of one, no registers held.  PF: 1 = prefetch.global.L1 (CCTL.E.PF1),
+// 2 = prefetch.global.L2 (CCTL.E.PF2).  (Loads into registers that are never read do not survive ptxas.)
+template <int PF>
+__device__ __forceinline__ void prefetch_contribution(const double *__restrict__ elemP, int pk, bool valid) {
+  if (PF == 0 || !valid) return;
+  const double *rec = elemP + (size_t)(pk >> 4) * F_COUNT;
+  const double *ra = rec + ((pk >> 2) & 3) * 8, *rb = rec + (pk & 3) * 8;
+  const double *de = rec + F_DE + (pk & 15) * 2;
+  if (PF == 1) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(ra));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(rb));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(de));
+  } else {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(ra));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(rb));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(de));
+  }
+}
+
 // Kernel B with tuning knobs (measured in profiles/r01_asm_variants.md): U2 = two contributions in
 // flight per lane, THREADS per CTA, MINB = minimum resident CTAs (register cap)
-template <bool U2, int THREADS, int MINB>
+template <bool U2, int THREADS, int MINB, int PF = 0>
 __global__ void __launch_bounds__(THREADS, MINB) fluid_gather_val_t_kernel(
     int nnz, double mu4, const int *__restrict__ blkOrder, const int *__restrict__ adjPtr,
     const int *__restrict__ adj, const double *__restrict__ elemP, double *__restrict__ Val) {
@@ -558,6 +583,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fluid_gather_val_t_kernel(
   for (int base = s; base < e; base += 8) {
     const int mine = base + q;
     const int cq = (mine < e) ? __ldg(adj + mine) : 0;
+    prefetch_contribution<PF>(elemP, cq, mine < e);
     const int cnt = min(8, e - base);
     int k = 0;
     if (U2) {
@@ -756,7 +782,7 @@ __global__ void __launch_bounds__(256) fluid_gather_r_kernel(int nNo, const int 
 // address is one IMAD.WIDE from a 32-bit record index with the lane's field offset folded into the
 // base pointer.  ~40 instructions per warp step of four contributions instead of ~75 (SASS).
 // sum_g N_a(g) (sN_of: 1 to within an ulp) is taken as exactly 1 here: a 1e-16 relative change.
-template <int THREADS, int MINB>
+template <int THREADS, int MINB, int PF = 0>
 __global__ void __launch_bounds__(THREADS, MINB) fluid_gather_lean_kernel(
     int nnz, double mu4, const int *__restrict__ blkOrder, const int *__restrict__ adjPtr,
     const int *__restrict__ adj, const double *__restrict__ elemP, double *__restrict__ Val) {
@@ -782,6 +808,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fluid_gather_lean_kernel(
   for (int base = s; base < e; base += 8) {
     const int mine = base + q;
     const int cq = (mine < e) ? __ldg(adj + mine) : 0;
+    prefetch_contribution<PF>(elemP, cq, mine < e);
     const int cnt = min(8, e - base);
 #pragma unroll 1
     for (int k = 0; k < cnt; k++) {
@@ -1152,15 +1179,18 @@ void launch_fluid_gather_parts(cudaStream_t st, int parts, const FluidPar &par, 
   if ((parts & 2) && (tune & 16384) && (double)nEl * F_COUNT < 4.0e9) {
     count_launch();
     const size_t lanes = (size_t)nnz * 8;
-#define GL(T, MB)                                                                              \
-  fluid_gather_lean_kernel<T, MB><<<(unsigned)((lanes + T - 1) / T), T, 0, st>>>(                \
+#define GL(T, MB, PF)                                                                          \
+  fluid_gather_lean_kernel<T, MB, PF><<<(unsigned)((lanes + T - 1) / T), T, 0, st>>>(            \
       nnz, 4.0 * par.mu, blkOrder, blkAdjPtr, blkAdj, elemP, Val)
-    if (tune & 4096) {
-      if (tune & 2048) GL(256, 8); else GL(128, 16);
+    const int pf = (tune >> 15) & 3;   // bits 15, 16: record prefetch (1 = L1, 2 = L2)
+    if (pf == 1) { if (tune & 8192) GL(128, 10, 1); else GL(128, 1, 1); }
+    else if (pf == 2) { if (tune & 8192) GL(128, 10, 2); else GL(128, 1, 2); }
+    else if (tune & 4096) {
+      if (tune & 2048) GL(256, 8, 0); else GL(128, 16, 0);
     } else if (tune & 8192) {
-      if (tune & 2048) GL(256, 5); else GL(128, 10);
+      if (tune & 2048) GL(256, 5, 0); else GL(128, 10, 0);
     } else {
-      if (tune & 2048) GL(256, 1); else GL(128, 1);
+      if (tune & 2048) GL(256, 1, 0); else GL(128, 1, 0);
     }
 #undef GL
     parts &= ~2;
@@ -1172,7 +1202,13 @@ void launch_fluid_gather_parts(cudaStream_t st, int parts, const FluidPar &par, 
   fluid_gather_val_t_kernel<U2, T, MB><<<(unsigned)((lanes + T - 1) / T), T, 0, st>>>(           \
       nnz, 4.0 * par.mu, blkOrder, blkAdjPtr, blkAdj, elemP, Val)
     const int knob = (tune >> 2) & 7;   // bits 2..4: 1 = U2, 2 = 128 threads, 4 = 32-register cap
-    if (tune & 2)
+    const int pf = (tune >> 15) & 3;    // bits 15, 16: record prefetch (1 = L1, 2 = L2)
+#define GVP(PF)                                                                                  \
+  fluid_gather_val_t_kernel<false, 128, 1, PF><<<(unsigned)((lanes + 127) / 128), 128, 0, st>>>(   \
+      nnz, 4.0 * par.mu, blkOrder, blkAdjPtr, blkAdj, elemP, Val)
+    if (pf == 1) GVP(1);
+    else if (pf == 2) GVP(2);
+    else if (tune & 2)
       fluid_gather_val2_kernel<<<(unsigned)((nnz + GCH - 1) / GCH), 256, 0, st>>>(
           nnz, 4.0 * par.mu, blkOrder, blkAdjPtr, blkAdj, elemP, Val);
     else if (knob == 1) GV(true, 256, 1);

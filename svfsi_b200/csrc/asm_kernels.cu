@@ -910,6 +910,70 @@ __global__ void __launch_bounds__(THREADS, MINB) fluid_gather_wide_kernel(
 }
 
 // ---------------------------------------------------------------------------
+// Kernel B, quad version: FOUR lanes per block, lane r owns row r of the 4x4 block (four entries).
+// ncu's per-instruction stall samples of the 8-lane kernel (profiles/r01_asm_variants.md) put 30% of the
+// wait on the three dependent loads that start a group (processing order -> list bounds -> list) and
+// 37% on the first use of each contribution's operands: a group is a chain of ~9 serialised memory
+// round trips, and only warps-per-SM x groups-per-warp of them run at once.  With four lanes per
+// block a warp carries EIGHT chains instead of four for about the same registers; the 256-bit loads
+// of the wide kernel give a lane the whole (Nx_0..2, C2) of both nodes, which is exactly what a row of
+// the block needs.  Per step: 4 loads and ~55 instructions for eight contributions (8-lane kernel:
+// 6 loads, ~75 instructions for four).  Contributions still arrive in ascending element order.
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) fluid_gather_quad_kernel(
+    int nnz, double mu4, const int *__restrict__ blkOrder, const int *__restrict__ adjPtr,
+    const int *__restrict__ adj, const double *__restrict__ elemP, double *__restrict__ Val) {
+  const int lane = threadIdx.x & 31, r = lane & 3;
+  const unsigned gmask = 0xFu << (lane & 28);
+  const int g = (int)((blockIdx.x * (unsigned)THREADS + threadIdx.x) >> 2);
+  if (g >= nnz) return;   // whole 4-lane groups leave together
+  const int p = blkOrder ? __ldg(blkOrder + g) : g;
+  const int s = __ldg(adjPtr + p), e = __ldg(adjPtr + p + 1);
+  const bool row3 = (r == 3), i0 = (r == 0), i1 = (r == 1), i2 = (r == 2);
+  const double P = row3 ? 1.0 : mu4;       // coefficient of Nx_a(j) * bi, j < 3
+  const double P3 = row3 ? 0.0 : 1.0;      // last column: C2_a * Nx_b(i) on a momentum row
+  const double c3 = row3 ? 0.0 : -1.0;     // last column: -Nx_a(i) (sum_g N_b = 1) on a momentum row
+  const unsigned oD = (unsigned)F_DE + (row3 ? 1u : 0u);
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int cq = (s + r < e) ? __ldg(adj + s + r) : 0;
+  for (int base = s; base < e; base += 4) {
+    // the next slice of the list is in flight while this one is processed
+    const int nxt = base + 4 + r;
+    const int cqn = (nxt < e) ? __ldg(adj + nxt) : 0;
+    const int cnt = min(4, e - base);
+#pragma unroll 1
+    for (int k = 0; k < cnt; k++) {
+      const unsigned pk = (unsigned)__shfl_sync(gmask, cq, k, 4);
+      const unsigned eb = (pk >> 4) * (unsigned)F_COUNT;       // record index (32 bit: nEl * 80 < 2^32)
+      const unsigned ia = eb + ((pk << 1) & 24u), ib = eb + ((pk << 3) & 24u);
+      const dbl4 La = ldg256(elemP + (size_t)ia);                          // Nx_0..2, C2 of a
+      const dbl4 Lb = ldg256(elemP + (size_t)ib);                          // Nx_0..2 of b
+      const dbl4 Ls = ldg256(elemP + (size_t)((row3 ? ib : ia) + 4u));     // sum tauC, wl, -, R2
+      const double de = __ldg(elemP + (size_t)(ia + ((pk << 1) & 6u) + oD));   // D_ab | E_ab
+      const double ai = i0 ? La.x : (i1 ? La.y : La.z);        // Nx_i of a (unused on the continuity row)
+      const double bi = row3 ? Ls.w : (i0 ? Lb.x : (i1 ? Lb.y : Lb.z));   // Nx_i of b | R2_b
+      const double u = row3 ? 1.0 : Ls.x * ai;
+      double s0 = fma(u, Lb.x, i0 ? de : 0.0);
+      double s1 = fma(u, Lb.y, i1 ? de : 0.0);
+      double s2 = fma(u, Lb.z, i2 ? de : 0.0);
+      double s3 = fma(ai, c3, row3 ? de : 0.0);
+      s0 = fma(P, La.x * bi, s0);
+      s1 = fma(P, La.y * bi, s1);
+      s2 = fma(P, La.z * bi, s2);
+      s3 = fma(P3, La.w * bi, s3);
+      a0 += Ls.y * s0;
+      a1 += Ls.y * s1;
+      a2 += Ls.y * s2;
+      a3 += Ls.y * s3;
+    }
+    cq = cqn;
+  }
+  double2 *out = (double2 *)(Val + (size_t)p * 16 + r * 4);
+  __stcs(out, make_double2(a0, a1));
+  __stcs(out + 1, make_double2(a2, a3));
+}
+
+// ---------------------------------------------------------------------------
 // Kernels B + C, pair-owner version (default).  The tangent blocks (a,b) and (b,a) of one element
 // are built from the SAME operands with the roles of the two nodes exchanged (S/FLUID.f:482-557,
 // :1052-1081): Nx_a, Nx_b, C2, R2, the element-wide (sum tauC, wl), and only the (D,E) pair differs.
@@ -1244,6 +1308,24 @@ void launch_fluid_gather_parts(cudaStream_t st, int parts, const FluidPar &par, 
     }
 #undef GR
     return;
+  }
+  // bit 18 (262144): quad kernel (four lanes per block); bit 11 (2048): 256-thread CTAs; bit 13 (8192) /
+  // bit 12 (4096): 48 / 64-register cap
+  if ((parts & 2) && (tune & 262144) && (double)nEl * F_COUNT < 4.0e9) {
+    count_launch();
+    const size_t lanes = (size_t)nnz * 4;
+#define GQ(T, MB)                                                                              \
+  fluid_gather_quad_kernel<T, MB><<<(unsigned)((lanes + T - 1) / T), T, 0, st>>>(                \
+      nnz, 4.0 * par.mu, blkOrder, blkAdjPtr, blkAdj, elemP, Val)
+    if (tune & 8192) {
+      if (tune & 2048) GQ(256, 5); else GQ(128, 10);
+    } else if (tune & 4096) {
+      if (tune & 2048) GQ(256, 4); else GQ(128, 8);
+    } else {
+      if (tune & 2048) GQ(256, 1); else GQ(128, 1);
+    }
+#undef GQ
+    parts &= ~2;
   }
   // bit 17 (131072): wide-load block-owner kernel; bit 11 (2048): 256-thread CTAs; bit 13 (8192) / bit 12
   // (4096): 48 / 64-register cap

@@ -919,16 +919,23 @@ __global__ void __launch_bounds__(THREADS, MINB) fluid_gather_wide_kernel(
 // of the wide kernel give a lane the whole (Nx_0..2, C2) of both nodes, which is exactly what a row of
 // the block needs.  Per step: 4 loads and ~55 instructions for eight contributions (8-lane kernel:
 // 6 loads, ~75 instructions for four).  Contributions still arrive in ascending element order.
-template <int THREADS, int MINB>
+template <int THREADS, int MINB, bool DESC = false>
 __global__ void __launch_bounds__(THREADS, MINB) fluid_gather_quad_kernel(
     int nnz, double mu4, const int *__restrict__ blkOrder, const int *__restrict__ adjPtr,
-    const int *__restrict__ adj, const double *__restrict__ elemP, double *__restrict__ Val) {
+    const int *__restrict__ adj, const double *__restrict__ elemP, double *__restrict__ Val,
+    const int4 *__restrict__ desc) {
   const int lane = threadIdx.x & 31, r = lane & 3;
   const unsigned gmask = 0xFu << (lane & 28);
   const int g = (int)((blockIdx.x * (unsigned)THREADS + threadIdx.x) >> 2);
   if (g >= nnz) return;   // whole 4-lane groups leave together
-  const int p = blkOrder ? __ldg(blkOrder + g) : g;
-  const int s = __ldg(adjPtr + p), e = __ldg(adjPtr + p + 1);
+  int p, s, e;
+  if (DESC) {   // one 16-byte load: (block, list begin, list end)
+    const int4 d = __ldg(desc + g);
+    p = d.x; s = d.y; e = d.z;
+  } else {
+    p = blkOrder ? __ldg(blkOrder + g) : g;
+    s = __ldg(adjPtr + p); e = __ldg(adjPtr + p + 1);
+  }
   const bool row3 = (r == 3), i0 = (r == 0), i1 = (r == 1), i2 = (r == 2);
   const double P = row3 ? 1.0 : mu4;       // coefficient of Nx_a(j) * bi, j < 3
   const double P3 = row3 ? 0.0 : 1.0;      // last column: C2_a * Nx_b(i) on a momentum row
@@ -1235,14 +1242,16 @@ void launch_fluid_asm(cudaStream_t st, const FluidPar &par, int n, int e0, const
 // 2 = 128-thread CTAs, 4 = 32-register cap).  bit 5 (32): row-owner kernel for B + C (one warp per block
 // row, accumulation in shared memory); bit 6 (64): two visits in flight in it.
 // bit 7 (128): record kernel v3.  bits 10..13: pair-owner kernel for B + C (see the dispatch below).
-// Default = 136: record kernel v3 + block-owner gather with 128-thread CTAs, the fastest measured
-// combination (profiles/r01_asm_variants.md: the row-owner kernel measured SLOWER, 6.9 vs 6.15 + 0.32 ms);
+// bits 14..19: lean / prefetching / wide-load / quad block-owner kernels (see the dispatch below).
+// Default = 266368 = 128 + 262144 + 4096: record kernel v3 + quad gather (four lanes per block, 64-register
+// cap), the fastest measured combination (profiles/r01_asm_variants.md: 2.59 + 4.28 + 0.33 ms; the 8-lane
+// kernel takes 6.15, the row-owner and pair-owner kernels 6.9 and 7.2);
 // SVFSI_ASM_TUNE overrides (kernel-variant timings in profiles/).
 int asm_tune() {
   static int t = -1;
   if (t < 0) {
     const char *e = getenv("SVFSI_ASM_TUNE");
-    t = e ? atoi(e) : 136;
+    t = e ? atoi(e) : 266368;
   }
   return t;
 }
@@ -1315,8 +1324,15 @@ void launch_fluid_gather_parts(cudaStream_t st, int parts, const FluidPar &par, 
     count_launch();
     const size_t lanes = (size_t)nnz * 4;
 #define GQ(T, MB)                                                                              \
-  fluid_gather_quad_kernel<T, MB><<<(unsigned)((lanes + T - 1) / T), T, 0, st>>>(                \
-      nnz, 4.0 * par.mu, blkOrder, blkAdjPtr, blkAdj, elemP, Val)
+  do {                                                                                         \
+    if ((tune & 524288) && pairs.desc)                                                         \
+      fluid_gather_quad_kernel<T, MB, true><<<(unsigned)((lanes + T - 1) / T), T, 0, st>>>(      \
+          nnz, 4.0 * par.mu, blkOrder, blkAdjPtr, blkAdj, elemP, Val, pairs.desc);             \
+    else                                                                                       \
+      fluid_gather_quad_kernel<T, MB, false><<<(unsigned)((lanes + T - 1) / T), T, 0, st>>>(     \
+          nnz, 4.0 * par.mu, blkOrder, blkAdjPtr, blkAdj, elemP, Val, nullptr);                \
+  } while (0)
+    // bit 19 (524288): block descriptors (one load instead of two dependent ones at group start)
     if (tune & 8192) {
       if (tune & 2048) GQ(256, 5); else GQ(128, 10);
     } else if (tune & 4096) {

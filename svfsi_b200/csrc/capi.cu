@@ -97,6 +97,7 @@ void color_elements(int nEl, int nNo, const std::vector<int> &ien, std::vector<i
 static PairLists pair_lists(const Ctx &c) {
   PairLists pl;
   pl.list = c.d_pairList; pl.tpos = c.d_pairT; pl.rowOf = c.d_rowOf; pl.n = c.nPair;
+  pl.desc = c.d_blkDesc;
   return pl;
 }
 
@@ -234,7 +235,7 @@ int32_t gpu_lhs_free_(void) {
   dev_free(&c.d_ien); dev_free(&c.d_edest); dev_free(&c.d_x); dev_free(&c.d_colorElems);
   dev_free(&c.d_blkAdjPtr); dev_free(&c.d_blkAdj); dev_free(&c.d_nodeAdjPtr);
   dev_free(&c.d_nodeAdj); dev_free(&c.d_blkOrder); dev_free(&c.d_elemP); dev_free(&c.d_nodeSlots);
-  dev_free(&c.d_pairList); dev_free(&c.d_pairT); c.nPair = 0;
+  dev_free(&c.d_pairList); dev_free(&c.d_pairT); c.nPair = 0; dev_free(&c.d_blkDesc);
   dev_free(&c.d_R); dev_free(&c.d_Val); dev_free(&c.d_Ag); dev_free(&c.d_Yg); dev_free(&c.d_Bf);
   gpu_pic_free_();
   faces_free_all();
@@ -489,7 +490,7 @@ int32_t gpu_mesh_create_(const int32_t *nEl_, const int32_t *eNoN, const int32_t
   if (int rc = dev_upload(&c.d_colorElems, colorElems)) return rc;
   dev_free(&c.d_blkAdjPtr); dev_free(&c.d_blkAdj); dev_free(&c.d_nodeAdjPtr);
   dev_free(&c.d_nodeAdj); dev_free(&c.d_blkOrder); dev_free(&c.d_elemP); dev_free(&c.d_nodeSlots);
-  dev_free(&c.d_pairList); dev_free(&c.d_pairT); c.nPair = 0;
+  dev_free(&c.d_pairList); dev_free(&c.d_pairT); c.nPair = 0; dev_free(&c.d_blkDesc);
   if (int rc = build_gather_adjacency(c.stream, nEl, c.nNo, c.nnz, c.d_ien, c.d_edest,
                                       &c.d_blkAdjPtr, &c.d_blkAdj, &c.d_nodeAdjPtr, &c.d_nodeAdj,
                                       &c.d_blkOrder))
@@ -503,6 +504,7 @@ int32_t gpu_mesh_create_(const int32_t *nEl_, const int32_t *eNoN, const int32_t
   if (int rc = build_pair_lists(c.stream, c.nnz, c.d_blkOrder, c.d_rowOf, c.d_col, c.d_rowPtr,
                                 &c.d_pairList, &c.d_pairT, &c.nPair))
     return rc;
+  if (int rc = build_block_desc(c.stream, c.nnz, c.d_blkOrder, c.d_blkAdjPtr, &c.d_blkDesc)) return rc;
   CUDA_TRY(cudaStreamSynchronize(c.stream));
   // every (a,b) of every element must exist in the pattern
   c.mesh = true;
@@ -690,11 +692,14 @@ int32_t gpu_time_kernel_(const int32_t *what, const int32_t *dof, const int32_t 
     if ((rc = ensure_ws(2 * stride * sizeof(double)))) return rc;
     double *U = c.d_ws, *KU = c.d_ws + stride;
     launch_vecop(c.stream, VOP_ZERO, U, nullptr, nullptr, 2 * stride, nullptr, 0.0, nullptr);
+    // variant: 0 = the 8-lanes-per-row SPARMULVV kernel, 1 = the 4-lanes-per-row one, < 0 = as configured
+    const int prevQuad = (*variant >= 0) ? set_spmv_quad(*variant) : -1;
     launch_spmv(c.stream, d == 1 ? 3 : 0, d, 0, c.nNo, c.d_rowPtr, c.d_col, c.d_Val, U, KU, nullptr);
     CUDA_TRY(cudaEventRecord(a, c.stream));
     for (int r = 0; r < *reps; r++)
       launch_spmv(c.stream, d == 1 ? 3 : 0, d, 0, c.nNo, c.d_rowPtr, c.d_col, c.d_Val, U, KU, nullptr);
     CUDA_TRY(cudaEventRecord(b, c.stream));
+    if (prevQuad >= 0) set_spmv_quad(prevQuad);
   } else if (*what == 3 || *what == 4) {
     const int kk = *k;
     if ((rc = ensure_ws((size_t)(kk + 1) * stride * sizeof(double)))) return rc;

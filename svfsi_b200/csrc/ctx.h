@@ -131,6 +131,7 @@ struct Ctx {
   int *d_pairList = nullptr;    // [nPair] blocks (r,c), c >= r, in processing order (pair-owner gather)
   int *d_pairT = nullptr;       // [nPair] position of the transposed block (c,r)
   int nPair = 0;
+  int4 *d_blkDesc = nullptr;    // [nnz] (block, list begin, list end, 0) in processing order
 
   // ---- system ----
   int dof = 0;                // dof of the resident R/Val

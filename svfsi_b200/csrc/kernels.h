@@ -183,7 +183,11 @@ void launch_heat_asm(cudaStream_t st, const HeatPar &par, int n, int e0, const i
 struct PairLists {
   const int *list = nullptr, *tpos = nullptr, *rowOf = nullptr;
   int n = 0;
+  // block descriptors in processing order for the quad gather kernel: (block, list begin, list end, 0)
+  // in ONE 16-byte load instead of the dependent pair blkOrder[g] -> adjPtr[p], adjPtr[p+1]
+  const int4 *desc = nullptr;
 };
+int build_block_desc(cudaStream_t st, int nnz, const int *blkOrder, const int *adjPtr, int4 **desc);
 int build_pair_lists(cudaStream_t st, int nnz, const int *blkOrder, const int *rowOf, const int *col,
                      const int *rowPtr, int **pairList, int **pairT, int *nPair);
 // gather variant: element records + owner-computes accumulation (deterministic, no atomics)
@@ -220,6 +224,8 @@ int build_gather_adjacency(cudaStream_t st, int nEl, int nNo, int nnz, const int
 // edest[e][a*4+b] = device block index of (row ien[e][a], col ien[e][b])
 void launch_build_edest(cudaStream_t st, int nEl, const int *ien, const int *rowPtr,
                         const int *col, int *edest);
+
+int set_spmv_quad(int on);   // SPARMULVV dof=4 kernel variant on the unfused path (la_kernels.cu)
 
 void count_launch(int n = 1);
 

@@ -96,6 +96,63 @@ __global__ void __launch_bounds__(256) spmv_vv4_kernel(int r0, int r1, int r2, i
 }
 
 // ---------------------------------------------------------------------------
+// SPARMULVV dof = 4, quad version: FOUR lanes per block row; lane r holds row r of every 4x4 block
+// (one 256-bit streaming load, LDG.E.EF.ENL2.256) and the whole U(:,col) (one 256-bit load, the
+// same address for the four lanes), so KU(r,row) = sum_j sum_m K(r,m,j) U(m,col_j) accumulates in
+// ONE register in exactly the j, m order of L/SPARMUL.f:104-111 -- no partial sums, no shuffle
+// reduction -- and a warp keeps eight rows (eight dependent chains rowPtr -> col -> U) in flight
+// instead of four.  The next four column ids are fetched while the current four are used.
+struct __align__(32) ldbl4 { double x, y, z, w; };
+__device__ __forceinline__ ldbl4 ld256_stream(const double *p) {
+  ldbl4 r;
+  asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ ldbl4 ld256_nc(const double *p) {
+  ldbl4 r;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  return r;
+}
+__global__ void __launch_bounds__(256) spmv_vv4_quad_kernel(int r0, int r1, int r2, int r3,
+                                                             const int *__restrict__ rowPtr,
+                                                             const int *__restrict__ col,
+                                                             const double *__restrict__ K,
+                                                             const double *__restrict__ U,
+                                                             double *__restrict__ KU,
+                                                             const int *done) {
+  DONE_GUARD(done);
+  const int lane = threadIdx.x & 31, r = lane & 3;
+  const unsigned gmask = 0xFu << (lane & 28);
+  int row = r0 + (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 2);
+  if (row >= r1) row += r2 - r1;
+  if (row >= r3) return;  // whole 4-lane groups leave together
+  const int s = __ldg(rowPtr + row), e = __ldg(rowPtr + row + 1);
+  double acc = 0.0;
+  int cq = (s + r < e) ? __ldg(col + s + r) : 0;
+  for (int base = s; base < e; base += 4) {
+    const int nxt = base + 4 + r;
+    const int cqn = (nxt < e) ? __ldg(col + nxt) : 0;
+    const int cnt = min(4, e - base);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (k < cnt) {   // group-uniform
+        const int c = __shfl_sync(gmask, cq, k, 4);
+        const ldbl4 kv = ld256_stream(K + (size_t)(base + k) * 16 + r * 4);
+        const ldbl4 uv = ld256_nc(U + (size_t)c * 4);
+        acc = fma(kv.x, uv.x, acc);
+        acc = fma(kv.y, uv.y, acc);
+        acc = fma(kv.z, uv.z, acc);
+        acc = fma(kv.w, uv.w, acc);
+      }
+    }
+    cq = cqn;
+  }
+  KU[(size_t)row * 4 + r] = acc;
+}
+
+// ---------------------------------------------------------------------------
 // SpMV + halo send in ONE kernel (peer-memory path, FSILS_SPARMUL* = product followed by
 // FSILS_COMMUV, L/SPARMUL.f:130).  The rows shared with other ranks -- the two slabs at the ends
 // of the reordered numbering -- are given to the FIRST CTAs of the grid; each of their results is
@@ -382,6 +439,23 @@ static void launch_generic(cudaStream_t st, int r0, int r1, int r2, int r3, cons
   spmv_generic_kernel<BR, BC><<<blocks, 256, 0, st>>>(r0, r1, r2, r3, rowPtr, col, K, U, KU, done);
 }
 
+// SVFSI_SPMV_QUAD=1|0 selects the four-lanes-per-row SPARMULVV kernel on the unfused path
+// (measured in profiles/r01_spmv_quad.md)
+static int g_spmv_quad = -1;
+static bool spmv_quad() {
+  if (g_spmv_quad < 0) {
+    const char *e = getenv("SVFSI_SPMV_QUAD");
+    g_spmv_quad = e ? (atoi(e) != 0) : 0;
+  }
+  return g_spmv_quad != 0;
+}
+// kernel-variant timings (gpu_time_kernel_): returns the previous setting
+int set_spmv_quad(int on) {
+  const int prev = spmv_quad() ? 1 : 0;
+  g_spmv_quad = on ? 1 : 0;
+  return prev;
+}
+
 void launch_spmv2(cudaStream_t st, int kind, int dof, int r0, int r1, int r2, int r3,
                   const int *rowPtr, const int *col, const double *K, const double *U, double *KU,
                   const int *done) {
@@ -391,6 +465,11 @@ void launch_spmv2(cudaStream_t st, int kind, int dof, int r0, int r1, int r2, in
   if (rows <= 0) return;
   count_launch();
   if (kind == 0 && dof == 4) {
+    if (spmv_quad()) {
+      const int blocks = (int)(((size_t)rows * 4 + 255) / 256);
+      spmv_vv4_quad_kernel<<<blocks, 256, 0, st>>>(r0, r1, r2, r3, rowPtr, col, K, U, KU, done);
+      return;
+    }
     const int blocks = (int)(((size_t)rows * 8 + 255) / 256);
     spmv_vv4_kernel<<<blocks, 256, 0, st>>>(r0, r1, r2, r3, rowPtr, col, (const double2 *)K,
                                             (const double2 *)U, KU, done);

@@ -62,9 +62,16 @@ def test_deterministic_assembly_variants_are_bitwise_repeatable(prob, variant):
 # every kernel variant of the gather assembly behind SVFSI_ASM_TUNE (asm_kernels.cu asm_tune()):
 # records v1 / v2 / v3 x block-owner / row-owner gather (1, 2, 4 visits in flight; 4 or 8 warps)
 # x pair-owner gather (128 / 256-thread CTAs, uncapped / 48 / 64 registers) x lean block-owner gather
-@pytest.mark.parametrize("tune", [0, 1, 8, 40, 104, 296, 552, 808, 128 + 8, 128 + 40, 128 + 104,
-                                  128 + 808, 1024, 3072, 5120, 7168, 9216, 11264, 128 + 1024,
-                                  128 + 9216])
+# x lean / prefetching / wide-load (256-bit) 8-lane kernels x quad kernel (4 lanes per block)
+ASM_TUNES = [0, 1, 8, 40, 104, 296, 552, 808, 128 + 8, 128 + 40, 128 + 104, 128 + 808,        # v1..v3, rows
+             1024, 3072, 5120, 7168, 9216, 11264, 128 + 1024, 128 + 9216,                      # pair-owner
+             16384, 18432, 24576, 20480, 128 + 16384, 32776, 65544, 49152, 81920, 57344,       # lean, prefetch
+             131072, 133120, 139264, 135168, 128 + 139264,                                     # wide-load
+             262144, 264192, 270336, 272384, 266240, 128 + 262144, 128 + 270336, 128 + 266240,  # quad
+             786432, 790528, 794624, 128 + 790528]                                              # quad + descriptors
+
+
+@pytest.mark.parametrize("tune", ASM_TUNES)
 def test_gather_kernel_variants(prob, tune):
     m, p = prob
     Rs, Vs = cm.oracle_assemble([p])

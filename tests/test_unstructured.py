@@ -76,7 +76,7 @@ def test_gpu_assembly_and_solve_on_irregular_mesh(gpu_lib, name):
             errs = cm.block_class_errs(V, Vr)
             assert max(errs.values()) <= TOL_ASM, (name, variant, errs)
         # every gather-kernel variant (row-owner ones fall back to block-owner on the fan)
-        for tune in (0, 8, 40, 104, 808, 128 + 40, 1024, 128 + 1024, 128 + 11264, 16384, 128 + 24576, 128 + 57344, 131072, 128 + 139264, 262144, 128 + 270336):
+        for tune in (0, 8, 40, 104, 808, 128 + 40, 1024, 128 + 1024, 128 + 11264, 16384, 128 + 24576, 128 + 57344, 131072, 128 + 139264, 262144, 128 + 270336, 128 + 790528):
             api.time_kernel(5, 4, 7, 1, tune)
             assert cm.rel_err(api.get_R(4), Rr) <= TOL_ASM, (name, tune)
             assert max(cm.block_class_errs(api.get_Val(4), Vr).values()) <= TOL_ASM, (name, tune)

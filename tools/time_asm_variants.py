@@ -22,14 +22,19 @@ out = dict(nEl=int(p.rm.nEl), nnz=int(p.colPtr.size))
 # gather (B + C in one launch), +2048 = 256-thread CTAs, +4096 / +8192 = 48 / 64-register cap;
 # +32768 / +65536 = record prefetch into L1 / L2 (block-owner kernels 8 and 16384);
 # 262144 = quad gather (4 lanes per block, 256-bit loads), +2048 = 256-thread CTAs, +8192 / +4096 = 48 / 64-register cap;
+#   +524288 = block descriptors (one load at group start);
 # 131072 = wide-load (256-bit) block-owner gather, +2048 = 256-thread CTAs, +8192 / +4096 = 48 / 64-register cap;
 # 16384 = lean block-owner gather, +2048 = 256-thread CTAs, +8192 / +4096 = 48 / 32-register cap;
 # records: 0 = v1, 128 = v3 (pair staging, rsqrt arithmetic)
-tunes_val = tuple(int(t) for t in os.environ.get("ASM_TUNES", "8,57344,262144,264192,270336,272384,266240").split(","))
+tunes_val = tuple(int(t) for t in os.environ.get("ASM_TUNES", "8,266240,270336,786432,790528,794624").split(","))
 tunes_rec = tuple(int(t) for t in os.environ.get("ASM_TUNES_REC", "0,128").split(","))
 for part, name, tunes in ((1, "record", tunes_rec), (2, "gather_val", tunes_val), (4, "gather_r", (0,))):
     for tune in tunes:
         api.time_kernel(5, 4, part, 2, tune)
         out[f"{name}_tune{tune}_ms"] = api.time_kernel(5, 4, part, 10, tune) / 10
+# SPARMULVV dof=4: 8 lanes per row (0) vs 4 lanes per row with 256-bit loads (1)
+for v in (0, 1):
+    api.time_kernel(0, 4, 0, 3, v)
+    out[f"spmv_vv4_variant{v}_ms"] = api.time_kernel(0, 4, 0, 20, v) / 20
 print(json.dumps(out))
 api.finalize()

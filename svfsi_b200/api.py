@@ -76,7 +76,7 @@ EXPORTS = [
     "gpu_get_val_", "gpu_set_val_", "gpu_commu_", "gpu_commu_dev_", "gpu_solve_",
     "gpu_solve_dev_", "gpu_ls_create_", "gpu_sparmul_", "gpu_dot_", "gpu_time_kernel_",
     "gpu_prof_enable_", "gpu_prof_reset_", "gpu_prof_get_", "gpu_launch_count_",
-    "gpu_get_stream_", "gpu_sync_", "gpu_comm_mode_",
+    "gpu_get_stream_", "gpu_sync_", "gpu_comm_mode_", "gpu_spmv_variant_",
     "gpu_pic_init_", "gpu_pic_free_", "gpu_picp_", "gpu_setbcdir_", "gpu_pici_", "gpu_picc_",
     "gpu_pic_advance_", "gpu_pic_get_",
     "gpu_face_create_", "gpu_face_free_", "gpu_bassem_neu_fluid_", "gpu_face_integ_v_",
@@ -522,6 +522,12 @@ def comm_mode():
     m = C.c_int32()
     _check(lib().gpu_comm_mode_(C.byref(m)))
     return m.value
+
+
+def spmv_variant():
+    v = C.c_int32()
+    _check(lib().gpu_spmv_variant_(C.byref(v)))
+    return v.value
 
 
 def launch_count():

@@ -1243,15 +1243,16 @@ void launch_fluid_asm(cudaStream_t st, const FluidPar &par, int n, int e0, const
 // row, accumulation in shared memory); bit 6 (64): two visits in flight in it.
 // bit 7 (128): record kernel v3.  bits 10..13: pair-owner kernel for B + C (see the dispatch below).
 // bits 14..19: lean / prefetching / wide-load / quad block-owner kernels (see the dispatch below).
-// Default = 266368 = 128 + 262144 + 4096: record kernel v3 + quad gather (four lanes per block, 64-register
-// cap), the fastest measured combination (profiles/r01_asm_variants.md: 2.59 + 4.28 + 0.33 ms; the 8-lane
-// kernel takes 6.15, the row-owner and pair-owner kernels 6.9 and 7.2);
+// Default = 790656 = 128 + 262144 + 4096 + 524288: record kernel v3 + quad gather (four lanes per block,
+// 64-register cap, block descriptors), the fastest measured combination (profiles/r01_asm_variants.md:
+// 2.59 + 3.99 + 0.33 ms at 10M tets; the 8-lane kernel takes 6.15, the row-owner and pair-owner kernels
+// 6.9 and 7.2);
 // SVFSI_ASM_TUNE overrides (kernel-variant timings in profiles/).
 int asm_tune() {
   static int t = -1;
   if (t < 0) {
     const char *e = getenv("SVFSI_ASM_TUNE");
-    t = e ? atoi(e) : 266368;
+    t = e ? atoi(e) : 790656;
   }
   return t;
 }

@@ -765,6 +765,12 @@ int32_t gpu_launch_count_(int64_t *n) {
   *n = ctx().launches;
   return 0;
 }
+int32_t gpu_spmv_variant_(int32_t *variant) {
+  const int prev = set_spmv_quad(1);   // read ...
+  set_spmv_quad(prev);                 // ... and put back
+  *variant = prev;
+  return 0;
+}
 int32_t gpu_comm_mode_(int32_t *mode) {
   Ctx &c = ctx();
   if (c.nranks == 1) *mode = 0;

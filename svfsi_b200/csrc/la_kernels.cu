@@ -439,13 +439,14 @@ static void launch_generic(cudaStream_t st, int r0, int r1, int r2, int r3, cons
   spmv_generic_kernel<BR, BC><<<blocks, 256, 0, st>>>(r0, r1, r2, r3, rowPtr, col, K, U, KU, done);
 }
 
-// SVFSI_SPMV_QUAD=1|0 selects the four-lanes-per-row SPARMULVV kernel on the unfused path
-// (measured in profiles/r01_spmv_quad.md)
+// SVFSI_SPMV_QUAD=1|0 selects the four-lanes-per-row SPARMULVV kernel on the unfused path (default 1;
+// measured in profiles/r01_spmv_quad.md).  The fused SpMV + halo-send kernel of the multi-GPU path
+// still uses 8 lanes per row.
 static int g_spmv_quad = -1;
 static bool spmv_quad() {
   if (g_spmv_quad < 0) {
     const char *e = getenv("SVFSI_SPMV_QUAD");
-    g_spmv_quad = e ? (atoi(e) != 0) : 0;
+    g_spmv_quad = e ? (atoi(e) != 0) : 1;   // default: quad (0.589 vs 0.648 ms at 10M tets)
   }
   return g_spmv_quad != 0;
 }

@@ -107,7 +107,9 @@ def main():
         dist.all_reduce(num)
         err = float(torch.sqrt(num[0] / num[1]))
         tag = f"GMRES relTol={relTol} sD={sD} res={res_out}"
-        check(tag + " itr", abs(ls.RI.itr - ls_o.RI.itr) <= 1, f"{ls.RI.itr} vs {ls_o.RI.itr} (1-rank {ls_1.RI.itr})")
+        # +-1 around the reference's own spread (k-rank vs 1-rank oracle: only the summation order differs)
+        lo, hi = min(ls_o.RI.itr, ls_1.RI.itr), max(ls_o.RI.itr, ls_1.RI.itr)
+        check(tag + " itr", lo - 1 <= ls.RI.itr <= hi + 1, f"{ls.RI.itr} vs {ls_o.RI.itr} (1-rank {ls_1.RI.itr})")
         check(tag + " iNorm", abs(ls.RI.iNorm - ls_o.RI.iNorm) <= 1e-10 * ls_o.RI.iNorm)
         if ls.RI.itr == ls_o.RI.itr:
             check(tag + " step", err <= max(1e-8, 2 * floor), f"err={err:.2e} ref-floor={floor:.2e}")

@@ -327,7 +327,11 @@ def test_device_resident_time_loop(prob, resist):
     tA_in, tY_in = ora.setbcdirl(-12.0, gx, nV, 3)
     tA_w, tY_w = np.zeros((gw.size, 3)), np.zeros((gw.size, 3))
     gout, fIEN, gE = cm.local_face(m, p.rm, "outlet")
-    lskw = dict(relTol=1e-6, absTol=1e-14, maxItr=10, dimKry=80)
+    # relTol 1e-5, not 1e-6: at 1e-6 this system sits on the stagnation plateau of the reference's
+    # classical Gram-Schmidt GMRES, and the ORACLE's own SpMV counts then move by up to 7 under 1e-14 of
+    # relative noise on R / Val (one of six solves flips between 79 and 86); at 1e-5 they do not move
+    # under 1e-12, so +-1 is a meaningful bar
+    lskw = dict(relTol=1e-5, absTol=1e-14, maxItr=10, dimKry=80)
     res = [0.0, 0.0, ga["gam"] * cm.DT * resist]
     bf = 0.2                                                       # backflow_stab default
     nsteps, nnewton = 2, 3

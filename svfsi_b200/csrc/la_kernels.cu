@@ -115,19 +115,11 @@ __device__ __forceinline__ ldbl4 ld256_nc(const double *p) {
                : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
   return r;
 }
-__global__ void __launch_bounds__(256) spmv_vv4_quad_kernel(int r0, int r1, int r2, int r3,
-                                                             const int *__restrict__ rowPtr,
-                                                             const int *__restrict__ col,
-                                                             const double *__restrict__ K,
-                                                             const double *__restrict__ U,
-                                                             double *__restrict__ KU,
-                                                             const int *done) {
-  DONE_GUARD(done);
-  const int lane = threadIdx.x & 31, r = lane & 3;
-  const unsigned gmask = 0xFu << (lane & 28);
-  int row = r0 + (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 2);
-  if (row >= r1) row += r2 - r1;
-  if (row >= r3) return;  // whole 4-lane groups leave together
+__device__ __forceinline__ double spmv_vv4_quad_row(int row, int r, unsigned gmask,
+                                                    const int *__restrict__ rowPtr,
+                                                    const int *__restrict__ col,
+                                                    const double *__restrict__ K,
+                                                    const double *__restrict__ U) {
   const int s = __ldg(rowPtr + row), e = __ldg(rowPtr + row + 1);
   double acc = 0.0;
   int cq = (s + r < e) ? __ldg(col + s + r) : 0;
@@ -149,7 +141,22 @@ __global__ void __launch_bounds__(256) spmv_vv4_quad_kernel(int r0, int r1, int 
     }
     cq = cqn;
   }
-  KU[(size_t)row * 4 + r] = acc;
+  return acc;
+}
+__global__ void __launch_bounds__(256) spmv_vv4_quad_kernel(int r0, int r1, int r2, int r3,
+                                                             const int *__restrict__ rowPtr,
+                                                             const int *__restrict__ col,
+                                                             const double *__restrict__ K,
+                                                             const double *__restrict__ U,
+                                                             double *__restrict__ KU,
+                                                             const int *done) {
+  DONE_GUARD(done);
+  const int lane = threadIdx.x & 31, r = lane & 3;
+  const unsigned gmask = 0xFu << (lane & 28);
+  int row = r0 + (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 2);
+  if (row >= r1) row += r2 - r1;
+  if (row >= r3) return;  // whole 4-lane groups leave together
+  KU[(size_t)row * 4 + r] = spmv_vv4_quad_row(row, r, gmask, rowPtr, col, K, U);
 }
 
 // ---------------------------------------------------------------------------
@@ -213,6 +220,27 @@ __global__ void __launch_bounds__(256) spmv_vv4_fused_kernel(SpmvFuse f,
       KU[(size_t)row * 4 + (q >> 1)] = acc;
       if (bidx >= 0) fuse_send(f, bidx, 4, q >> 1, acc);
     }
+  }
+  fuse_publish(f);
+}
+// the same with four lanes per block row (64 rows per CTA): every lane owns one component of its row
+// and sends it itself
+__global__ void __launch_bounds__(256) spmv_vv4_quad_fused_kernel(SpmvFuse f,
+                                                                   const int *__restrict__ rowPtr,
+                                                                   const int *__restrict__ col,
+                                                                   const double *__restrict__ K,
+                                                                   const double *__restrict__ U,
+                                                                   double *__restrict__ KU,
+                                                                   const int *done) {
+  const bool skip = (done != nullptr && *(volatile const int *)done != 0);
+  const int lane = threadIdx.x & 31, r = lane & 3;
+  const unsigned gmask = 0xFu << (lane & 28);
+  int row, bidx;
+  const bool have = fuse_map_row(f, 64, threadIdx.x >> 2, row, bidx);
+  if (have && !skip) {
+    const double acc = spmv_vv4_quad_row(row, r, gmask, rowPtr, col, K, U);
+    KU[(size_t)row * 4 + r] = acc;
+    if (bidx >= 0) fuse_send(f, bidx, 4, r, acc);
   }
   fuse_publish(f);
 }
@@ -450,6 +478,15 @@ static bool spmv_quad() {
   }
   return g_spmv_quad != 0;
 }
+// SVFSI_SPMV_FUSED_QUAD=1|0: the same choice for the fused SpMV + halo-send kernel of the multi-GPU path
+static bool spmv_fused_quad() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("SVFSI_SPMV_FUSED_QUAD");
+    v = e ? (atoi(e) != 0) : 0;
+  }
+  return v != 0;
+}
 // kernel-variant timings (gpu_time_kernel_): returns the previous setting
 int set_spmv_quad(int on) {
   const int prev = spmv_quad() ? 1 : 0;
@@ -512,11 +549,16 @@ void launch_spmv_fused(cudaStream_t st, int kind, int dof, SpmvFuse f, const int
     FLAT_DISPATCH(FLF);
 #undef FLF
   }
-  const int rpc = vv4 ? 32 : 64;
+  const bool quad = vv4 && spmv_fused_quad();
+  const int rpc = (vv4 && !quad) ? 32 : 64;
   f.bndCtas = (f.nBnd + rpc - 1) / rpc;
   const int inner = f.mynNo - f.shnNo;
   const int blocks = f.bndCtas + (inner + rpc - 1) / rpc;
   if (blocks <= 0) return;
+  if (quad) {
+    spmv_vv4_quad_fused_kernel<<<blocks, 256, 0, st>>>(f, rowPtr, col, K, U, KU, done);
+    return;
+  }
   if (vv4) {
     spmv_vv4_fused_kernel<<<blocks, 256, 0, st>>>(f, rowPtr, col, (const double2 *)K,
                                                   (const double2 *)U, KU, done);

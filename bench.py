@@ -376,6 +376,9 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the native arm has no CPU fallback")
     if world > 1:
+        # stdout carries ONE JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -467,7 +470,7 @@ def main():
     if os.path.exists(tp) and dof == 4 and SOLVER == "gmres":
         with open(tp) as fh:
             tj = json.load(fh)
-        kname = "spmv_vv4_quad_kernel" if api.spmv_variant() == 1 else "spmv_vv4_kernel"
+        kname = "spmv_vv4_quad_kernel" if api.spmv_variant() & 1 else "spmv_vv4_kernel"
         if tj.get("nnz") == int(nnz) and tj.get("nNo") == int(nNo) and tj.get("kernel") == kname:
             traffic = int(tj["dram_bytes_read"] + tj["dram_bytes_write"])
     asm_ms, asm_n = prof["asm"]
@@ -483,8 +486,9 @@ def main():
                             h2d_bytes_per_step=int(Ag_h.nbytes + Yg_h.nbytes),
                             d2h_bytes_per_step=int(R_h.nbytes), ms_per_step=ms_e2e / args.steps),
                    gpu_launches=int(launches), comm=api.COMM_MODES[comm],
-                   roofline=dict(bound="hbm", kernel=(("spmv_vv4_fused_kernel" if comm == 3 else
-                                                       ("spmv_vv4_quad_kernel" if api.spmv_variant() == 1 else "spmv_vv4_kernel")) +
+                   roofline=dict(bound="hbm", kernel=((("spmv_vv4_quad_fused_kernel" if api.spmv_variant() & 2 else
+                                                        "spmv_vv4_fused_kernel") if comm == 3 else
+                                                       ("spmv_vv4_quad_kernel" if api.spmv_variant() & 1 else "spmv_vv4_kernel")) +
                                          " (FSILS_SPARMULVV dof=4)" if dof == 4 and SOLVER == "gmres"
                                                     else "spmv kernels (flat-row, mixed shapes: average over the step's SpMVs)"),
                                  achieved=achieved, peak=peak, unit="GB/s",

@@ -239,8 +239,9 @@ int32_t gpu_launch_count_(int64_t *n);
  * 2 peer-memory kernels (CUDA IPC over NVLink), 3 peer-memory with the halo send fused into the
  * SpMV kernel (one launch per FSILS_SPARMUL*; replaces MPI_ISEND/IRECV of L/INCOMMU.f:91-96) */
 int32_t gpu_comm_mode_(int32_t *mode);
-/* which FSILS_SPARMULVV dof=4 kernel (L/SPARMUL.f:98-113) the unfused path runs: 0 = 8 lanes per block
- * row, 1 = 4 lanes per block row with 256-bit loads (default; SVFSI_SPMV_QUAD=0 selects the other) */
+/* which FSILS_SPARMULVV dof=4 kernel (L/SPARMUL.f:98-113) runs: bit 0 = the unfused path uses 4 lanes per
+ * block row with 256-bit loads (default; SVFSI_SPMV_QUAD=0 selects the 8-lane kernel), bit 1 = so does the
+ * fused SpMV + halo-send kernel of the multi-GPU path (SVFSI_SPMV_FUSED_QUAD) */
 int32_t gpu_spmv_variant_(int32_t *variant);
 /* cudaStream_t of the library (so a caller can record its own events on it) */
 int32_t gpu_get_stream_(void **stream);

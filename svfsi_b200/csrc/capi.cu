@@ -768,7 +768,7 @@ int32_t gpu_launch_count_(int64_t *n) {
 int32_t gpu_spmv_variant_(int32_t *variant) {
   const int prev = set_spmv_quad(1);   // read ...
   set_spmv_quad(prev);                 // ... and put back
-  *variant = prev;
+  *variant = prev | (spmv_fused_quad_enabled() ? 2 : 0);
   return 0;
 }
 int32_t gpu_comm_mode_(int32_t *mode) {

@@ -225,6 +225,7 @@ int build_gather_adjacency(cudaStream_t st, int nEl, int nNo, int nnz, const int
 void launch_build_edest(cudaStream_t st, int nEl, const int *ien, const int *rowPtr,
                         const int *col, int *edest);
 
+int spmv_fused_quad_enabled();   // the fused SpMV + halo-send kernel runs 4 lanes per row
 int set_spmv_quad(int on);   // SPARMULVV dof=4 kernel variant on the unfused path (la_kernels.cu)
 
 void count_launch(int n = 1);

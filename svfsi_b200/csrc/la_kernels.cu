@@ -487,6 +487,7 @@ static bool spmv_fused_quad() {
   }
   return v != 0;
 }
+int spmv_fused_quad_enabled() { return spmv_fused_quad() ? 1 : 0; }
 // kernel-variant timings (gpu_time_kernel_): returns the previous setting
 int set_spmv_quad(int on) {
   const int prev = spmv_quad() ? 1 : 0;

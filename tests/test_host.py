@@ -74,6 +74,75 @@ def test_lhs_plan_matches_oracle(nparts):
             assert iPa == iPb and np.array_equal(pa, pb)
 
 
+def _quadrant_problems(nx=4, ny=4, nz=8, L=3.0):
+    """an element partition whose cut nodes are shared by up to four ranks (the slab partitions of
+    the other tests never share a node between more than two): sign of the element centroid's x and
+    y picks the rank"""
+    m = mesh.make_cylinder(nx, ny, nz, L=L)
+    c = m.x[m.IEN.astype(np.int64) - 1].mean(axis=1)
+    part = ((c[:, 0] > 0).astype(np.int32) + 2 * (c[:, 1] > 0).astype(np.int32))
+    rms = mesh.split_mesh(m, part, 4)
+    Ag, Yg = mesh.poiseuille_state(m)
+    probs = []
+    for rm in rms:
+        rp, cp = mesh.csr_pattern(rm.nNo, rm.IEN)
+        probs.append(mesh.RankProblem(rm, rp, cp, mesh.scatter_nodal(rm, Ag), mesh.scatter_nodal(rm, Yg), {}))
+    return m, probs
+
+
+def test_lhs_plan_matches_oracle_when_nodes_are_shared_by_four_ranks():
+    m, probs = _quadrant_problems()
+    ltgs = [p.rm.ltg for p in probs]
+    mult = np.zeros(m.nNo + 1, dtype=int)
+    for l in ltgs:
+        mult[l] += 1
+    assert mult.max() == 4                      # the axis nodes
+    w = cm.oracle_world(probs, m.nNo, with_faces=False)
+    for r in range(4):
+        plan = api.lhs_plan(r, 4, m.nNo, ltgs)
+        oi = w.info(r)
+        assert (plan["mynNo"], plan["nReq"], plan["shnNo"]) == (oi["mynNo"], oi["nReq"], oi["shnNo"])
+        assert np.array_equal(plan["map"], w.map(r))
+        assert len(plan["cS"]) == len(w.cs(r)) == 3
+        for (iPa, pa), (iPb, pb) in zip(plan["cS"], w.cs(r)):
+            assert iPa == iPb and np.array_equal(pa, pb)
+    # every global node is owned by exactly one rank (owned = the first mynNo of the reordered numbering)
+    owned = np.zeros(m.nNo + 1, dtype=int)
+    for r in range(4):
+        plan = api.lhs_plan(r, 4, m.nNo, ltgs)
+        inv = np.argsort(plan["map"])
+        owned[ltgs[r][inv[: plan["mynNo"]]]] += 1
+    assert (owned[1:] == 1).all()
+
+
+def test_oracle_four_rank_solve_matches_one_rank_on_the_quadrant_partition():
+    """COMMUV with three neighbours per rank and nodes summed over four ranks: the 4-rank oracle's
+    assembled + halo-summed residual and its GMRES step equal the 1-rank oracle's."""
+    m, probs = _quadrant_problems()
+    Rs, Vs = cm.oracle_assemble(probs)
+    w = cm.oracle_world(probs, m.nNo, nFaces=0, with_faces=False)
+    Rc = cm.oracle_commu(w, probs, Rs)
+    m1, probs1, _ = mesh.build_problem(4, 4, 8, nparts=1, L=3.0)
+    R1, V1 = cm.oracle_assemble(probs1)
+    G = np.zeros((m.nNo, 4))
+    for p, r in zip(probs, Rc):
+        G[p.rm.ltg - 1] = r
+    assert cm.rel_err(G, R1[0][np.argsort(probs1[0].rm.ltg)]) <= 1e-13
+    ls4 = ora.ls_create(ora.LS_TYPE_GMRES, relTol=1e-4, absTol=1e-14, maxItr=10, dimKry=80)
+    X = [r.copy() for r in Rc]
+    w.solve(ls4, 4, X, [v.copy() for v in Vs])
+    w1 = cm.oracle_world(probs1, m.nNo, nFaces=0, with_faces=False)
+    ls1 = ora.ls_create(ora.LS_TYPE_GMRES, relTol=1e-4, absTol=1e-14, maxItr=10, dimKry=80)
+    X1 = [R1[0].copy()]
+    w1.solve(ls1, 4, X1, [V1[0].copy()])
+    G4 = np.zeros((m.nNo, 4))
+    for p, x in zip(probs, X):
+        G4[p.rm.ltg - 1] = x
+    G1 = np.zeros((m.nNo, 4)); G1[probs1[0].rm.ltg - 1] = X1[0]
+    assert abs(ls4.RI.itr - ls1.RI.itr) <= 1
+    assert np.linalg.norm(G4 - G1) / np.linalg.norm(G1) <= 1e-8
+
+
 def test_csr_pattern_matches_lhsa():
     m = mesh.make_cylinder(4, 4, 5)
     rp, cp = mesh.csr_pattern(m.nNo, m.IEN)

@@ -45,3 +45,39 @@ def test_parse_svfsi_iteration_table():
     s = psl.summarise(rows, cores=8)
     assert s["iterations"] == 3 and abs(s["seconds"] - 27.0) < 1e-9
     assert abs(s["value"] - 3 / 27.0) < 1e-12 and s["cores"] == 8
+
+
+def test_pick_asm_tune_prefers_the_fastest_tested_combination(tmp_path):
+    """tools/pick_asm_tune.py: fastest records kernel | fastest gather kernel among the variants whose
+    parity test passed; the 8-lane kernels pay for the separate residual gather"""
+    import json
+    v = tmp_path / "v.json"; ok = tmp_path / "ok.txt"
+    v.write_text(json.dumps({"nEl": 1, "nnz": 1, "record_tune0_ms": 3.2, "record_tune128_ms": 2.6,
+                             "gather_val_tune8_ms": 6.1, "gather_val_tune40_ms": 6.3,
+                             "gather_val_tune790528_ms": 4.0, "gather_r_tune0_ms": 0.33}))
+    tool = os.path.join(ROOT, "tools", "pick_asm_tune.py")
+
+    def pick():
+        return int(subprocess.check_output([sys.executable, tool, str(v), str(ok)], text=True))
+    ok.write_text("0\n8\n40\n136\n168\n790528\n790656\n")
+    assert pick() == 128 + 790528
+    ok.write_text("0\n8\n40\n136\n168\n")            # quad variant failed its test: not eligible
+    assert pick() == 128 + 40                         # 6.3 (B + C in one launch) beats 6.1 + 0.33
+    ok.write_text("")
+    assert pick() == 8                                # nothing verified: the plain 8-lane kernel
+
+
+def test_launch_list_summary(tmp_path):
+    csvf = tmp_path / "l.csv"
+    csvf.write_text('==PROF== Connected\n"ID","Process ID","Process Name","Host Name","Kernel Name","Context","Stream",'
+                    '"Block Size","Grid Size","Device","CC","Section Name","Metric Name","Metric Unit","Metric Value"\n'
+                    '"0","1","p","h","svfsi::a_kernel(int)","1","13","(256, 1, 1)","(1, 1, 1)","0","10.0","s",'
+                    '"gpu__time_duration.sum","ns","1500"\n'
+                    '"1","1","p","h","svfsi::a_kernel(int)","1","13","(256, 1, 1)","(1, 1, 1)","0","10.0","s",'
+                    '"gpu__time_duration.sum","us","2.5"\n'
+                    '"2","1","p","h","svfsi::b_kernel(int)","1","13","(256, 1, 1)","(1, 1, 1)","0","10.0","s",'
+                    '"gpu__time_duration.sum","ns","1000"\n')
+    out = subprocess.check_output([sys.executable, os.path.join(ROOT, "tools", "summarize_launches.py"), str(csvf)],
+                                  text=True)
+    assert "| `svfsi::a_kernel` | 2 | 4.0 | 2.0 | 80.0% |" in out
+    assert "| `svfsi::b_kernel` | 1 | 1.0 | 1.0 | 20.0% |" in out

@@ -417,3 +417,51 @@ def integ_v(x, IEN, fIEN, gE, S):
     for v in acc:
         tot = tot + v
     return tot
+
+
+# ------------------------------------------------------------------------------------------
+# RCR (Windkessel) 0-D coupling, host side of the reference: RCR_Integ_X and CALCDERCPLBC
+def rcr_integ_x(xo, Qo, Qn, Rp, C, Rd, Pd, dt, time, nTS=100):
+    """RCR_Integ_X, S/SETBC.f:1292-1372, one face at a time in scalar arithmetic (loop order of the
+    Fortran): returns (xn[nFa], y[nFa])"""
+    nX = len(xo)
+    X = [float(v) for v in xo]
+    tt = max(time - dt, 0.0)
+    dtt = dt / float(nTS)
+    Qrk = [[0.0] * 4 for _ in range(nX)]
+    for n in range(1, nTS + 1):
+        for i in range(1, 5):
+            r = float(i - 1) / 3.0
+            r = (float(n - 1) + r) / float(nTS)
+            for k in range(nX):
+                Qrk[k][i - 1] = Qo[k] + (Qn[k] - Qo[k]) * r
+        for k in range(nX):
+            f1 = (Qrk[k][0] - (X[k] - Pd[k]) / Rd[k]) / C[k]
+            Xrk = X[k] + dtt * f1 / 3.0
+            f2 = (Qrk[k][1] - (Xrk - Pd[k]) / Rd[k]) / C[k]
+            Xrk = X[k] - dtt * f1 / 3.0 + dtt * f2
+            f3 = (Qrk[k][2] - (Xrk - Pd[k]) / Rd[k]) / C[k]
+            Xrk = X[k] + dtt * f1 - dtt * f2 + dtt * f3
+            f4 = (Qrk[k][3] - (Xrk - Pd[k]) / Rd[k]) / C[k]
+            X[k] = X[k] + (dtt / 8.0) * (f1 + 3.0 * (f2 + f3) + f4)
+        tt = tt + dtt
+    return np.array(X), np.array([X[k] + Qn[k] * Rp[k] for k in range(nX)])
+
+
+def calc_der_cplbc(xo, Qo, Qn, Rp, C, Rd, Pd, dt, time):
+    """CALCDERCPLBC, S/SETBC.f:1037-1123 (all faces of the Neumann group): returns (y, r) with
+    r_i = (y_i(Qn_i + diff) - y_i(Qn)) / diff, diff = max(absTol, relTol * rms(Qo))"""
+    nX = len(xo)
+    _, y0 = rcr_integ_x(xo, Qo, Qn, Rp, C, Rd, Pd, dt, time)
+    diff = 0.0
+    for k in range(nX):
+        diff = diff + Qo[k] * Qo[k]
+    diff = np.sqrt(diff / float(nX))
+    diff = 1e-8 if diff * 1e-5 < 1e-8 else diff * 1e-5
+    r = np.zeros(nX)
+    for k in range(nX):
+        Q = [float(v) for v in Qn]
+        Q[k] = Qn[k] + diff
+        _, y = rcr_integ_x(xo, Qo, Q, Rp, C, Rd, Pd, dt, time)
+        r[k] = (y[k] - y0[k]) / diff
+    return y0, r

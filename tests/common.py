@@ -126,3 +126,55 @@ def local_face(m, rm, name):
     fIEN = gtl[fa.tri[sel].astype(np.int64)].astype(np.int32)
     gE = (np.searchsorted(rm.elems, fa.parent[sel]) + 1).astype(np.int32)
     return rm.faces[name]["gN"], fIEN, gE
+
+
+def oracle_rcr_time_loop(m, p, faces_rcr, nsteps=2, nnewton=3, relTol=1e-5, sD=80, umax_in=-12.0, scheme="SI"):
+    """The shape of BASELINE configs[0] (04-fluid/01-pipe3D_RCR) on one rank with the ORACLE: steady
+    parabolic Dirichlet inlet, no-slip wall, RCR outlet.  Per Newton iteration (S/MAIN.f:111-206):
+    SETBCCPL (fluxes of Yo / Yn through the outlet -> RCR_Integ_X -> g) -> PICI -> element loop ->
+    Neumann face with h = g (S/SETBC.f:267-270, BASSEMNEUBC) -> FSILS_SOLVE with res = gam*dt*r -> PICC;
+    per time step cplBC%xo = cplBC%xn.  Returns per-iteration (iNorm, itr, g, Qn) and the final (An, Yn)."""
+    from svfsi_b200 import cplbc
+    ga = GA
+    nNo = p.rm.nNo
+    rng = np.random.default_rng(21)
+    Ao = 0.05 * rng.standard_normal((nNo, 4)); Ao[:, 3] = 0.0
+    Yo = p.Yg.copy()
+    gin = p.faces["inlet"]["gN"]; gw = p.faces["wall"]["gN"]
+    xin = p.rm.x[gin - 1]
+    r2 = (xin[:, 0] ** 2 + xin[:, 1] ** 2) / (np.abs(p.rm.x[:, :2]).max() ** 2)
+    gx = np.clip(1.0 - r2, 0.0, None)
+    nV = np.tile(np.array([0.0, 0.0, -1.0]), (gin.size, 1))
+    tA_in, tY_in = ora.setbcdirl(umax_in, gx, nV, 3)
+    tA_w, tY_w = np.zeros((gw.size, 3)), np.zeros((gw.size, 3))
+    gout, fIEN, gE = local_face(m, p.rm, "outlet")
+    w = oracle_world([p], m.nNo)
+    par = fluid_par()
+    cpl = cplbc.CplBC(faces_rcr, DT, scheme)
+    state = dict(Yo=Yo, Yn=Yo)
+
+    def integ(i, which):
+        return ora.integ_v(p.rm.x, p.rm.IEN, fIEN, gE, state["Y" + which][:, :3])
+    cpl.init(integ)
+    out = []
+    time = 0.0
+    for ts in range(nsteps):
+        time += DT
+        An, Yn = ora.picp(Ao, Yo, ga["gam"])
+        ora.setbcdir(An, Yn, gin, 1, tA_in, tY_in)
+        ora.setbcdir(An, Yn, gw, 1, tA_w, tY_w)
+        for it in range(nnewton):
+            state["Yo"], state["Yn"] = Yo, Yn
+            g = cpl.setbccpl(integ, time)[0]
+            Ag, Yg = ora.pici(Ao, An, Yo, Yn, ga["am"], ga["af"])
+            R, V = ora.construct_fluid(par, p.rm.IEN, p.rm.x, Ag, Yg, np.zeros((nNo, 3)), p.rowPtr, p.colPtr)
+            hg = np.zeros(nNo); hg[gout - 1] = -g * 1.0
+            ora.bassem_neu_fluid(p.rm.x, p.rm.IEN, fIEN, gE, hg, Yg, p.rowPtr, p.colPtr, R, V, RHO, 0.2,
+                                 ga["af"], ga["gam"], DT)
+            ls = ora.ls_create(ora.LS_TYPE_GMRES, relTol=relTol, absTol=1e-14, maxItr=10, dimKry=sD)
+            w.solve(ls, 4, [R], [V], incL=[1, 1, 1], res=[0.0, 0.0, ga["gam"] * DT * cpl.r[0]])
+            out.append((ls.RI.iNorm, ls.RI.itr, g, cpl.Qn[0]))
+            ora.picc(An, Yn, R, ga["gam"], ga["beta"], DT)
+        Ao, Yo = An, Yn
+        cpl.advance()
+    return out, (Ao, Yo), cpl

@@ -43,7 +43,9 @@ extern "C" {
 #define SVFSI_ERR_CUDA 1      /* CUDA runtime / no device: the product path has no CPU fallback */
 #define SVFSI_ERR_STATE 2     /* call order (e.g. solve before lhs_create) */
 #define SVFSI_ERR_ARG 3       /* bad argument (faIn out of range, unknown LS_type, ...) */
-#define SVFSI_ERR_JAC 4       /* ISZERO(Jac) at some element, S/FLUID.f:115 */
+#define SVFSI_ERR_JAC 4       /* ISZERO(Jac) at some element, S/FLUID.f:115; from the host-buffer
+                               * gpu_construct_*_ at once, from the device-resident gpu_construct_*_dev_
+                               * at the next call that synchronises (gpu_solve_dev_, gpu_sync_) */
 #define SVFSI_ERR_COMM 5      /* NCCL / host collective */
 #define SVFSI_ERR_UNSUPPORTED 6
 
@@ -243,6 +245,11 @@ int32_t gpu_comm_mode_(int32_t *mode);
  * block row with 256-bit loads (default; SVFSI_SPMV_QUAD=0 selects the 8-lane kernel), bit 1 = so does the
  * fused SpMV + halo-send kernel of the multi-GPU path (SVFSI_SPMV_FUSED_QUAD) */
 int32_t gpu_spmv_variant_(int32_t *variant);
+/* Every in-kernel wait on a peer's flag (the MPI_WAIT of L/INCOMMU.f:98-100 and the MPI_ALLREDUCE of
+ * L/DOT.f / L/NORM.f on the peer-memory path) is bounded: after `seconds` (default 120, or
+ * SVFSI_COMM_TIMEOUT_S) the kernels give up, the stream drains, and every later call that synchronises
+ * returns SVFSI_ERR_COMM until gpu_finalize_ -- a dead or late rank cannot hang the GPUs of the box. */
+int32_t gpu_set_comm_timeout_(const double *seconds);
 /* cudaStream_t of the library (so a caller can record its own events on it) */
 int32_t gpu_get_stream_(void **stream);
 int32_t gpu_sync_(void);

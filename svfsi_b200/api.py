@@ -80,7 +80,7 @@ EXPORTS = [
     "gpu_pic_init_", "gpu_pic_free_", "gpu_picp_", "gpu_setbcdir_", "gpu_pici_", "gpu_picc_",
     "gpu_pic_advance_", "gpu_pic_get_",
     "gpu_face_create_", "gpu_face_free_", "gpu_bassem_neu_fluid_", "gpu_face_integ_v_",
-    "gpu_prof_spmv_",
+    "gpu_prof_spmv_", "gpu_set_comm_timeout_",
 ]
 
 
@@ -528,6 +528,11 @@ def spmv_variant():
     v = C.c_int32()
     _check(lib().gpu_spmv_variant_(C.byref(v)))
     return v.value
+
+
+def set_comm_timeout(seconds):
+    """bound of every in-kernel wait on a peer's flag; afterwards calls return ERR_COMM"""
+    _check(lib().gpu_set_comm_timeout_(_cd(seconds)))
 
 
 def launch_count():

@@ -1639,7 +1639,7 @@ void launch_heat_asm(cudaStream_t st, const HeatPar &par, int n, int e0, const i
 // short (<= ~30), so a linear scan is used.
 __global__ void build_edest_kernel(int nEl, const int *__restrict__ ien,
                                    const int *__restrict__ rowPtr, const int *__restrict__ col,
-                                   int *__restrict__ edest) {
+                                   int *__restrict__ edest, int *__restrict__ missing) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t)nEl * 16) return;
   const int e = (int)(t >> 4), a = (int)((t >> 2) & 3), b = (int)(t & 3);
@@ -1647,14 +1647,16 @@ __global__ void build_edest_kernel(int nEl, const int *__restrict__ ien,
   int p = -1;
   for (int j = rowPtr[row]; j < rowPtr[row + 1]; j++)
     if (col[j] == c) { p = j; break; }
+  if (p < 0) atomicAdd(missing, 1);
   edest[t] = p;
 }
 void launch_build_edest(cudaStream_t st, int nEl, const int *ien, const int *rowPtr,
-                        const int *col, int *edest) {
+                        const int *col, int *edest, int *missing) {
   if (nEl <= 0) return;
   count_launch();
   size_t tot = (size_t)nEl * 16;
-  build_edest_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(nEl, ien, rowPtr, col, edest);
+  build_edest_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(nEl, ien, rowPtr, col, edest,
+                                                                    missing);
 }
 
 }  // namespace svfsi

@@ -14,6 +14,7 @@ using namespace svfsi;
 
 namespace svfsi {
 void faces_free_all();   // face.cu
+void solver_free_static();   // solver.cu
 int solver_bcpre(int nsd, double *sS);
 }
 
@@ -44,12 +45,10 @@ int need_init() {
 int ensure_system(int dof) {
   Ctx &c = ctx();
   if (!c.lhs) return fail(SVFSI_ERR_STATE, "FSILS_LHS_CREATE has not been called");
+  // R and Val are sized for the largest block this library handles (nsd + 1 = 4)
+  if (dof < 1 || dof > 4) return fail(SVFSI_ERR_ARG, "dof must be 1..4");
   if (!c.d_R) CUDA_TRY(cudaMalloc(&c.d_R, sizeof(double) * (size_t)c.nNo * 4));
   if (!c.d_Val) CUDA_TRY(cudaMalloc(&c.d_Val, sizeof(double) * (size_t)c.nnz * 16));
-  if (!c.d_flag) {
-    CUDA_TRY(cudaMalloc(&c.d_flag, sizeof(int) * 16));
-    CUDA_TRY(cudaMemset(c.d_flag, 0, sizeof(int) * 16));
-  }
   c.dof = dof;
   return 0;
 }
@@ -111,7 +110,6 @@ int run_fluid_asm(const FluidPar &par, int variant) {
     CUDA_TRY(cudaMemsetAsync(c.d_R, 0, sizeof(double) * (size_t)c.nNo * 4, c.stream));
     CUDA_TRY(cudaMemsetAsync(c.d_Val, 0, sizeof(double) * (size_t)c.nnz * 16, c.stream));
   }
-  CUDA_TRY(cudaMemsetAsync(c.d_flag, 0, sizeof(int), c.stream));
   const double *bf = g_haveBf ? c.d_Bf : nullptr;
   {
     ProfScope ps(PROF_ASM);
@@ -133,6 +131,7 @@ int run_fluid_asm(const FluidPar &par, int variant) {
       return fail(SVFSI_ERR_ARG, "unknown assembly variant");
     }
   }
+  jac_publish();   // bad-Jacobian count -> mapped host word, read at the next synchronisation point
   return 0;
 }
 
@@ -144,7 +143,6 @@ int run_heat_asm(const HeatPar &par, int variant) {
     CUDA_TRY(cudaMemsetAsync(c.d_R, 0, sizeof(double) * (size_t)c.nNo, c.stream));
     CUDA_TRY(cudaMemsetAsync(c.d_Val, 0, sizeof(double) * (size_t)c.nnz, c.stream));
   }
-  CUDA_TRY(cudaMemsetAsync(c.d_flag, 0, sizeof(int), c.stream));
   {
     ProfScope ps(PROF_ASM);
     if (variant == SVFSI_ASM_ATOMIC) {
@@ -164,16 +162,17 @@ int run_heat_asm(const HeatPar &par, int variant) {
       return fail(SVFSI_ERR_ARG, "unknown assembly variant");
     }
   }
+  jac_publish();
   return 0;
 }
 
+// the reference aborts in the element loop ("Jac < 0 @ element", S/FLUID.f:115).  Host-buffer calls
+// report it at once; the device-resident calls (gpu_construct_*_dev_) do not synchronise, so the
+// count travels to a mapped host word behind the kernels and the NEXT call that synchronises anyway
+// (gpu_solve_dev_, gpu_sync_, gpu_get_*_) returns SVFSI_ERR_JAC.  The count is never cleared.
 int check_jac() {
-  Ctx &c = ctx();
-  int bad = 0;
-  CUDA_TRY(cudaMemcpyAsync(&bad, c.d_flag, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
-  CUDA_TRY(cudaStreamSynchronize(c.stream));
-  if (bad) return fail(SVFSI_ERR_JAC, "Jac < 0 @ element (ISZERO(Jac), S/FLUID.f:115)");
-  return 0;
+  CUDA_TRY(cudaStreamSynchronize(ctx().stream));
+  return jac_check();
 }
 
 }  // namespace
@@ -197,6 +196,7 @@ int32_t gpu_init_(const int32_t *device, const int32_t *rank, const int32_t *nra
   c.nranks = *nranks;
   CUDA_TRY(cudaSetDevice(c.device));
   CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  if (int rc = status_words_init()) return rc;
   if (c.nranks > 1) {
     if (!uid128) return fail(SVFSI_ERR_ARG, "nranks > 1 needs the NCCL unique id");
     if (int rc = nccl_init_rank(uid128, c.nranks, c.rank)) return rc;
@@ -251,7 +251,13 @@ int32_t gpu_finalize_(void) {
   gpu_lhs_free_();
   dev_free(&c.d_ws); c.wsBytes = 0;
   dev_free(&c.d_stage); c.stageBytes = 0;
-  dev_free(&c.d_flag);
+  dev_free(&c.d_small); dev_free(&c.d_partial); c.partialDoubles = 0;
+  if (c.h_small) cudaFreeHost(c.h_small);
+  c.h_small = nullptr;
+  solver_free_static();     // W / RCS work vectors, transposed-position map, host mirror
+  status_words_free();
+  for (EventPair &ep : c.evPool) { cudaEventDestroy(ep.a); cudaEventDestroy(ep.b); }
+  c.evPool.clear(); c.evUsed = 0;
   nccl_destroy();
   if (c.stream) cudaStreamDestroy(c.stream);
   c.stream = nullptr;
@@ -414,8 +420,13 @@ int32_t gpu_bc_create_(const int32_t *faIn, const int32_t *nNo_, const int32_t *
   if (f.created) return fail(SVFSI_ERR_STATE, "FSILS: face is not free, you may use FSILS_BC_FREE to free it");
   const int n = *nNo_, dof = *dof_;
   f.nNo = n; f.dof = dof; f.bGrp = *BC_type;
+  if (n < 0 || dof < 1) return fail(SVFSI_ERR_ARG, "FSILS_BC_CREATE: bad nNo / dof");
   f.glob.resize(n);
-  for (int a = 0; a < n; a++) f.glob[a] = c.map[gNodes[a] - 1];
+  for (int a = 0; a < n; a++) {
+    if (gNodes[a] < 1 || gNodes[a] > c.nNo)
+      return fail(SVFSI_ERR_ARG, "FSILS_BC_CREATE: face node id out of range");
+    f.glob[a] = c.map[gNodes[a] - 1];
+  }
   std::vector<double> v((size_t)n * dof, 0.0);
   if (val) std::copy(val, val + (size_t)n * dof, v.begin());
   // sharedFlag: more than one rank holds nodes of the face (L/BC.f:99-118)
@@ -479,7 +490,19 @@ int32_t gpu_mesh_create_(const int32_t *nEl_, const int32_t *eNoN, const int32_t
   if (int rc = upload_nodal(x, 3, c.d_x)) return rc;
   dev_free(&c.d_edest);
   CUDA_TRY(cudaMalloc(&c.d_edest, sizeof(int) * (size_t)nEl * 16));
-  launch_build_edest(c.stream, nEl, c.d_ien, c.d_rowPtr, c.d_col, c.d_edest);
+  // every (a,b) of every element must exist in the pattern (DOASSEM would fall off the end of its
+  // search, S/LHSA.f:282-292): build_edest counts the missing ones into d_flag[1]
+  CUDA_TRY(cudaMemsetAsync(c.d_flag + 1, 0, sizeof(int), c.stream));
+  launch_build_edest(c.stream, nEl, c.d_ien, c.d_rowPtr, c.d_col, c.d_edest, c.d_flag + 1);
+  {
+    int missing = 0;
+    CUDA_TRY(cudaMemcpyAsync(&missing, c.d_flag + 1, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    CUDA_TRY(cudaStreamSynchronize(c.stream));
+    if (missing)
+      return fail(SVFSI_ERR_ARG, "gpu_mesh_create_: " + std::to_string(missing) +
+                                     " element node pairs are not in the rowPtr/colPtr pattern given to "
+                                     "gpu_lhs_create_");
+  }
   std::vector<int> colorElems;
   try {
     color_elements(nEl, c.nNo, ien, c.colorOff, colorElems);
@@ -506,7 +529,6 @@ int32_t gpu_mesh_create_(const int32_t *nEl_, const int32_t *eNoN, const int32_t
     return rc;
   if (int rc = build_block_desc(c.stream, c.nnz, c.d_blkOrder, c.d_blkAdjPtr, &c.d_blkDesc)) return rc;
   CUDA_TRY(cudaStreamSynchronize(c.stream));
-  // every (a,b) of every element must exist in the pattern
   c.mesh = true;
   return 0;
 }
@@ -603,7 +625,7 @@ int32_t gpu_commu_(const int32_t *dof, double *R) {
   launch_perm_gather(c.stream, c.nNo, *dof, c.d_perm, dv, c.d_stage);
   CUDA_TRY(cudaMemcpyAsync(R, c.d_stage, bytes, cudaMemcpyDeviceToHost, c.stream));
   CUDA_TRY(cudaStreamSynchronize(c.stream));
-  return 0;
+  return comm_check();
 }
 
 int32_t gpu_ls_create_(svfsi_ls_t *ls, const int32_t *LS_type) {
@@ -621,7 +643,8 @@ int32_t gpu_solve_dev_(svfsi_ls_t *ls, const int32_t *dof, const int32_t *prec,
   if (int rc = need_init()) return rc;
   if (int rc = fsils_solve_dev(ls, *dof, *prec, incL, res)) return rc;
   CUDA_TRY(cudaStreamSynchronize(ctx().stream));
-  return 0;
+  if (int rc = comm_check()) return rc;
+  return jac_check();   // of the element loop that produced this system (device-resident path)
 }
 
 int32_t gpu_solve_(svfsi_ls_t *ls, const int32_t *dof, double *Ri, const double *Val,
@@ -631,7 +654,8 @@ int32_t gpu_solve_(svfsi_ls_t *ls, const int32_t *dof, double *Ri, const double 
   if (Val)
     if (int rc = gpu_set_val_(dof, Val)) return rc;
   if (int rc = fsils_solve_dev(ls, *dof, *prec, incL, res)) return rc;
-  return gpu_get_r_(dof, Ri);
+  if (int rc = gpu_get_r_(dof, Ri)) return rc;
+  return comm_check();
 }
 
 int32_t gpu_sparmul_(const int32_t *kind, const int32_t *dof, const double *K, const double *U,
@@ -649,6 +673,7 @@ int32_t gpu_sparmul_(const int32_t *kind, const int32_t *dof, const double *K, c
   if (!rc) rc = upload_nodal(U, bc, dU);
   if (!rc) rc = sparmul(k, d, dK, dU, dKU, nullptr);
   if (!rc) rc = download_nodal(dKU, br, KU);
+  if (!rc) rc = comm_check();
   cudaFree(dK); cudaFree(dU); cudaFree(dKU);
   return rc;
 }
@@ -670,6 +695,7 @@ int32_t gpu_dot_(const int32_t *dof, const double *U, const double *V, double *r
   if (!rc) {
     cudaMemcpyAsync(result, c.d_small + 64, sizeof(double), cudaMemcpyDeviceToHost, c.stream);
     cudaStreamSynchronize(c.stream);
+    rc = comm_check();
   }
   cudaFree(dU); cudaFree(dV);
   return rc;
@@ -785,6 +811,12 @@ int32_t gpu_get_stream_(void **stream) {
 int32_t gpu_sync_(void) {
   if (int rc = need_init()) return rc;
   CUDA_TRY(cudaStreamSynchronize(ctx().stream));
+  if (int rc = comm_check()) return rc;
+  return jac_check();
+}
+int32_t gpu_set_comm_timeout_(const double *seconds) {
+  if (!(*seconds > 0.0)) return fail(SVFSI_ERR_ARG, "gpu_set_comm_timeout_: seconds must be > 0");
+  ctx().commTimeoutS = *seconds;
   return 0;
 }
 

@@ -278,7 +278,61 @@ static P2PDev p2p_dev() {
   pd.haloCap = c.p2p.haloCap;
   pd.rank = c.rank;
   pd.nranks = c.nranks;
+  pd.errDev = c.d_flag + 2;
+  pd.errHost = c.h_status_dev;
+  pd.timeoutNs = (long long)(c.commTimeoutS * 1e9);
   return pd;
+}
+
+// ------------------------------------------------------------------ sticky error words
+int status_words_init() {
+  Ctx &c = ctx();
+  if (!c.d_flag) {
+    CUDA_TRY(cudaMalloc(&c.d_flag, sizeof(int) * 16));
+    CUDA_TRY(cudaMemset(c.d_flag, 0, sizeof(int) * 16));
+  }
+  if (!c.h_status) {
+    void *p = nullptr, *d = nullptr;
+    CUDA_TRY(cudaHostAlloc(&p, sizeof(int) * 16, cudaHostAllocMapped));
+    memset(p, 0, sizeof(int) * 16);
+    CUDA_TRY(cudaHostGetDevicePointer(&d, p, 0));
+    c.h_status = (volatile int *)p;
+    c.h_status_dev = (int *)d;
+  }
+  c.jacSeen = 0;
+  const char *e = getenv("SVFSI_COMM_TIMEOUT_S");
+  if (e && atof(e) > 0.0) c.commTimeoutS = atof(e);
+  return 0;
+}
+void status_words_free() {
+  Ctx &c = ctx();
+  if (c.d_flag) cudaFree(c.d_flag);
+  c.d_flag = nullptr;
+  if (c.h_status) cudaFreeHost((void *)c.h_status);
+  c.h_status = nullptr;
+  c.h_status_dev = nullptr;
+}
+int comm_check() {
+  Ctx &c = ctx();
+  if (c.h_status && c.h_status[0])
+    return fail(SVFSI_ERR_COMM, "a peer-flag wait timed out inside a halo / all-reduce kernel (a rank is "
+                                "dead or more than the comm time-out late); results since then are invalid");
+  return 0;
+}
+void jac_publish() {
+  Ctx &c = ctx();
+  if (c.d_flag && c.h_status)
+    cudaMemcpyAsync((void *)(c.h_status + 1), c.d_flag, sizeof(int), cudaMemcpyDeviceToHost, c.stream);
+}
+int jac_check() {
+  Ctx &c = ctx();
+  if (!c.h_status) return 0;
+  const int bad = c.h_status[1];
+  if (bad != c.jacSeen) {
+    c.jacSeen = bad;
+    return fail(SVFSI_ERR_JAC, "Jac < 0 @ element (ISZERO(Jac), S/FLUID.f:115)");
+  }
+  return 0;
 }
 
 // ------------------------------------------------------------------ collectives

@@ -36,6 +36,15 @@ int sparmul(int kind, int dof, const double *K, const double *U, double *KU, con
 int row_dof(int kind, int dof);  // dof of KU
 int col_dof(int kind, int dof);  // dof of U
 
+// ---- sticky error words (ctx.h: d_flag / h_status) ----
+int status_words_init();   // allocate d_flag + the mapped host words (gpu_init_)
+void status_words_free();
+// after a host synchronisation: SVFSI_ERR_COMM if an in-kernel peer-flag wait timed out (sticky until
+// gpu_finalize_), SVFSI_ERR_JAC if an element loop met ISZERO(Jac) since the last report
+int comm_check();
+int jac_check();           // host already synchronised with the copy queued by jac_publish()
+void jac_publish();        // queue d_flag[0] -> h_status[1] behind the element kernels (no sync)
+
 // ---- workspace ----
 int ensure_ws(size_t bytes);          // d_ws >= bytes (contents not preserved)
 int ensure_stage(size_t bytes);

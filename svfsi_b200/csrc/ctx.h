@@ -140,7 +140,16 @@ struct Ctx {
   double *d_Ag = nullptr, *d_Yg = nullptr, *d_Bf = nullptr;  // [nNo][4],[nNo][4],[nNo][3]
   double *d_stage = nullptr;  // staging for H2D/D2H permutes
   size_t stageBytes = 0;
-  int *d_flag = nullptr;      // device int flags (e.g. bad Jacobian count)
+  // device int words: [0] bad-Jacobian count (monotone since gpu_init_, never cleared so that a hit is
+  // not lost before the host has seen it), [1] scratch of the setup checks, [2] sticky "peer flag wait
+  // timed out"
+  int *d_flag = nullptr;
+  // mapped pinned host words the device (or an async copy) writes and the host reads at its next
+  // synchronisation point without another copy: [0] comm time-out, [1] copy of d_flag[0]
+  volatile int *h_status = nullptr;
+  int *h_status_dev = nullptr;   // device alias of h_status
+  int jacSeen = 0;               // value of the bad-Jacobian count already reported
+  double commTimeoutS = 120.0;   // bound of every in-kernel peer-flag wait (gpu_set_comm_timeout_)
 
   // ---- solver workspace (grown on demand) ----
   double *d_ws = nullptr;

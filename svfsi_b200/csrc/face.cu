@@ -287,10 +287,6 @@ int32_t gpu_face_create_(const int32_t *iFa, const int32_t *nNo_, const int32_t 
   CUDA_TRY(cudaMalloc(&f.d_lK, sizeof(double) * ne * 9));
   CUDA_TRY(cudaMalloc(&f.d_part, sizeof(double) * ne));
   if (nEl > 0) {
-    if (!c.d_flag) {
-      CUDA_TRY(cudaMalloc(&c.d_flag, sizeof(int) * 16));
-      CUDA_TRY(cudaMemset(c.d_flag, 0, sizeof(int) * 16));
-    }
     CUDA_TRY(cudaMemsetAsync(c.d_flag + 1, 0, sizeof(int), c.stream));
     face_setup_kernel<<<(nEl + 127) / 128, 128, 0, c.stream>>>(nEl, f.d_node, f.d_par, c.d_ien,
                                                                c.d_rowPtr, c.d_col, f.d_opp, f.d_dest,

@@ -50,6 +50,9 @@ struct P2PDev {
   char **peer;          // [nranks] arena bases
   size_t offMail, offHalo;
   int haloCap, rank, nranks;
+  int *errDev;              // sticky "a flag wait timed out" word in device memory (Ctx::d_flag + 2)
+  volatile int *errHost;    // the same in mapped pinned host memory (Ctx::h_status[0])
+  long long timeoutNs;      // bound of every in-kernel flag wait
 };
 // SpMV with the halo send fused into the kernel (la_kernels.cu: spmv_*_fused_kernel)
 struct SpmvFuse {
@@ -222,8 +225,9 @@ int build_gather_adjacency(cudaStream_t st, int nEl, int nNo, int nnz, const int
                            const int *edest, int **blkAdjPtr, int **blkAdj, int **nodeAdjPtr,
                            int **nodeAdj, int **blkOrder);
 // edest[e][a*4+b] = device block index of (row ien[e][a], col ien[e][b])
+// (a,b) pairs that are not in the pattern get -1 and are counted into *missing
 void launch_build_edest(cudaStream_t st, int nEl, const int *ien, const int *rowPtr,
-                        const int *col, int *edest);
+                        const int *col, int *edest, int *missing);
 
 int spmv_fused_quad_enabled();   // the fused SpMV + halo-send kernel runs 4 lanes per row
 int set_spmv_quad(int on);   // SPARMULVV dof=4 kernel variant on the unfused path (la_kernels.cu)

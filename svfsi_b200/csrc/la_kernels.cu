@@ -32,8 +32,33 @@ __device__ __forceinline__ void st_flag_sys(volatile int *p, int v) {
   __threadfence_system();
   *p = v;
 }
-__device__ __forceinline__ void wait_flag_sys(volatile int *p, int v) {
-  while (*p != v) { /* spin on a word in local memory that the peer writes */ }
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// Spin on a word in local memory that the peer writes -- BOUNDED: a dead or late rank must not
+// deadlock every GPU of the box (the reference's MPI_WAIT would block too, but an MPI job is killed
+// as a whole; a spinning kernel cannot be).  After pd.timeoutNs the waiter raises the sticky error
+// words (device copy: later kernels of the stream see it on their first poll and leave at once;
+// mapped host copy: the host returns SVFSI_ERR_COMM at its next synchronisation point) and goes on
+// with whatever the buffers hold.
+__device__ __forceinline__ void wait_flag_sys(volatile int *p, int v, const P2PDev &pd) {
+  const int e0 = *(volatile int *)pd.errDev;   // issued together with the first poll
+  if (*p != v && e0 == 0) {
+    const unsigned long long t0 = global_ns();
+    unsigned it = 0;
+    while (*p != v) {
+      if ((++it & 255u) == 0) {
+        if (*(volatile int *)pd.errDev != 0) break;
+        if (global_ns() - t0 > (unsigned long long)pd.timeoutNs) {
+          *(volatile int *)pd.errDev = 1;
+          *pd.errHost = 1;
+          break;
+        }
+      }
+    }
+  }
   __threadfence_system();
 }
 // flags live at the start of the arena: int[4][64]: 0 = halo slot0, 1 = halo slot1, 2 = ar slot0, 3 = ar slot1
@@ -672,7 +697,7 @@ __global__ void __launch_bounds__(256) halo_recv_add_kernel(P2PDev pd, int dof, 
                                                             const int *__restrict__ uniqSlot,
                                                             double *__restrict__ R, int seq) {
   const int slot = seq & 1;
-  if (threadIdx.x < nNbr) wait_flag_sys(flag_ptr(pd.peer[pd.rank], slot, nbrRank[threadIdx.x]), seq);
+  if (threadIdx.x < nNbr) wait_flag_sys(flag_ptr(pd.peer[pd.rank], slot, nbrRank[threadIdx.x]), seq, pd);
   __syncthreads();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nUniq * dof) return;
@@ -804,7 +829,7 @@ __global__ void __launch_bounds__(512) p2p_allreduce_kernel(P2PDev pd, const dou
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x < pd.nranks) st_flag_sys(flag_ptr(pd.peer[threadIdx.x], 2 + slot, pd.rank), seq);
-  if (threadIdx.x < pd.nranks) wait_flag_sys(flag_ptr(pd.peer[pd.rank], 2 + slot, threadIdx.x), seq);
+  if (threadIdx.x < pd.nranks) wait_flag_sys(flag_ptr(pd.peer[pd.rank], 2 + slot, threadIdx.x), seq, pd);
   __syncthreads();
   const double *mb = (const double *)(pd.peer[pd.rank] + pd.offMail) + (size_t)slot * pd.nranks * kArMax;
   __syncthreads();   // everyone is done reading mine[] as the send buffer

@@ -101,6 +101,12 @@ int g_tpos_gen = -1;
 
 }  // namespace
 
+void nssolver_free_static() {
+  if (g_tpos) cudaFree(g_tpos);
+  g_tpos = nullptr;
+  g_tpos_gen = -1;
+}
+
 int nssolver_dev(svfsi_ls_t *ls, int dof, const double *Val, double *Ri) {
   Ctx &c = ctx();
   const int nsd = dof - 1;

@@ -22,6 +22,10 @@ namespace svfsi {
 struct PicState {
   int tDof = 0, gen = -1;
   bool haveD = false;
+  // Ao = An; Yo = Yn; Do = Dn (S/MAIN.f:277-279) is a pointer swap here; in the reference An/Yn/Dn
+  // still EQUAL the new state after those copies, so until the next PICP overwrites the "new"
+  // buffers every read of the new state is served from the "old" ones
+  bool advanced = false;
   double *Ao = nullptr, *Yo = nullptr, *Do = nullptr, *An = nullptr, *Yn = nullptr, *Dn = nullptr,
          *Dg = nullptr;
 };
@@ -86,7 +90,8 @@ __global__ void setbcdir_kernel(int faNo, int tDof, int s, int lDof, const int *
 }
 
 const double *pic_state_Yn() {
-  return (g_pic.Yn && g_pic.gen == ctx().lhsGen && g_pic.tDof == 4) ? g_pic.Yn : nullptr;
+  if (!(g_pic.Yn && g_pic.gen == ctx().lhsGen && g_pic.tDof == 4)) return nullptr;
+  return g_pic.advanced ? g_pic.Yo : g_pic.Yn;
 }
 
 static int pic_ready() {
@@ -134,6 +139,7 @@ int32_t gpu_pic_init_(const int32_t *tDof, const double *Ao, const double *Yo, c
   if (g_pic.haveD)
     CUDA_TRY(cudaMemcpyAsync(g_pic.Dn, g_pic.Do, bytes, cudaMemcpyDeviceToDevice, c.stream));
   g_pic.gen = c.lhsGen;
+  g_pic.advanced = false;
   return 0;
 }
 
@@ -147,6 +153,7 @@ int32_t gpu_picp_(const double *gam) {
   Ctx &c = ctx();
   const size_t n = (size_t)c.nNo * g_pic.tDof;
   const double coef = (*gam - 1.0) / *gam;
+  g_pic.advanced = false;
   picp_kernel<<<pic_grid(n), 256, 0, c.stream>>>(n, coef, g_pic.Ao, g_pic.Yo, g_pic.Do, g_pic.An,
                                                  g_pic.Yn, g_pic.haveD ? g_pic.Dn : nullptr);
   count_launch();
@@ -215,12 +222,14 @@ int32_t gpu_pic_advance_(void) {
   std::swap(g_pic.Ao, g_pic.An);
   std::swap(g_pic.Yo, g_pic.Yn);
   if (g_pic.haveD) std::swap(g_pic.Do, g_pic.Dn);
+  g_pic.advanced = true;
   return 0;
 }
 
 int32_t gpu_pic_get_(const int32_t *which, double *A, double *Y, double *D) {
   if (int rc = pic_ready()) return rc;
-  const bool nw = (*which != 0);   // 0: old (Ao, Yo, Do), 1: new (An, Yn, Dn)
+  // 0: old (Ao, Yo, Do), 1: new (An, Yn, Dn); right after gpu_pic_advance_ both are the same state
+  const bool nw = (*which != 0) && !g_pic.advanced;
   if (A) if (int rc = download_nodal(nw ? g_pic.An : g_pic.Ao, g_pic.tDof, A)) return rc;
   if (Y) if (int rc = download_nodal(nw ? g_pic.Yn : g_pic.Yo, g_pic.tDof, Y)) return rc;
   if (D && g_pic.haveD)

@@ -58,6 +58,7 @@ int wait_flag(int seq, int *flag) {
   Ctx &c = ctx();
   unsigned long spins = 0;
   while (g_hm->progress - seq < 0) {
+    if (c.h_status && c.h_status[0]) return comm_check();   // an in-kernel peer wait timed out
     if ((++spins & 0xFFFFF) == 0) {  // every ~1M polls make sure the stream is still alive
       cudaError_t e = cudaStreamQuery(c.stream);
       if (e != cudaSuccess && e != cudaErrorNotReady)
@@ -266,10 +267,29 @@ GmresScal gmres_scal(double *base, int sD, int nFaces) {
   return g;
 }
 
+static size_t g_smallCap = 1 << 17;
+static double *g_dW = nullptr, *g_dRcs = nullptr;   // W of PRECONDDIAG; Wr, Wc, W1 of PRECONDRCS
+static size_t g_wCap = 0, g_rcsCap = 0;
+void nssolver_free_static();   // nssolver.cu
+
+// gpu_finalize_: everything this file and nssolver.cu keep between calls belongs to the device that
+// is going away
+void solver_free_static() {
+  if (g_dW) cudaFree(g_dW);
+  if (g_dRcs) cudaFree(g_dRcs);
+  g_dW = g_dRcs = nullptr;
+  g_wCap = g_rcsCap = 0;
+  g_smallCap = 1 << 17;
+  if (g_hm) cudaFreeHost((void *)g_hm);
+  g_hm = g_hm_dev = nullptr;
+  g_seq = 0;
+  nssolver_free_static();
+}
+
 int ensure_small_n(size_t nd) {
   Ctx &c = ctx();
   if (int rc = ensure_small()) return rc;
-  static size_t cap = 1 << 17;
+  size_t &cap = g_smallCap;
   if (nd <= cap) return 0;
   cudaFree(c.d_small);
   cudaFreeHost(c.h_small);
@@ -687,6 +707,14 @@ int fsils_solve_dev(svfsi_ls_t *ls, int dof, int prec, const int32_t *incL, cons
       f.coupled = true;
     }
   }
+  // "Krylov space dimension": the fused multi-dot / column kernels hold one Arnoldi column (sD + 1
+  // inner products) in kArMax-sized shared-memory arrays and partial-sum rows
+  if (ls->LS_type == SVFSI_LS_TYPE_GMRES || ls->LS_type == SVFSI_LS_TYPE_NS) {
+    const int sDk = (ls->LS_type == SVFSI_LS_TYPE_NS) ? ls->GM.sD : ls->RI.sD;
+    if (sDk < 1 || sDk + 1 > kArMax)
+        return fail(SVFSI_ERR_ARG, "FSILS: Krylov space dimension must be 1.." + std::to_string(kArMax - 1));
+  }
+  if (dof < 1 || dof > 4) return fail(SVFSI_ERR_ARG, "FSILS: dof must be 1..4");
   if (prec != SVFSI_PRECOND_FSILS && prec != SVFSI_PRECOND_RCS)
     return fail(SVFSI_ERR_UNSUPPORTED,
                 "FSILS: this linear solver and preconditioner combination is not supported");
@@ -694,8 +722,8 @@ int fsils_solve_dev(svfsi_ls_t *ls, int dof, int prec, const int32_t *incL, cons
 
   ProfScope ps(PROF_SOLVE);
   // the solvers may grow (reallocate) the workspace, so W lives in its own buffer
-  static double *d_W = nullptr;
-  static size_t wCap = 0;
+  double *&d_W = g_dW;
+  size_t &wCap = g_wCap;
   const size_t wNeed = (size_t)c.nNo * dof * sizeof(double);
   if (wCap < wNeed) {
     if (d_W) cudaFree(d_W);
@@ -705,8 +733,8 @@ int fsils_solve_dev(svfsi_ls_t *ls, int dof, int prec, const int32_t *incL, cons
   if (prec == SVFSI_PRECOND_FSILS) {
     if (int rc = preconddiag(dof, c.d_Val, c.d_R, d_W)) return rc;
   } else {
-    static double *d_rcs = nullptr;   // Wr, Wc, W1 of PRECONDRCS
-    static size_t rcsCap = 0;
+    double *&d_rcs = g_dRcs;
+    size_t &rcsCap = g_rcsCap;
     const size_t need = 3 * padded((size_t)c.nNo * dof);
     if (rcsCap < need) {
       if (d_rcs) cudaFree(d_rcs);

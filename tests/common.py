@@ -128,13 +128,55 @@ def local_face(m, rm, name):
     return rm.faces[name]["gN"], fIEN, gE
 
 
+class OracleCplBC:
+    """SETBCCPL / CALCDERCPLBC / RCRINIT sequencing (S/SETBC.f:981-1123, S/BAFINI.f:69-104, S/MAIN.f:280)
+    around the ORACLE's own RCR_Integ_X restatement (oracle.rcr_integ_x / calc_der_cplbc), so that the
+    RCR parity tests do not compare the product's `svfsi_b200/cplbc.py` with itself.  `faces` only needs
+    the attributes Rp, C, Rd, Pd, Xo."""
+
+    def __init__(self, faces, dt, scheme="SI"):
+        self.Rp = [f.Rp for f in faces]; self.C = [f.C for f in faces]
+        self.Rd = [f.Rd for f in faces]; self.Pd = [f.Pd for f in faces]
+        self.Xo0 = [f.Xo for f in faces]
+        self.n, self.dt, self.schm = len(faces), float(dt), scheme
+        self.xo = np.zeros(self.n); self.xn = np.zeros(self.n); self.y = np.zeros(self.n)
+        self.r = np.zeros(self.n); self.Qo = np.zeros(self.n); self.Qn = np.zeros(self.n)
+
+    def _fluxes(self, integ):
+        for i in range(self.n):
+            self.Qo[i] = integ(i, "o"); self.Qn[i] = integ(i, "n")
+
+    def _calcder(self, integ, time):
+        self._fluxes(integ)
+        self.xn, _ = ora.rcr_integ_x(self.xo, self.Qo, self.Qn, self.Rp, self.C, self.Rd, self.Pd, self.dt, time)
+        y, r = ora.calc_der_cplbc(self.xo, self.Qo, self.Qn, self.Rp, self.C, self.Rd, self.Pd, self.dt, time)
+        self.y, self.r = np.array(y, dtype=np.float64), np.array(r, dtype=np.float64)
+
+    def init(self, integ, time=0.0):
+        self.xo = np.array(self.Xo0, dtype=np.float64)
+        self.y[:] = 0.0
+        if self.schm != "E":
+            self._calcder(integ, time)
+
+    def setbccpl(self, integ, time):
+        if self.schm == "I":
+            self._calcder(integ, time)
+        else:
+            self._fluxes(integ)
+            self.xn, y = ora.rcr_integ_x(self.xo, self.Qo, self.Qn, self.Rp, self.C, self.Rd, self.Pd, self.dt, time)
+            self.y = np.array(y, dtype=np.float64)
+        return self.y.copy()
+
+    def advance(self):
+        self.xo = np.array(self.xn, dtype=np.float64).copy()
+
+
 def oracle_rcr_time_loop(m, p, faces_rcr, nsteps=2, nnewton=3, relTol=1e-5, sD=80, umax_in=-12.0, scheme="SI"):
     """The shape of BASELINE configs[0] (04-fluid/01-pipe3D_RCR) on one rank with the ORACLE: steady
     parabolic Dirichlet inlet, no-slip wall, RCR outlet.  Per Newton iteration (S/MAIN.f:111-206):
     SETBCCPL (fluxes of Yo / Yn through the outlet -> RCR_Integ_X -> g) -> PICI -> element loop ->
     Neumann face with h = g (S/SETBC.f:267-270, BASSEMNEUBC) -> FSILS_SOLVE with res = gam*dt*r -> PICC;
     per time step cplBC%xo = cplBC%xn.  Returns per-iteration (iNorm, itr, g, Qn) and the final (An, Yn)."""
-    from svfsi_b200 import cplbc
     ga = GA
     nNo = p.rm.nNo
     rng = np.random.default_rng(21)
@@ -150,7 +192,7 @@ def oracle_rcr_time_loop(m, p, faces_rcr, nsteps=2, nnewton=3, relTol=1e-5, sD=8
     gout, fIEN, gE = local_face(m, p.rm, "outlet")
     w = oracle_world([p], m.nNo)
     par = fluid_par()
-    cpl = cplbc.CplBC(faces_rcr, DT, scheme)
+    cpl = OracleCplBC(faces_rcr, DT, scheme)     # the ORACLE's 0-D restatement, not the product's cplbc.py
     state = dict(Yo=Yo, Yn=Yo)
 
     def integ(i, which):

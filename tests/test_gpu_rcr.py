@@ -4,10 +4,8 @@ model stays on the host (`svfsi_b200/cplbc.py`, as in the reference); the device
 (`gpu_face_integ_v_`) and consumes the face pressure (`gpu_bassem_neu_fluid_`) and the resistance
 (`res` of `gpu_solve_dev_` -> ADDBCMUL).
 
-Written at the end of round 1 after the GPU budget was spent: NOT YET RUN ON A B200.  It is collected only
-with SVFSI_RUN_UNVERIFIED=1 so that an unverified test cannot turn the suite red; run it first thing in
-the next GPU session and drop the guard."""
-import os
+First run on a B200 in round 2 (gpurun_out/r02s1_pytest_rcr.log: passed); the oracle loop it is compared
+with integrates the 0-D model with the oracle's own restatement (tests/common.py::OracleCplBC)."""
 
 import numpy as np
 import pytest
@@ -15,9 +13,7 @@ import pytest
 import common as cm
 from svfsi_b200 import api, cplbc, mesh
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("SVFSI_RUN_UNVERIFIED") != "1",
-                                 reason="not yet verified on a B200 (set SVFSI_RUN_UNVERIFIED=1)")]
+pytestmark = pytest.mark.gpu
 
 
 def test_device_resident_rcr_time_loop(gpu_lib):

@@ -214,6 +214,23 @@ def partition_slabs(m: Mesh, nparts: int) -> np.ndarray:
     return np.clip(part, 0, nparts - 1).astype(np.int32)
 
 
+def partition_blocks(m: Mesh, nparts: int) -> np.ndarray:
+    """Element -> rank by QUADRANT of the cross-section (sign of the centroid's x and y) times
+    nparts/4 axial slabs: cut nodes on the pipe axis are shared by four ranks (eight where an axial
+    cut crosses the axis), every rank has three to seven neighbours -- what a ParMETIS partition of
+    a real vessel looks like and the axial slabs never do (there a node is shared by two ranks at
+    most).  nparts must be a multiple of 4."""
+    if nparts % 4:
+        raise ValueError("partition_blocks needs nparts % 4 == 0")
+    c = m.x[m.IEN.astype(np.int64) - 1].mean(axis=1)
+    quad = (c[:, 0] > 0).astype(np.int32) + 2 * (c[:, 1] > 0).astype(np.int32)
+    nax = nparts // 4
+    nz = m.dims[2]
+    bounds = np.linspace(0, nz, nax + 1).round().astype(np.int64)
+    ax = np.clip(np.searchsorted(bounds, m.cell_k, side="right") - 1, 0, nax - 1).astype(np.int32)
+    return (ax * 4 + quad).astype(np.int32)
+
+
 def first_touch_unique(ien_flat: np.ndarray):
     """Unique values of `ien_flat` in order of first appearance, and the inverse map."""
     uniq, first, inv = np.unique(ien_flat, return_index=True, return_inverse=True)
@@ -290,13 +307,13 @@ class RankProblem:
 
 
 def build_problem(nx, ny, nz, nparts=1, R=2.0, L=30.0, umax=10.0, pert=0.01, acc=0.0,
-                  seed=SEED):
+                  seed=SEED, partition="slabs"):
     """Synthetic pipe problem: mesh, axial-slab partition, per-rank CSR and state, and the three
     faces (inlet/wall Dirichlet with zero mask, outlet Neumann with val = int N n dGamma,
     BAFINI.f:490-533)."""
     m = make_cylinder(nx, ny, nz, R=R, L=L)
     Ag, Yg = poiseuille_state(m, umax=umax, pert=pert, seed=seed, acc=acc)
-    part = partition_slabs(m, nparts)
+    part = partition_blocks(m, nparts) if partition == "blocks" else partition_slabs(m, nparts)
     rms = split_mesh(m, part, nparts)
     out = []
     for rm in rms:

@@ -1,5 +1,7 @@
 """Shared helpers of the parity tests: run the CPU oracle (oracle/) end to end on the same
 synthetic problem the CUDA path gets.  Test infrastructure only."""
+import os
+
 import numpy as np
 
 from oracle import oracle as ora
@@ -60,11 +62,22 @@ def oracle_commu(w, probs, Rs, dof=4):
     return [t[mp].copy() for t, mp in zip(tmp, maps)]
 
 
+def log_parity(name, **vals):
+    """every measured parity error goes to stdout and, when SVFSI_PARITY_LOG names a file, into it
+    (profiles/r02_parity.log is such a file from a B200 run)"""
+    line = name + ": " + ", ".join(f"{k}={v:.3e}" if isinstance(v, float) else f"{k}={v}" for k, v in vals.items())
+    print(line, flush=True)
+    path = os.environ.get("SVFSI_PARITY_LOG")
+    if path:
+        with open(path, "a") as fh:
+            fh.write(line + "\n")
+
+
 def oracle_gmres_global(nparts, relTol, sD, mItr, res_out, dims=(8, 8, 20), L=4.0,
-                        ls_type=None, prec=ora.PRECOND_FSILS, perturb=None, **lskw):
+                        ls_type=None, prec=ora.PRECOND_FSILS, perturb=None, partition="slabs", **lskw):
     """Assemble + COMMU + FSILS_SOLVE with the oracle on `nparts` simulated ranks; returns
     (ls, X_global) with X gathered by global node id."""
-    m, probs, _ = mesh.build_problem(*dims, nparts=nparts, L=L)
+    m, probs, _ = mesh.build_problem(*dims, nparts=nparts, L=L, partition=partition)
     Rs, Vs = oracle_assemble(probs)
     if perturb is not None:      # rounding-level relative noise on the assembled system
         rng = np.random.default_rng(perturb)

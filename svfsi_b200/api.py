@@ -478,6 +478,16 @@ def PICC(eq: EqState, ls: "Ls", gam, beta, dt):
     return eq.ok
 
 
+def pici(am, af):
+    """the vector part of PICI alone (S/PIC.f:141-152), no eqType bookkeeping"""
+    _check(lib().gpu_pici_(_cd(am), _cd(af)))
+
+
+def picc(gam, beta, dt):
+    """the vector part of PICC alone (S/PIC.f:203-207)"""
+    _check(lib().gpu_picc_(_cd(gam), _cd(beta), _cd(dt)))
+
+
 def pic_advance(eq: EqState | None = None):
     _check(lib().gpu_pic_advance_())
     if eq is not None:

@@ -376,12 +376,17 @@ def build_rank_problem(nx, ny, nz, rank=0, nparts=1, R=2.0, L=30.0, umax=10.0, p
         present = (name == "wall") or (name == "inlet" and k0 == 0) or (name == "outlet" and k1 == nz)
         if not present:
             faces[name] = dict(gN=np.zeros(0, dtype=np.int32), val=None if name != "outlet" else np.zeros((0, 3)),
-                               bc="Neu" if name == "outlet" else "Dir")
+                               bc="Neu" if name == "outlet" else "Dir", IEN=np.zeros((0, 3), dtype=np.int32),
+                               gE=np.zeros(0, dtype=np.int32))
             continue
         gN_old = fa.gN.astype(np.int64)
         if name == "outlet":
             val = face_normal_integrals(sl, fa, fa.gN)
-            faces[name] = dict(gN=old2new[gN_old - 1].astype(np.int32), val=val, bc="Neu")
+            # faceType IEN / gE of the rank's share (S/DISTRIBUTE.f:1679-1689): boundary triangles in
+            # local node ids, parent tets as local element ids (1-based)
+            faces[name] = dict(gN=old2new[gN_old - 1].astype(np.int32), val=val, bc="Neu",
+                               IEN=old2new[fa.tri.astype(np.int64) - 1].astype(np.int32),
+                               gE=(fa.parent + 1).astype(np.int32))
         else:
             faces[name] = dict(gN=old2new[gN_old - 1].astype(np.int32), val=None, bc="Dir")
     g = ltg.astype(np.int64)

@@ -100,6 +100,28 @@ static PairLists pair_lists(const Ctx &c) {
   return pl;
 }
 
+// the owner-computes (gather) assembly: parts 1 = element records, 2 = tangent gather, 4 = residual gather.
+// tune bit 20 (1048576): second generation (asm_gather5.cu: 512-byte records v5, transposed blocks in adjacent
+// groups, residual folded into the diagonal groups; bit 21: 256-thread CTAs), otherwise the first-generation
+// kernels of asm_kernels.cu selected by the lower bits.
+static constexpr int kTuneVisit = 1 << 20;
+int fluid_gather_dispatch(int parts, const FluidPar &par, int tune) {
+  Ctx &c = ctx();
+  const double *bf = g_haveBf ? c.d_Bf : nullptr;
+  if (!c.d_elemP) CUDA_TRY(cudaMalloc(&c.d_elemP, sizeof(double) * 80 * (size_t)c.nEl));
+  if ((tune & kTuneVisit) && c.d_pairDesc && (double)c.nEl * 64 < 4.0e9) {
+    int p2 = (parts & 1) | ((parts & 6) ? 2 : 0);
+    launch_fluid_gather5(c.stream, p2, par, 0, c.nEl, 0, c.nnz, c.d_ien, c.d_x, c.d_Ag, c.d_Yg, bf, c.d_elemP,
+                         ~0u, c.d_pairDesc, c.d_blkAdj, c.d_R, c.d_Val, c.d_flag, (tune >> 21) & 7);
+    return 0;
+  }
+  launch_fluid_gather_parts(c.stream, parts, par, c.nEl, c.nNo, c.nnz, c.d_ien, c.d_x, c.d_Ag, c.d_Yg, bf,
+                            c.d_elemP, c.d_blkOrder, c.d_blkAdjPtr, c.d_blkAdj, c.d_nodeAdjPtr, c.d_nodeAdj,
+                            c.d_R, c.d_Val, c.d_flag, tune, c.d_rowPtr, c.d_nodeSlots, c.maxRowLen,
+                            pair_lists(c));
+  return 0;
+}
+
 int run_fluid_asm(const FluidPar &par, int variant) {
   Ctx &c = ctx();
   if (!c.mesh) return fail(SVFSI_ERR_STATE, "gpu_mesh_create_ has not been called");
@@ -122,11 +144,7 @@ int run_fluid_asm(const FluidPar &par, int variant) {
                          c.d_colorElems, c.d_ien, c.d_edest, c.d_x, c.d_Ag, c.d_Yg, bf, c.d_R,
                          c.d_Val, 0, c.d_flag);
     } else if (variant == SVFSI_ASM_GATHER) {
-      if (!c.d_elemP) CUDA_TRY(cudaMalloc(&c.d_elemP, sizeof(double) * 80 * (size_t)c.nEl));
-      launch_fluid_gather(c.stream, par, c.nEl, c.nNo, c.nnz, c.d_ien, c.d_x, c.d_Ag, c.d_Yg, bf,
-                          c.d_elemP, c.d_blkOrder, c.d_blkAdjPtr, c.d_blkAdj, c.d_nodeAdjPtr,
-                          c.d_nodeAdj, c.d_R, c.d_Val, c.d_flag, c.d_rowPtr, c.d_nodeSlots, c.maxRowLen,
-                          pair_lists(c));
+      if (int rc = fluid_gather_dispatch(7, par, asm_tune())) return rc;
     } else {
       return fail(SVFSI_ERR_ARG, "unknown assembly variant");
     }
@@ -236,6 +254,7 @@ int32_t gpu_lhs_free_(void) {
   dev_free(&c.d_blkAdjPtr); dev_free(&c.d_blkAdj); dev_free(&c.d_nodeAdjPtr);
   dev_free(&c.d_nodeAdj); dev_free(&c.d_blkOrder); dev_free(&c.d_elemP); dev_free(&c.d_nodeSlots);
   dev_free(&c.d_pairList); dev_free(&c.d_pairT); c.nPair = 0; dev_free(&c.d_blkDesc);
+  dev_free(&c.d_pairDesc); c.nPairDescOff = 0;
   dev_free(&c.d_R); dev_free(&c.d_Val); dev_free(&c.d_Ag); dev_free(&c.d_Yg); dev_free(&c.d_Bf);
   gpu_pic_free_();
   faces_free_all();
@@ -252,6 +271,7 @@ int32_t gpu_finalize_(void) {
   dev_free(&c.d_ws); c.wsBytes = 0;
   dev_free(&c.d_stage); c.stageBytes = 0;
   dev_free(&c.d_small); dev_free(&c.d_partial); c.partialDoubles = 0;
+  dev_free(&c.d_ticket);
   if (c.h_small) cudaFreeHost(c.h_small);
   c.h_small = nullptr;
   solver_free_static();     // W / RCS work vectors, transposed-position map, host mirror
@@ -373,6 +393,11 @@ int32_t gpu_lhs_create_(const int32_t *gnNo_, const int32_t *nNo_, const int32_t
     uniqSlot[uniqPtr[u] + fill[u]++] = (int)s;
   }
   c.nUniq = (int)uniqNode.size();
+  // the fused halo receive (la_kernels.cu multidot_fused_kernel) relies on what L/LHS.f:134-180 guarantees:
+  // the shared nodes are exactly rows [0, shnNo) and [mynNo, nNo)
+  c.uniqOrdered = (c.nUniq >= c.shnNo);
+  for (int u = 0; u < c.nUniq && c.uniqOrdered; u++)
+    c.uniqOrdered = (u < c.shnNo) ? (uniqNode[u] == u) : (uniqNode[u] >= c.mynNo);
   if (int rc = dev_upload(&c.d_packIdx, packIdx)) return rc;
   if (int rc = dev_upload(&c.d_uniqNode, uniqNode)) return rc;
   if (int rc = dev_upload(&c.d_uniqPtr, uniqPtr)) return rc;
@@ -514,6 +539,7 @@ int32_t gpu_mesh_create_(const int32_t *nEl_, const int32_t *eNoN, const int32_t
   dev_free(&c.d_blkAdjPtr); dev_free(&c.d_blkAdj); dev_free(&c.d_nodeAdjPtr);
   dev_free(&c.d_nodeAdj); dev_free(&c.d_blkOrder); dev_free(&c.d_elemP); dev_free(&c.d_nodeSlots);
   dev_free(&c.d_pairList); dev_free(&c.d_pairT); c.nPair = 0; dev_free(&c.d_blkDesc);
+  dev_free(&c.d_pairDesc); c.nPairDescOff = 0;
   if (int rc = build_gather_adjacency(c.stream, nEl, c.nNo, c.nnz, c.d_ien, c.d_edest,
                                       &c.d_blkAdjPtr, &c.d_blkAdj, &c.d_nodeAdjPtr, &c.d_nodeAdj,
                                       &c.d_blkOrder))
@@ -528,6 +554,9 @@ int32_t gpu_mesh_create_(const int32_t *nEl_, const int32_t *eNoN, const int32_t
                                 &c.d_pairList, &c.d_pairT, &c.nPair))
     return rc;
   if (int rc = build_block_desc(c.stream, c.nnz, c.d_blkOrder, c.d_blkAdjPtr, &c.d_blkDesc)) return rc;
+  if (int rc = build_paired_desc(c.stream, c.nPair, c.d_pairList, c.d_pairT, c.d_blkAdjPtr, c.d_rowOf, c.nnz,
+                                 &c.d_pairDesc, &c.nPairDescOff))
+    return rc;
   CUDA_TRY(cudaStreamSynchronize(c.stream));
   c.mesh = true;
   return 0;
@@ -733,7 +762,9 @@ int32_t gpu_time_kernel_(const int32_t *what, const int32_t *dof, const int32_t 
     launch_vecop(c.stream, VOP_ZERO, U, nullptr, nullptr, (size_t)(kk + 1) * stride, nullptr, 0.0, nullptr);
     CUDA_TRY(cudaEventRecord(a, c.stream));
     for (int r = 0; r < *reps; r++) {
-      if (*what == 3) launch_multidot(c.stream, U, stride, w, n, kk, c.d_partial, nullptr);
+      if (*what == 3 && *variant == 1) {   // the fused column kernel (multi-dot + block sums in one launch)
+        if ((rc = multidot_column(U, stride, w, n, kk, c.d_small + 64, nullptr, nullptr, false))) return rc;
+      } else if (*what == 3) launch_multidot(c.stream, U, stride, w, n, kk, c.d_partial, nullptr);
       else launch_multi_axpy_scale(c.stream, U, stride, w, n, kk, c.d_small + 64, nullptr, nullptr);
     }
     CUDA_TRY(cudaEventRecord(b, c.stream));
@@ -747,10 +778,7 @@ int32_t gpu_time_kernel_(const int32_t *what, const int32_t *dof, const int32_t 
     par.dt = 5e-3; par.af = 1.0 / 1.2; par.am = 0.5 * 2.8 / 1.2; par.gam = 0.5 + par.am - par.af;
     CUDA_TRY(cudaEventRecord(a, c.stream));
     for (int r = 0; r < *reps; r++)
-      launch_fluid_gather_parts(c.stream, *k, par, c.nEl, c.nNo, c.nnz, c.d_ien, c.d_x, c.d_Ag,
-                                c.d_Yg, nullptr, c.d_elemP, c.d_blkOrder, c.d_blkAdjPtr, c.d_blkAdj,
-                                c.d_nodeAdjPtr, c.d_nodeAdj, c.d_R, c.d_Val, c.d_flag, *variant,
-                                c.d_rowPtr, c.d_nodeSlots, c.maxRowLen, pair_lists(c));
+      if ((rc = fluid_gather_dispatch(*k, par, *variant))) return rc;
     CUDA_TRY(cudaEventRecord(b, c.stream));
   } else {
     return fail(SVFSI_ERR_ARG, "gpu_time_kernel_: unknown kernel id");

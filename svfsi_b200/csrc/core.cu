@@ -451,7 +451,57 @@ int host_allgather_i32(const int32_t *send, int32_t n, int32_t *recv) {
 int row_dof(int kind, int dof) { return (kind == 0 || kind == 2) ? dof : 1; }
 int col_dof(int kind, int dof) { return (kind == 0 || kind == 1) ? dof : 1; }
 
-int sparmul(int kind, int dof, const double *K, const double *U, double *KU, const int *done) {
+int multidot_column(const double *U, size_t stride, double *w, size_t nOwned, int k, double *out,
+                    const ColArgs *col, const int *done, bool recvPending) {
+  Ctx &c = ctx();
+  const bool fusedOk = k <= kArMax && (c.nranks == 1 || c.p2p.on) && (!recvPending || c.uniqOrdered);
+  static int useFused = -1;
+  if (useFused < 0) {
+    const char *e = getenv("SVFSI_DOT_FUSED");
+    useFused = e ? (atoi(e) != 0) : 1;
+  }
+  if (fusedOk && useFused) {
+    if (!c.d_ticket) {
+      CUDA_TRY(cudaMalloc((void **)&c.d_ticket, sizeof(unsigned int)));
+      CUDA_TRY(cudaMemsetAsync(c.d_ticket, 0, sizeof(unsigned int), c.stream));
+    }
+    HaloRecv hr;
+    memset(&hr, 0, sizeof(hr));
+    DotTail tail;
+    memset(&tail, 0, sizeof(tail));
+    if (recvPending) {
+      hr.on = 1;
+      hr.nNbr = (int)c.nbr.size(); hr.dof = c.pendRecvDof; hr.seq = c.p2p.haloSeq;
+      hr.shnNo = c.shnNo; hr.mynNo = c.mynNo; hr.nUniq = c.nUniq;
+      hr.nbrRank = c.p2p.d_nbrRank; hr.uniqNode = c.d_uniqNode; hr.uniqPtr = c.d_uniqPtr;
+      hr.uniqSlot = c.d_uniqSlot;
+    }
+    tail.nranks = c.nranks;
+    if (c.nranks > 1) {
+      tail.pd = p2p_dev();
+      tail.arSeq = ++c.p2p.arSeq;
+    }
+    tail.out = out;
+    tail.counter = c.d_ticket;
+    if (col) tail.col = *col;
+    ProfScope ps(PROF_DOT);
+    launch_multidot_fused(c.stream, U, stride, w, nOwned, k, c.d_partial, done, hr, tail);
+    return 0;
+  }
+  if (recvPending) {
+    ProfScope ps(PROF_HALO);
+    if (int rc = halo_recv(w, c.pendRecvDof, done)) return rc;
+  }
+  {
+    ProfScope ps(PROF_DOT);
+    launch_multidot(c.stream, U, stride, w, nOwned, k, c.d_partial, done);
+  }
+  if (col) return reduce_allreduce_column(c.d_partial, k, out, *col, done);
+  return reduce_allreduce(c.d_partial, k, out, done);
+}
+
+int sparmul(int kind, int dof, const double *K, const double *U, double *KU, const int *done,
+            bool *deferRecv) {
   Ctx &c = ctx();
   if (kind == 3) dof = 1;
   const int rd = row_dof(kind, dof);
@@ -473,6 +523,11 @@ int sparmul(int kind, int dof, const double *K, const double *U, double *KU, con
       f.nbrRank = c.p2p.d_nbrRank; f.nNbr = (int)c.nbr.size();
       f.pd = p2p_dev(); f.seq = c.p2p.haloSeq; f.counter = c.p2p.d_counter;
       launch_spmv_fused(c.stream, kind, dof, f, c.d_rowPtr, c.d_col, K, U, KU, done);
+    }
+    if (deferRecv && c.uniqOrdered) {   // the next multidot_column on KU receives
+      *deferRecv = true;
+      c.pendRecvDof = rd;
+      return 0;
     }
     ProfScope ps(PROF_HALO);
     return halo_recv(KU, rd, done);

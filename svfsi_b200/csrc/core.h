@@ -25,6 +25,12 @@ int allreduce_dev(double *buf, size_t n);
 int reduce_allreduce(const double *partial, int k, double *out, const int *done);
 int reduce_allreduce_column(const double *partial, int k, double *out, const ColArgs &col,
                             const int *done);
+// One Gram-Schmidt column: out[j] = all-reduce(<U_j, w> over owned rows), j < k, optionally preceded by
+// the halo receive that a sparmul(..., &deferred) left pending on w and followed by the GMRES column step
+// (col != NULL) -- ONE kernel on the single-rank and peer-memory paths (launch_multidot_fused), the
+// separate kernels otherwise.
+int multidot_column(const double *U, size_t stride, double *w, size_t nOwned, int k, double *out,
+                    const ColArgs *col, const int *done, bool recvPending);
 // peer-memory arena (IPC) set up after the halo schedule is known; falls back to NCCL
 int p2p_setup();
 void p2p_teardown();
@@ -32,7 +38,10 @@ void p2p_teardown();
 int host_allgather_i32(const int32_t *send, int32_t n, int32_t *recv);
 
 // ---- full FSILS_SPARMUL*: kernel + halo sum ----
-int sparmul(int kind, int dof, const double *K, const double *U, double *KU, const int *done);
+// deferRecv != NULL: on the fused peer-memory path the final halo RECEIVE is left to the caller's next
+// multidot_column(..., recvPending = *deferRecv) on KU (set to true when it was deferred)
+int sparmul(int kind, int dof, const double *K, const double *U, double *KU, const int *done,
+            bool *deferRecv = nullptr);
 int row_dof(int kind, int dof);  // dof of KU
 int col_dof(int kind, int dof);  // dof of U
 

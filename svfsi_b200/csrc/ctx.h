@@ -104,6 +104,9 @@ struct Ctx {
   // halo
   int nShared = 0;           // total entries in pack buffers (sum of nbr.n)
   int *d_packIdx = nullptr;  // [nShared] node id per pack slot
+  bool uniqOrdered = false;  // uniqNode = [0..shnNo) then nodes >= mynNo (what the fused receive assumes)
+  int pendRecvDof = 0;       // dof of the vector whose halo receive a sparmul left pending
+  unsigned int *d_ticket = nullptr;  // CTA ticket of the fused multi-dot kernel
   int nUniq = 0;             // unique shared nodes
   int *d_uniqNode = nullptr; // [nUniq]
   int *d_uniqPtr = nullptr;  // [nUniq+1] -> d_uniqSlot
@@ -132,6 +135,8 @@ struct Ctx {
   int *d_pairT = nullptr;       // [nPair] position of the transposed block (c,r)
   int nPair = 0;
   int4 *d_blkDesc = nullptr;    // [nnz] (block, list begin, list end, 0) in processing order
+  int4 *d_pairDesc = nullptr;   // [nnz] paired order: (r,c) / (c,r) adjacent, then diagonal blocks (row + 1 in .w)
+  int nPairDescOff = 0;         // entries of d_pairDesc that belong to off-diagonal pairs
 
   // ---- system ----
   int dof = 0;                // dof of the resident R/Val

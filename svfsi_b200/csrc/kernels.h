@@ -88,6 +88,33 @@ struct ColArgs {
 };
 void launch_p2p_allreduce(cudaStream_t st, const P2PDev &pd, const double *partial, int nblk, int k,
                           double *out, int seq, const ColArgs *col = nullptr);
+
+// ---- one kernel per Gram-Schmidt column: [halo receive] + multi-dot + block sums + [all-reduce] + [column]
+// The halo sum that FSILS_SPARMUL* ends with (L/SPARMUL.f:130 -> L/INCOMMU.f:91-151) only touches the
+// rows shared with other ranks; when the SpMV's result goes straight into inner products
+// (L/GMRES.f:328-339) the first CTAs of the multi-dot grid wait for the neighbours' flags, add what
+// arrived to THEIR rows and then take those rows' part of the inner products, while every other CTA
+// streams the interior rows at once.  The last CTA to finish sums the per-CTA partials, exchanges them
+// with the peers (stores into their mailboxes, rank-ordered sum: bit-identical on all ranks), and runs
+// the Givens / Hessenberg column step.  Replaces halo_recv_add + multidot + reduce/all-reduce(+column):
+// three launches and two rank synchronisations per column instead of five and two.
+struct HaloRecv {
+  int on;                 // 0: the vector is already halo-consistent
+  int nNbr, dof, seq;     // neighbours to wait for, dofs per node of w, halo sequence number
+  int shnNo, mynNo, nUniq;
+  const int *nbrRank, *uniqNode, *uniqPtr, *uniqSlot;
+};
+struct DotTail {
+  int nranks;             // > 1: all-reduce over the peers' mailboxes (pd), sequence number arSeq
+  P2PDev pd;
+  int arSeq;
+  double *out;            // [k] the reduced inner products
+  unsigned int *counter;  // CTA ticket (zero between launches)
+  ColArgs col;            // col.ctl == NULL: no column step
+};
+void launch_multidot_fused(cudaStream_t st, const double *U, size_t stride, double *w, size_t nOwned,
+                           int k, double *partial, const int *done, const HaloRecv &hr,
+                           const DotTail &tail);
 // single rank: out[j] = sum_b partial[j*nblk+b] and the column step, one kernel (k <= kArMax)
 void launch_reduce_column(cudaStream_t st, const double *partial, int nblk, int k, double *out,
                           const ColArgs &col);
@@ -220,6 +247,18 @@ void launch_fluid_gather_parts(cudaStream_t st, int parts, const FluidPar &par, 
 void launch_build_node_slots(cudaStream_t st, int nNo, const int *rowPtr, const int *nodeAdjPtr,
                              const int *nodeAdj, const int *edest, int *slots);
 int asm_tune();
+// second-generation gather assembly (asm_gather5.cu): 512-byte records v5 + four lanes per block with the
+// transposed blocks (r,c) / (c,r) in adjacent groups.  parts: 1 = records of elements [e0, e1), 2 = descriptor
+// entries [g0, g1) of `desc` (build_paired_desc); ringMask: the record of element e lives at slot
+// e & ringMask (~0u: one slot per element)
+void launch_fluid_gather5(cudaStream_t st, int parts, const FluidPar &par, int e0, int e1, int g0, int g1,
+                          const int *ien, const double *x, const double *Ag, const double *Yg, const double *Bf,
+                          double *recs, unsigned ringMask, const int4 *desc, const int *adj, double *R,
+                          double *Val, int *badJac, int knob);
+// descriptors (block, list begin, list end, row + 1 | 0) in the paired processing order: all (r,c) / (c,r)
+// pairs first (adjacent entries), then the diagonal blocks and any block without a transposed partner
+int build_paired_desc(cudaStream_t st, int nPair, const int *pairList, const int *pairT, const int *adjPtr,
+                      const int *rowOf, int nnz, int4 **desc, int *nOffEntries);
 // adjacency lists for the gather variant (built once at gpu_mesh_create_)
 int build_gather_adjacency(cudaStream_t st, int nEl, int nNo, int nnz, const int *ien,
                            const int *edest, int **blkAdjPtr, int **blkAdj, int **nodeAdjPtr,

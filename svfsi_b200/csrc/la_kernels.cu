@@ -940,6 +940,229 @@ __global__ void reduce_partials_kernel(const double *__restrict__ partial, int n
   }
 }
 
+// ---------------------------------------------------------------------------
+// The fused column kernel (see kernels.h: HaloRecv / DotTail).
+//   CTAs [0, nRecv): wait for the neighbours' halo flags, add the received contributions to the shared rows of
+//     w (ascending neighbour order per node, L/INCOMMU.f:91-96), then take the inner products over THEIR chunk
+//     of the rows shared with lower ranks [0, shnNo) -- rows >= mynNo are not owned and do not enter the dots.
+//   CTAs [nRecv, grid): inner products over the interior rows [shnNo, mynNo), grid-stride.
+//   last CTA (ticket): block sums, peer all-reduce, Givens column.
+template <int JT>
+__device__ __forceinline__ void mdf_tile(const double *U, size_t stride, const double *w,
+                                         size_t lo, size_t hi, unsigned crank, unsigned ccount, int j0,
+                                         double *__restrict__ partial, double *smem) {
+  double acc[JT];
+#pragma unroll
+  for (int jj = 0; jj < JT; jj++) acc[jj] = 0.0;
+  if (hi > lo) {
+    const size_t lo2 = lo + (lo & 1);                 // vector body on 16-byte aligned pairs
+    const size_t np = hi > lo2 ? (hi - lo2) >> 1 : 0;
+    const double2 *w2 = (const double2 *)(w + lo2);
+    // narrow tiles carry few loads per trip: unroll so that >= 8 loads are in flight per thread
+    constexpr int UNR = JT >= 4 ? 1 : (JT >= 2 ? 2 : 4);
+    const size_t step = (size_t)ccount * blockDim.x;
+    size_t e = (size_t)crank * blockDim.x + threadIdx.x;
+    for (; e + (UNR - 1) * step < np; e += UNR * step) {
+      double2 wv[UNR], uv[UNR][JT];
+#pragma unroll
+      for (int r = 0; r < UNR; r++) {
+        wv[r] = w2[e + r * step];   // plain load: this CTA may have just written these rows (halo receive)
+#pragma unroll
+        for (int jj = 0; jj < JT; jj++)
+          uv[r][jj] = __ldcs((const double2 *)(U + (size_t)(j0 + jj) * stride + lo2) + e + r * step);
+      }
+#pragma unroll
+      for (int r = 0; r < UNR; r++)
+#pragma unroll
+        for (int jj = 0; jj < JT; jj++) {
+          acc[jj] = fma(uv[r][jj].x, wv[r].x, acc[jj]);
+          acc[jj] = fma(uv[r][jj].y, wv[r].y, acc[jj]);
+        }
+    }
+    for (; e < np; e += step) {
+      const double2 wv = w2[e];
+#pragma unroll
+      for (int jj = 0; jj < JT; jj++) {
+        const double2 uv = __ldcs((const double2 *)(U + (size_t)(j0 + jj) * stride + lo2) + e);
+        acc[jj] = fma(uv.x, wv.x, acc[jj]);
+        acc[jj] = fma(uv.y, wv.y, acc[jj]);
+      }
+    }
+    if (crank == 0 && threadIdx.x == 0) {             // unpaired first / last element of the range
+      if (lo & 1) {
+        const double wv = w[lo];
+#pragma unroll
+        for (int jj = 0; jj < JT; jj++) acc[jj] = fma(U[(size_t)(j0 + jj) * stride + lo], wv, acc[jj]);
+      }
+      if (lo2 + 2 * np < hi) {
+        const double wv = w[hi - 1];
+#pragma unroll
+        for (int jj = 0; jj < JT; jj++) acc[jj] = fma(U[(size_t)(j0 + jj) * stride + hi - 1], wv, acc[jj]);
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int jj = 0; jj < JT; jj++) {
+    double v = warp_sum(acc[jj]);
+    if (lane == 0) smem[wid * JT + jj] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < JT) {
+    double v = 0.0;
+    for (int wq = 0; wq < kDotThreads / 32; wq++) v += smem[wq * JT + threadIdx.x];
+    partial[(size_t)(j0 + threadIdx.x) * gridDim.x + blockIdx.x] = v;
+  }
+  __syncthreads();
+}
+
+// (U is not __restrict__: in the Arnoldi loop U_{k-1} IS w, and the receive CTAs write w before reading it)
+template <int MINB>
+__global__ void __launch_bounds__(kDotThreads, MINB) multidot_fused_kernel(const double *U, size_t stride,
+                                                                     double *w, size_t nOwned, int k,
+                                                                     double *partial, const int *done,
+                                                                     HaloRecv hr, DotTail tail, int nRecv) {
+  __shared__ double smem[(kDotThreads / 32) * 8];
+  __shared__ double sh[kArMax], sc[kArMax], ss[kArMax], sv[kArMax];
+  __shared__ bool last;
+  const bool skip = (done != nullptr && *(volatile const int *)done != 0);
+  size_t lo, hi;
+  unsigned crank, ccount;
+  if ((int)blockIdx.x < nRecv) {
+    // ---- halo receive for this CTA's share of the shared rows (the flag protocol runs even when `skip`)
+    const int slot = hr.seq & 1;
+    const P2PDev &pd = tail.pd;
+    if ((int)threadIdx.x < hr.nNbr)
+      wait_flag_sys(flag_ptr(pd.peer[pd.rank], slot, hr.nbrRank[threadIdx.x]), hr.seq, pd);
+    __syncthreads();
+    const double *rbuf = (const double *)(pd.peer[pd.rank] + pd.offHalo) + (size_t)slot * pd.haloCap;
+    const int dof = hr.dof;
+    // rows [0, shnNo) are the first shnNo unique shared nodes, in order: contiguous chunks of them per CTA
+    const size_t L = (size_t)hr.shnNo * dof;
+    size_t chunk = (L + nRecv - 1) / nRecv;
+    chunk += chunk & 1;
+    lo = (size_t)blockIdx.x * chunk;
+    hi = lo + chunk;
+    if (lo > L) lo = L;
+    if (hi > L) hi = L;
+    if (!skip) {
+      for (size_t t = lo + threadIdx.x; t < hi; t += blockDim.x) {
+        const int u = (int)(t / dof), d = (int)(t - (size_t)u * dof);
+        double v = w[t];
+        for (int q = hr.uniqPtr[u]; q < hr.uniqPtr[u + 1]; q++) v = v + __ldcv(rbuf + (size_t)hr.uniqSlot[q] * dof + d);
+        w[t] = v;
+      }
+      // rows shared with higher ranks [mynNo, nNo): not owned, no inner product -- spread over the receive CTAs
+      const size_t H = (size_t)(hr.nUniq - hr.shnNo) * dof;
+      for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < H; t += (size_t)nRecv * blockDim.x) {
+        const int u = hr.shnNo + (int)(t / dof), d = (int)(t % dof);
+        const size_t at = (size_t)hr.uniqNode[u] * dof + d;
+        double v = w[at];
+        for (int q = hr.uniqPtr[u]; q < hr.uniqPtr[u + 1]; q++) v = v + __ldcv(rbuf + (size_t)hr.uniqSlot[q] * dof + d);
+        w[at] = v;
+      }
+    }
+    __syncthreads();
+    if (hi > nOwned) hi = nOwned;
+    if (lo > hi) lo = hi;
+    crank = 0; ccount = 1;
+  } else {
+    lo = hr.on ? (size_t)hr.shnNo * hr.dof : 0;
+    if (lo > nOwned) lo = nOwned;
+    hi = nOwned;
+    crank = blockIdx.x - nRecv; ccount = gridDim.x - nRecv;
+  }
+  if (!skip) {
+    // k vectors in ceil(k / 8) passes of (nearly) equal width: 9 = 5 + 4, not 8 + 1 (a one-vector pass runs at
+    // half the bandwidth of a wide one)
+    const int nt = (k + 7) / 8;
+    int j0 = 0;
+    for (int t = 0; t < nt; t++) {
+      const int jt = (k - j0 + (nt - t) - 1) / (nt - t);
+      switch (jt) {
+        case 8: mdf_tile<8>(U, stride, w, lo, hi, crank, ccount, j0, partial, smem); break;
+        case 7: mdf_tile<7>(U, stride, w, lo, hi, crank, ccount, j0, partial, smem); break;
+        case 6: mdf_tile<6>(U, stride, w, lo, hi, crank, ccount, j0, partial, smem); break;
+        case 5: mdf_tile<5>(U, stride, w, lo, hi, crank, ccount, j0, partial, smem); break;
+        case 4: mdf_tile<4>(U, stride, w, lo, hi, crank, ccount, j0, partial, smem); break;
+        case 3: mdf_tile<3>(U, stride, w, lo, hi, crank, ccount, j0, partial, smem); break;
+        case 2: mdf_tile<2>(U, stride, w, lo, hi, crank, ccount, j0, partial, smem); break;
+        default: mdf_tile<1>(U, stride, w, lo, hi, crank, ccount, j0, partial, smem); break;
+      }
+      j0 += jt;
+    }
+  }
+  // ---- ticket: the last CTA to arrive owns the tail
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(tail.counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  if (threadIdx.x == 0) *tail.counter = 0;
+  __threadfence();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int nblk = gridDim.x;
+  for (int j = wid; j < k; j += nw) {
+    double v = 0.0;
+    if (!skip)
+      for (int b = lane; b < nblk; b += 32) v += __ldcg(partial + (size_t)j * nblk + b);
+    v = warp_sum(v);
+    if (lane == 0) sh[j] = v;
+  }
+  __syncthreads();
+  if (tail.nranks > 1) {
+    const P2PDev &pd = tail.pd;
+    const int slot = tail.arSeq & 1;
+    for (int p = 0; p < pd.nranks; p++) {
+      double *mb = (double *)(pd.peer[p] + pd.offMail) + ((size_t)slot * pd.nranks + pd.rank) * kArMax;
+      for (int j = threadIdx.x; j < k; j += blockDim.x) mb[j] = sh[j];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < pd.nranks) st_flag_sys(flag_ptr(pd.peer[threadIdx.x], 2 + slot, pd.rank), tail.arSeq);
+    if ((int)threadIdx.x < pd.nranks) wait_flag_sys(flag_ptr(pd.peer[pd.rank], 2 + slot, threadIdx.x), tail.arSeq, pd);
+    __syncthreads();
+    const double *mb = (const double *)(pd.peer[pd.rank] + pd.offMail) + (size_t)slot * pd.nranks * kArMax;
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+      double v = 0.0;
+      for (int r = 0; r < pd.nranks; r++) v += __ldcv(mb + (size_t)r * kArMax + j);
+      sh[j] = v;
+    }
+    __syncthreads();
+  }
+  for (int j = threadIdx.x; j < k; j += blockDim.x) tail.out[j] = sh[j];
+  if (tail.col.ctl) {
+    __syncthreads();
+    column_step_block(tail.col, sh, sc, ss, sv);
+  }
+}
+
+void launch_multidot_fused(cudaStream_t st, const double *U, size_t stride, double *w, size_t nOwned,
+                           int k, double *partial, const int *done, const HaloRecv &hr,
+                           const DotTail &tail) {
+  count_launch();
+  int nRecv = 0;
+  if (hr.on) {
+    const size_t ent = (size_t)hr.nUniq * hr.dof;
+    nRecv = (int)((ent + 2047) / 2048);           // ~8 entries per thread
+    if (nRecv < 1) nRecv = 1;
+    if (nRecv > 32) nRecv = 32;
+  }
+  // 88 registers: two CTAs per SM without spills (measured: 7.0 TB/s at k = 34; capped to 80 registers for three
+  // CTAs per SM it spills and drops to 5.1 TB/s, profiles/r02_dot_fused.md); ONE wave of 2 x 148 CTAs
+  static int minb = -1;
+  if (minb < 0) {
+    const char *e = getenv("SVFSI_DOT_MINB");
+    minb = e ? atoi(e) : 2;
+  }
+  if (minb == 3)
+    multidot_fused_kernel<3><<<kSMs * 3, kDotThreads, 0, st>>>(U, stride, w, nOwned, k, partial, done, hr,
+                                                               tail, nRecv);
+  else
+    multidot_fused_kernel<2><<<kSMs * 2, kDotThreads, 0, st>>>(U, stride, w, nOwned, k, partial, done, hr,
+                                                               tail, nRecv);
+}
+
 void launch_multidot(cudaStream_t st, const double *U, size_t stride, const double *w, size_t n,
                      int k, double *partial, const int *done) {
   if (k <= 0) return;

@@ -237,12 +237,8 @@ int bcpre(int nsd, double *sS) {
 
 // squared 2-norm / dot over owned entries -> *out (device), all-reduced
 int dot_dev(const double *U, const double *V, size_t nOwned, double *out, const int *done) {
-  Ctx &c = ctx();
-  {
-    ProfScope ps(PROF_DOT);
-    launch_multidot(c.stream, U, 0, V, nOwned, 1, c.d_partial, done);
-  }
-  return reduce_allreduce(c.d_partial, 1, out, done);
+  // one kernel: partial sums + block sums (+ peer all-reduce)
+  return multidot_column(U, 0, const_cast<double *>(V), nOwned, 1, out, nullptr, done, false);
 }
 
 double now_s() {
@@ -312,24 +308,26 @@ int arnoldi_cycle(int kind, int dof, const double *Val, double *u, size_t stride
   int seqPrev = -1;
   for (int i = 1; i <= sD; i++) {
     double *ui = u + (size_t)i * stride, *um = u + (size_t)(i - 1) * stride;
-    if (int rc = sparmul(kind, dof, Val, um, ui, done)) return rc;
+    // the SpMV's halo RECEIVE rides on the column kernel below (its first CTAs wait for the neighbours
+    // and add what arrived) unless something reads the whole of u(i+1) before: the BCOP_TYPE_PRE step
+    const bool preStep = (kind == 0) && pre && any_coupled();
+    bool pend = false;
+    if (int rc = sparmul(kind, dof, Val, um, ui, done, preStep ? nullptr : &pend)) return rc;
     if (kind == 0) {
+      // rank-one face term: reads u(i), adds to u(i+1) on the face nodes (sums commute with the receive)
       if (int rc = addbcmul(0, dof, um, ui, g.faceS, done)) return rc;
-      if (pre && any_coupled()) {
+      if (preStep) {
         launch_vecop(c.stream, VOP_COPY, unCondU, ui, nullptr, n, nullptr, 0.0, done);
         if (int rc = addbcmul(1, dof, unCondU, ui, g.faceS, done)) return rc;
       }
     }
-    {
-      ProfScope ps(PROF_DOT);
-      launch_multidot(c.stream, u, stride, ui, nOwned, i + 1, c.d_partial, done);
-    }
     const int seq = ++g_seq;
     {
-      // block sums + all-reduce + Givens column + stop test + flag publication: one kernel
+      // [halo receive] + multi-dot + block sums + all-reduce + Givens column + stop test + flag
+      // publication: one kernel
       ColArgs col{g.ctl, i, sD, g.h, g.cc, g.ss, g.err, g.coef, &g_hm_dev->flag[seq & 63],
                   &g_hm_dev->progress, seq};
-      if (int rc = reduce_allreduce_column(c.d_partial, i + 1, g.hcol, col, done)) return rc;
+      if (int rc = multidot_column(u, stride, ui, nOwned, i + 1, g.hcol, &col, done, pend)) return rc;
     }
     {
       ProfScope ps(PROF_AXPY);

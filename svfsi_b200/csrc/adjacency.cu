@@ -149,28 +149,29 @@ int build_block_desc(cudaStream_t st, int nnz, const int *blkOrder, const int *a
   return 0;
 }
 
-// paired descriptors: unit g of the pair list is an off-diagonal pair (two adjacent entries), a diagonal
-// block or a block without a partner (one entry after all pairs)
-__global__ void pdesc_flag_kernel(int nPair, const int *__restrict__ pairList, const int *__restrict__ pairT,
-                                  int *__restrict__ isOff) {
+// paired descriptors: unit g of the pair list (processing order: chunks of 512 blocks of neighbouring rows,
+// longest lists first) is an off-diagonal pair -> two ADJACENT entries (r,c), (c,r), or a diagonal block / a
+// block without a partner -> one entry.  Units keep the pair-list order, so the diagonal blocks of a row chunk
+// are processed next to its pairs and find the element records in L2 (putting all diagonal blocks after all
+// pairs doubled the DRAM reads of the gather kernel, profiles/r02_asm_gather5.md).
+__global__ void pdesc_size_kernel(int nPair, const int *__restrict__ pairList, const int *__restrict__ pairT,
+                                  int *__restrict__ size) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= nPair) return;
   const int p = pairList[g], pt = pairT[g];
-  isOff[g] = (pt >= 0 && pt != p) ? 1 : 0;
+  size[g] = (pt >= 0 && pt != p) ? 2 : 1;
 }
 __global__ void pdesc_fill_kernel(int nPair, const int *__restrict__ pairList, const int *__restrict__ pairT,
-                                  const int *__restrict__ isOff, const int *__restrict__ offPos, int nOff,
-                                  const int *__restrict__ adjPtr, const int *__restrict__ rowOf,
-                                  int4 *__restrict__ desc) {
+                                  const int *__restrict__ pos, const int *__restrict__ adjPtr,
+                                  const int *__restrict__ rowOf, int4 *__restrict__ desc) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= nPair) return;
   const int p = pairList[g], pt = pairT[g];
-  if (isOff[g]) {
-    const int at = 2 * offPos[g];
+  const int at = pos[g];
+  if (pt >= 0 && pt != p) {
     desc[at] = make_int4(p, adjPtr[p], adjPtr[p + 1], 0);
     desc[at + 1] = make_int4(pt, adjPtr[pt], adjPtr[pt + 1], 0);
   } else {
-    const int at = 2 * nOff + (g - offPos[g]);
     desc[at] = make_int4(p, adjPtr[p], adjPtr[p + 1], pt == p ? rowOf[p] + 1 : 0);
   }
 }
@@ -179,27 +180,27 @@ int build_paired_desc(cudaStream_t st, int nPair, const int *pairList, const int
   *desc = nullptr;
   *nOffEntries = 0;
   if (nPair <= 0) return 0;
-  int *isOff = nullptr, *pos = nullptr;
-  CUDA_TRY(cudaMalloc(&isOff, sizeof(int) * (size_t)nPair));
+  int *size = nullptr, *pos = nullptr;
+  CUDA_TRY(cudaMalloc(&size, sizeof(int) * (size_t)nPair));
   CUDA_TRY(cudaMalloc(&pos, sizeof(int) * (size_t)nPair));
   const unsigned blocks = (unsigned)((nPair + 255) / 256);
-  pdesc_flag_kernel<<<blocks, 256, 0, st>>>(nPair, pairList, pairT, isOff);
-  thrust::exclusive_scan(thrust::cuda::par.on(st), isOff, isOff + nPair, pos);
-  int lastPos = 0, lastFlag = 0;
+  pdesc_size_kernel<<<blocks, 256, 0, st>>>(nPair, pairList, pairT, size);
+  thrust::exclusive_scan(thrust::cuda::par.on(st), size, size + nPair, pos);
+  int lastPos = 0, lastSize = 0;
   CUDA_TRY(cudaMemcpyAsync(&lastPos, pos + nPair - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(&lastFlag, isOff + nPair - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(&lastSize, size + nPair - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
-  const int nOff = lastPos + lastFlag;
-  if (2 * nOff + (nPair - nOff) != nnz) {   // a (c,r) block with c < r whose partner is missing was dropped
-    cudaFree(isOff); cudaFree(pos);
-    return 0;                               // caller falls back to the unpaired kernels
+  const int total = lastPos + lastSize;
+  if (total != nnz) {   // a block (c,r), c < r, whose partner is missing was dropped from the pair list
+    cudaFree(size); cudaFree(pos);
+    return 0;           // caller falls back to the unpaired kernels
   }
   CUDA_TRY(cudaMalloc(desc, sizeof(int4) * (size_t)nnz));
-  pdesc_fill_kernel<<<blocks, 256, 0, st>>>(nPair, pairList, pairT, isOff, pos, nOff, adjPtr, rowOf, *desc);
+  pdesc_fill_kernel<<<blocks, 256, 0, st>>>(nPair, pairList, pairT, pos, adjPtr, rowOf, *desc);
   count_launch(3);
   CUDA_TRY(cudaStreamSynchronize(st));
-  cudaFree(isOff); cudaFree(pos);
-  *nOffEntries = 2 * nOff;
+  cudaFree(size); cudaFree(pos);
+  *nOffEntries = total - (2 * nPair - total);   // entries that belong to pairs: 2 * (total - nPair)
   return 0;
 }
 

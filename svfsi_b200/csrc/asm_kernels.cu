@@ -1059,6 +1059,9 @@ void launch_fluid_gather_parts(cudaStream_t st, int parts, const FluidPar &par, 
   if ((parts & 2) && (tune & 262144) && (double)nEl * F_COUNT < 4.0e9) {
     count_launch();
     const size_t lanes = (size_t)nnz * 4;
+    static int rowMajor = -1;   // experiment: plain row-major block order (no length sorting)
+    if (rowMajor < 0) { const char *e = getenv("SVFSI_ASM_ROWMAJOR"); rowMajor = e ? atoi(e) : 0; }
+    if (rowMajor) { blkOrder = nullptr; tune &= ~524288; }
 #define GQ(T, MB)                                                                              \
   do {                                                                                         \
     if ((tune & 524288) && pairs.desc)                                                         \

@@ -183,6 +183,10 @@ void launch_face_dot(cudaStream_t st, int nFaceNo, int fdof, int dof, const int 
 void launch_face_axpy(cudaStream_t st, int nFaceNo, int fdof, int dof, const int *glob,
                       const double *valM, double coef, const double *S, double *Y,
                       const int *done);
+// both in one launch (a face that lives on one rank: no all-reduce between the two)
+void launch_face_dot_axpy(cudaStream_t st, int nFaceNo, int fdof, int dof, const int *glob,
+                          const double *valM, const double *X, int ownedLimit, double coef, double *S,
+                          double *Y, const int *done);
 // nS = sum valM^2 over nodes with glob < ownedLimit
 void launch_face_norm2(cudaStream_t st, int nFaceNo, int fdof, int nsd, const int *glob,
                        const double *valM, int ownedLimit, double *S);

@@ -483,6 +483,141 @@ static bool use_flat() {
     if (kind == 2 && dof == 2) { CALL(2, 1, 16); return; }               \
   } while (0)
 
+// ---------------------------------------------------------------------------
+// "Row-chunk stream" SpMV for the small block shapes of NSSOLVER / CG (K 3x3, G 3x1, D 1x3, L 1x1, heat 1x1;
+// L/SPARMUL.f:135-297).  The lane-per-block kernel above reads a different 128-byte line per lane (blocks are
+// 72 / 24 / 8 bytes apart) and is bound by L1 wavefronts, not HBM (0.53-0.66 of the measured peak,
+// profiles/r01_spmv_shapes.md).  Here a CTA owns ROWS consecutive block rows -- whose values and column ids are
+// ONE contiguous run -- copies that run to shared memory with fully coalesced 128-bit loads (every byte of every
+// line used, tens of independent loads in flight per thread), then LPR = 256 / ROWS lanes per row walk the
+// blocks out of shared memory and gather U through L1 / L2.  Partial sums of a row meet by shuffles in a fixed
+// order (deterministic).  The fused variant (halo send, boundary rows first) is the same kernel.
+struct StreamMap {
+  int a0, a1, b0, b1, c0, c1;   // three contiguous row ranges (the last two may be empty)
+  int n0, n1;                   // CTAs of the first two ranges
+};
+template <int BR, int BC, int ROWS>
+__global__ void __launch_bounds__(256) spmv_stream_kernel(StreamMap mp, int fused, SpmvFuse f, int capB,
+                                                          const int *__restrict__ rowPtr,
+                                                          const int *__restrict__ col,
+                                                          const double *__restrict__ K,
+                                                          const double *__restrict__ U,
+                                                          double *__restrict__ KU, const int *done) {
+  constexpr int BB = BR * BC, LPR = 256 / ROWS;
+  extern __shared__ double2 sm2[];
+  double *sK = (double *)sm2;                       // [capB * BB + 2]
+  int *sCol = (int *)(sK + (size_t)capB * BB + 2);  // [capB]
+  int *sRp = sCol + capB;                           // [ROWS + 1]
+  const bool skip = (done != nullptr && *(volatile const int *)done != 0);
+  if (skip && !fused) return;
+  int rs, re;
+  {
+    const int b = blockIdx.x;
+    if (b < mp.n0) { rs = mp.a0 + b * ROWS; re = min(rs + ROWS, mp.a1); }
+    else if (b < mp.n0 + mp.n1) { rs = mp.b0 + (b - mp.n0) * ROWS; re = min(rs + ROWS, mp.b1); }
+    else { rs = mp.c0 + (b - mp.n0 - mp.n1) * ROWS; re = min(rs + ROWS, mp.c1); }
+  }
+  const int nr = re - rs;
+  if (!skip && nr > 0) {
+    for (int t = threadIdx.x; t <= nr; t += 256) sRp[t] = __ldg(rowPtr + rs + t);
+    __syncthreads();
+    const int b0 = sRp[0], nb = sRp[nr] - b0;
+    // values: K[b0*BB .. (b0+nb)*BB) mirrored in shared memory with the same 16-byte parity
+    const size_t g0 = (size_t)b0 * BB;
+    const int pad = (int)(g0 & 1), nd = nb * BB;
+    const int head = pad ? 1 : 0;
+    if (head && threadIdx.x == 0 && nd > 0) sK[pad] = __ldcs(K + g0);
+    const int np = (nd - head) >> 1;
+    const double2 *Kv = (const double2 *)(K + g0 + head);
+    double2 *sv = (double2 *)(sK + pad + head);
+    for (int t = threadIdx.x; t < np; t += 256) sv[t] = __ldcs(Kv + t);
+    if (threadIdx.x == 0 && head + 2 * np < nd) sK[pad + nd - 1] = __ldcs(K + g0 + nd - 1);
+    for (int t = threadIdx.x; t < nb; t += 256) sCol[t] = __ldg(col + b0 + t);
+    __syncthreads();
+    const int rl = threadIdx.x / LPR, q = threadIdx.x % LPR;
+    double acc[BR];
+#pragma unroll
+    for (int l = 0; l < BR; l++) acc[l] = 0.0;
+    if (rl < nr) {
+      const int js = sRp[rl] - b0, je = sRp[rl + 1] - b0;
+      for (int j = js + q; j < je; j += LPR) {
+        const int c = sCol[j];
+        const double *k = sK + pad + (size_t)j * BB;
+        double u[BC];
+#pragma unroll
+        for (int m = 0; m < BC; m++) u[m] = __ldg(U + (size_t)c * BC + m);
+#pragma unroll
+        for (int l = 0; l < BR; l++)
+#pragma unroll
+          for (int m = 0; m < BC; m++) acc[l] = fma(k[l * BC + m], u[m], acc[l]);
+      }
+    }
+#pragma unroll
+    for (int l = 0; l < BR; l++)
+#pragma unroll
+      for (int o = 1; o < LPR; o <<= 1) acc[l] += __shfl_xor_sync(0xffffffffu, acc[l], o);
+    if (rl < nr && q == 0) {
+      const int row = rs + rl;
+      int bidx = -1;
+      if (fused && (int)blockIdx.x < mp.n0 + mp.n1) bidx = row < f.shnNo ? row : f.shnNo + (row - f.mynNo);
+#pragma unroll
+      for (int l = 0; l < BR; l++) {
+        KU[(size_t)row * BR + l] = acc[l];
+        if (bidx >= 0) fuse_send(f, bidx, BR, l, acc[l]);
+      }
+    }
+  }
+  if (fused) fuse_publish(f);
+}
+
+static int spmv_stream_mode() {
+  static int v = -1;
+  if (v < 0) {
+    // MEASURED (profiles/r02_spmv_stream.md, 10M tets): NSSOLVER step 25.1 ms with it vs 24.2 ms without
+    // (SpMV mix at 0.585 vs 0.641 of the measured peak), heat CG 6.45 vs 6.47 ms: the staging pass costs
+    // what the coalescing gains.  Off by default; SVFSI_SPMV_STREAM=1 selects it (parity-tested both ways).
+    const char *e = getenv("SVFSI_SPMV_STREAM");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+// returns false if the shape / row lengths do not fit (caller falls back to the lane-per-block kernel)
+template <int BR, int BC, int ROWS>
+static bool launch_stream(cudaStream_t st, StreamMap mp, int fused, SpmvFuse f, const int *rowPtr,
+                          const int *col, const double *K, const double *U, double *KU, const int *done) {
+  const int maxRow = ctx().maxRowLen;
+  if (maxRow <= 0) return false;
+  const int capB = ROWS * maxRow;
+  const size_t smem = sizeof(double) * ((size_t)capB * BR * BC + 2) + sizeof(int) * ((size_t)capB + ROWS + 1);
+  if (smem > 100 * 1024) return false;
+  static size_t attrSet = 0;
+  if (smem > attrSet) {
+    cudaFuncSetAttribute(spmv_stream_kernel<BR, BC, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attrSet = smem;
+  }
+  mp.n0 = (mp.a1 - mp.a0 + ROWS - 1) / ROWS;
+  mp.n1 = (mp.b1 - mp.b0 + ROWS - 1) / ROWS;
+  const int n2 = (mp.c1 - mp.c0 + ROWS - 1) / ROWS;
+  f.bndCtas = mp.n0 + mp.n1;
+  const int blocks = mp.n0 + mp.n1 + n2;
+  if (blocks <= 0) return true;
+  spmv_stream_kernel<BR, BC, ROWS><<<blocks, 256, smem, st>>>(mp, fused, f, capB, rowPtr, col, K, U, KU, done);
+  return true;
+}
+static bool stream_dispatch(cudaStream_t st, int kind, int dof, StreamMap mp, int fused, const SpmvFuse &f,
+                            const int *rowPtr, const int *col, const double *K, const double *U, double *KU,
+                            const int *done) {
+  if (!spmv_stream_mode()) return false;
+#define STR(BR, BC, ROWS) return launch_stream<BR, BC, ROWS>(st, mp, fused, f, rowPtr, col, K, U, KU, done)
+  if (kind == 3 || dof == 1) STR(1, 1, 128);
+  if (kind == 0) { if (dof == 2) STR(2, 2, 64); if (dof == 3) STR(3, 3, 32); return false; }
+  if (kind == 1) { if (dof == 2) STR(1, 2, 64); if (dof == 3) STR(1, 3, 64); STR(1, 4, 64); }
+  if (dof == 2) STR(2, 1, 64);
+  if (dof == 3) STR(3, 1, 64);
+  STR(4, 1, 64);
+#undef STR
+}
+
 template <int BR, int BC>
 static void launch_generic(cudaStream_t st, int r0, int r1, int r2, int r3, const int *rowPtr,
                            const int *col, const double *K, const double *U, double *KU,
@@ -544,6 +679,12 @@ void launch_spmv2(cudaStream_t st, int kind, int dof, int r0, int r1, int r2, in
     FLAT_DISPATCH(FL);
 #undef FL
   }
+  {
+    StreamMap mp{r0, r1, r2, r3, 0, 0, 0, 0};
+    SpmvFuse none;
+    memset(&none, 0, sizeof(none));
+    if (stream_dispatch(st, kind, dof, mp, 0, none, rowPtr, col, K, U, KU, done)) return;
+  }
 #define GEN(BR, BC) launch_generic<BR, BC>(st, r0, r1, r2, r3, rowPtr, col, K, U, KU, done)
   if (kind == 3 || dof == 1) {
     GEN(1, 1);
@@ -574,6 +715,10 @@ void launch_spmv_fused(cudaStream_t st, int kind, int dof, SpmvFuse f, const int
 #define FLF(BR, BC, T) launch_flat_fused<BR, BC, T>(st, f, rowPtr, col, K, U, KU, done)
     FLAT_DISPATCH(FLF);
 #undef FLF
+  }
+  if (!vv4) {
+    StreamMap mp{0, f.shnNo, f.mynNo, f.nNo, f.shnNo, f.mynNo, 0, 0};
+    if (stream_dispatch(st, kind, dof, mp, 1, f, rowPtr, col, K, U, KU, done)) return;
   }
   const bool quad = vv4 && spmv_fused_quad();
   const int rpc = (vv4 && !quad) ? 32 : 64;
@@ -777,8 +922,7 @@ __device__ void column_step_block(const ColArgs &a, double *sh, double *sc, doub
   if (threadIdx.x == 0 && a.pubFlag) {
     *a.pubFlag = a.ctl->done;
     __threadfence_system();
-    *a.pubProgress = a.seq;
-    __threadfence_system();
+    *a.pubProgress = a.seq;   // (the kernel ends here: its completion flushes the store)
   }
 }
 
@@ -1475,6 +1619,45 @@ __global__ void __launch_bounds__(1024) face_dot_kernel(int nFaceNo, int fdof, i
     *S = t;
   }
 }
+// ADDBCMUL for a face that lives on one rank: S = valM . X and Y += coef S valM in ONE launch (single CTA:
+// a face has O(10^3..10^4) nodes)
+__global__ void __launch_bounds__(1024) face_dot_axpy_kernel(int nFaceNo, int fdof, int dof,
+                                                             const int *__restrict__ glob,
+                                                             const double *__restrict__ valM,
+                                                             const double *__restrict__ X, int ownedLimit,
+                                                             double coef, double *__restrict__ S,
+                                                             double *__restrict__ Y, const int *done) {
+  DONE_GUARD(done);
+  __shared__ double smem[32];
+  __shared__ double tot;
+  const int m = fdof < dof ? fdof : dof;
+  double v = 0.0;
+  for (int a = threadIdx.x; a < nFaceNo; a += blockDim.x) {
+    const int Ac = glob[a];
+    if (Ac >= ownedLimit) continue;
+    for (int i = 0; i < m; i++) v += valM[(size_t)a * fdof + i] * X[(size_t)Ac * dof + i];
+  }
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int wq = 0; wq < (int)(blockDim.x >> 5); wq++) t += smem[wq];
+    *S = t;
+    tot = t;
+  }
+  __syncthreads();
+  const double s = coef * tot;
+  for (int a = threadIdx.x; a < nFaceNo; a += blockDim.x)
+    for (int i = 0; i < m; i++) Y[(size_t)glob[a] * dof + i] += valM[(size_t)a * fdof + i] * s;
+}
+void launch_face_dot_axpy(cudaStream_t st, int nFaceNo, int fdof, int dof, const int *glob,
+                          const double *valM, const double *X, int ownedLimit, double coef, double *S,
+                          double *Y, const int *done) {
+  count_launch();
+  face_dot_axpy_kernel<<<1, 1024, 0, st>>>(nFaceNo, fdof, dof, glob, valM, X, ownedLimit, coef, S, Y, done);
+}
+
 __global__ void face_axpy_kernel(int nFaceNo, int fdof, int dof, const int *__restrict__ glob,
                                  const double *__restrict__ valM, double coef,
                                  const double *__restrict__ S, double *__restrict__ Y,

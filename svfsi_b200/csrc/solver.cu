@@ -198,7 +198,10 @@ int addbcmul(int op, int dof, const double *X, double *Y, double *sS, const int 
       launch_face_dot(c.stream, f.nNo, f.dof, dof, f.d_glob, f.d_valM, X, c.mynNo, S, done);
       if (int rc = allreduce_dev(S, 1)) return rc;
     } else {
-      launch_face_dot(c.stream, f.nNo, f.dof, dof, f.d_glob, f.d_valM, X, c.nNo, S, done);
+      // the face lives on one rank (L/ADDBCMUL.f:80-92, not sharedFlag): nothing to do elsewhere, one launch here
+      if (f.nNo > 0)
+        launch_face_dot_axpy(c.stream, f.nNo, f.dof, dof, f.d_glob, f.d_valM, X, c.nNo, coef, S, Y, done);
+      continue;
     }
     launch_face_axpy(c.stream, f.nNo, f.dof, dof, f.d_glob, f.d_valM, coef, S, Y, done);
   }
@@ -447,8 +450,10 @@ int cgrad(svfsi_subls_t *ls, int dof, const double *K, double *R) {
   launch_vecop(c.stream, VOP_ZERO, X, nullptr, nullptr, n, nullptr, 0.0, nullptr);
   int seqPrev = publish(ctl);
   for (int i = 1; i <= ls->mItr; i++) {
-    if (int rc = sparmul(kind, dof, K, P, KP, done)) return rc;
-    if (int rc = dot_dev(P, KP, nOwned, sc, done)) return rc;
+    // the halo receive of K P rides on the <P, K P> kernel (its first CTAs wait for the neighbours)
+    bool pend = false;
+    if (int rc = sparmul(kind, dof, K, P, KP, done, &pend)) return rc;
+    if (int rc = multidot_column(P, 0, KP, nOwned, 1, sc, nullptr, done, pend)) return rc;
     cg_alpha_kernel<<<1, 1, 0, c.stream>>>(ctl, sc);
     {
       ProfScope ps(PROF_AXPY);

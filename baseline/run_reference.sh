@@ -16,6 +16,16 @@ NP=${6:-$(nproc)}
 HERE=$(cd "$(dirname "$0")" && pwd)
 BUILD=${SVFSI_BUILD:-$CASE/build}
 
+# SVFSI_DUMP=1: build from a copy of the source with `CALL PDEBUGVALR()` inserted after COMMU(R) (S/MAIN.f:161), so
+# that every Newton iteration writes the assembled R / Val of each rank (S/DEBUG.f:122-176, file
+# Val_R_<cTS>_<itr>_<rank>).  Run with NP=1 and copy Val_R_1_1_0 to tests/golden/ref_Val_R_${NX}x${NY}x${NZ}_1_1_0:
+# tests/test_reference_dumps.py then pins the oracle and the CUDA path to the real svFSI.
+if [ "${SVFSI_DUMP:-0}" = "1" ]; then
+  cp -r "$SRC" "$CASE/src_dump"
+  SRC="$CASE/src_dump"
+  sed -i 's/^\(\s*\)CALL COMMU(R)\s*$/&\n\1CALL PDEBUGVALR()/' "$SRC/Code/Source/svFSI/MAIN.f"
+  BUILD="$CASE/build_dump"
+fi
 if [ ! -x "$BUILD/svFSI-build/bin/svFSI" ]; then
   mkdir -p "$BUILD"
   (cd "$BUILD" && cmake "$SRC" -DCMAKE_BUILD_TYPE=Release && make -j"$NP")

@@ -23,7 +23,8 @@ BUILD=${SVFSI_BUILD:-$CASE/build}
 if [ "${SVFSI_DUMP:-0}" = "1" ]; then
   cp -r "$SRC" "$CASE/src_dump"
   SRC="$CASE/src_dump"
-  sed -i 's/^\(\s*\)CALL COMMU(R)\s*$/&\n\1CALL PDEBUGVALR()/' "$SRC/Code/Source/svFSI/MAIN.f"
+  # S/MAIN.f:161 reads "IF (.NOT.eq(cEq)%assmTLS) CALL COMMU(R)"
+  sed -i '/CALL COMMU(R)/a\            CALL PDEBUGVALR()' "$SRC/Code/Source/svFSI/MAIN.f"
   BUILD="$CASE/build_dump"
 fi
 if [ ! -x "$BUILD/svFSI-build/bin/svFSI" ]; then

@@ -63,10 +63,7 @@ __global__ void bicgs_err_kernel(KrylovCtl *ctl, const double *d, int mItr, vola
       ctl->done = 1;
     }
   }
-  *pubFlag = ctl->done;
-  __threadfence_system();
-  *pubProgress = seq;
-  __threadfence_system();
+  *pubFlag = (seq << 1) | (ctl->done ? 1 : 0);
 }
 // S = R - alpha V
 __global__ void __launch_bounds__(256) bicgs_s_kernel(const KrylovCtl *ctl, double *__restrict__ S,

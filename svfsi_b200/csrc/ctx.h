@@ -148,6 +148,8 @@ struct Ctx {
   // device int words: [0] bad-Jacobian count (monotone since gpu_init_, never cleared so that a hit is
   // not lost before the host has seen it), [1] scratch of the setup checks, [2] sticky "peer flag wait
   // timed out"
+  // PRECONDDIAG's scaling of Val left to the first FSILS_SPARMULVV of the solve (fused kernel); W of that scaling
+  const double *valScaleW = nullptr;
   int *d_flag = nullptr;
   // mapped pinned host words the device (or an async copy) writes and the host reads at its next
   // synchronisation point without another copy: [0] comm time-out, [1] copy of d_flag[0]

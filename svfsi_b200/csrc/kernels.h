@@ -38,6 +38,10 @@ void launch_spmv2(cudaStream_t st, int kind, int dof, int r0, int r1, int r2, in
                   const int *rowPtr, const int *col, const double *K, const double *U, double *KU,
                   const int *done);
 
+// K <- (W_row K) W_col and KU = K U in one pass over Val (dof = 4, single rank): the first product of a solve
+void launch_spmv_vv4_scale(cudaStream_t st, int nNo, const int *rowPtr, const int *col, double *K,
+                           const double *W, const double *U, double *KU);
+
 // ---------------- halo (L/INCOMMU.f) ----------------
 void launch_pack(cudaStream_t st, int dof, int nShared, const int *packIdx, const double *R,
                  double *sbuf, const int *done);

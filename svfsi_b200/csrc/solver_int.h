@@ -4,8 +4,9 @@
 
 namespace svfsi {
 
-// Mapped pinned words written by the device.  Every Krylov iteration ends with a publish kernel
-// that stores the stop flag AS OF THAT ITERATION in flag[seq & 63] and then advances `progress`.
+// Mapped pinned words written by the device.  Every Krylov iteration ends with a publish step that
+// stores (sequence number << 1 | stop flag AS OF THAT ITERATION) in flag[seq & 63] -- one word, one
+// store, no system-scope fence on the device side (`progress` is no longer written).
 // The host enqueues iteration i, then waits for the flag of iteration i-1: it never idles the
 // GPU, and -- because the flag is a function of all-reduced scalars only -- every rank reads the
 // same value for the same iteration and so enqueues the same number of NCCL operations.

@@ -214,6 +214,9 @@ int32_t gpu_init_(const int32_t *device, const int32_t *rank, const int32_t *nra
   c.nranks = *nranks;
   CUDA_TRY(cudaSetDevice(c.device));
   CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&c.stream2, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&c.evFork, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&c.evJoin, cudaEventDisableTiming));
   if (int rc = status_words_init()) return rc;
   if (c.nranks > 1) {
     if (!uid128) return fail(SVFSI_ERR_ARG, "nranks > 1 needs the NCCL unique id");
@@ -267,6 +270,7 @@ int32_t gpu_lhs_free_(void) {
 int32_t gpu_finalize_(void) {
   Ctx &c = ctx();
   if (!c.inited) return 0;
+  trace_dump();
   gpu_lhs_free_();
   dev_free(&c.d_ws); c.wsBytes = 0;
   dev_free(&c.d_stage); c.stageBytes = 0;
@@ -281,6 +285,11 @@ int32_t gpu_finalize_(void) {
   nccl_destroy();
   if (c.stream) cudaStreamDestroy(c.stream);
   c.stream = nullptr;
+  if (c.stream2) cudaStreamDestroy(c.stream2);
+  c.stream2 = nullptr;
+  if (c.evFork) cudaEventDestroy(c.evFork);
+  if (c.evJoin) cudaEventDestroy(c.evJoin);
+  c.evFork = c.evJoin = nullptr;
   c.inited = false;
   return 0;
 }

@@ -451,6 +451,40 @@ int host_allgather_i32(const int32_t *send, int32_t n, int32_t *recv) {
 int row_dof(int kind, int dof) { return (kind == 0 || kind == 2) ? dof : 1; }
 int col_dof(int kind, int dof) { return (kind == 0 || kind == 1) ? dof : 1; }
 
+static constexpr int kTraceCols = 4096;
+static unsigned long long *trace_slot(bool advance) {
+  Ctx &c = ctx();
+  static int on = -1;
+  if (on < 0) on = getenv("SVFSI_TRACE_FILE") ? 1 : 0;
+  if (!on) return nullptr;
+  if (!c.d_trace) {
+    if (cudaMalloc((void **)&c.d_trace, sizeof(unsigned long long) * 8 * kTraceCols) != cudaSuccess) return nullptr;
+    cudaMemset(c.d_trace, 0, sizeof(unsigned long long) * 8 * kTraceCols);
+  }
+  unsigned long long *p = c.d_trace + (size_t)(c.traceCol % kTraceCols) * 8;
+  if (advance) c.traceCol++;
+  return p;
+}
+void trace_dump() {
+  Ctx &c = ctx();
+  const char *path = getenv("SVFSI_TRACE_FILE");
+  if (!c.d_trace || !path) return;
+  std::vector<unsigned long long> h((size_t)8 * kTraceCols);
+  cudaMemcpy(h.data(), c.d_trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  const std::string fn = std::string(path) + "." + std::to_string(c.rank);
+  if (FILE *fh = fopen(fn.c_str(), "w")) {
+    const int n = c.traceCol < kTraceCols ? c.traceCol : kTraceCols;
+    for (int i = 0; i < n; i++) {
+      for (int j = 0; j < 8; j++) fprintf(fh, "%llu ", h[(size_t)i * 8 + j]);
+      fprintf(fh, "\n");
+    }
+    fclose(fh);
+  }
+  cudaFree(c.d_trace);
+  c.d_trace = nullptr;
+  c.traceCol = 0;
+}
+
 int multidot_column(const double *U, size_t stride, double *w, size_t nOwned, int k, double *out,
                     const ColArgs *col, const int *done, bool recvPending) {
   Ctx &c = ctx();
@@ -484,6 +518,7 @@ int multidot_column(const double *U, size_t stride, double *w, size_t nOwned, in
     tail.out = out;
     tail.counter = c.d_ticket;
     if (col) tail.col = *col;
+    tail.trace = col ? trace_slot(true) : nullptr;   // Gram-Schmidt columns only
     ProfScope ps(PROF_DOT);
     launch_multidot_fused(c.stream, U, stride, w, nOwned, k, c.d_partial, done, hr, tail);
     return 0;
@@ -522,6 +557,7 @@ int sparmul(int kind, int dof, const double *K, const double *U, double *KU, con
       f.sendPtr = c.p2p.d_sendPtr; f.sendRank = c.p2p.d_sendRank; f.sendOff = c.p2p.d_sendOff;
       f.nbrRank = c.p2p.d_nbrRank; f.nNbr = (int)c.nbr.size();
       f.pd = p2p_dev(); f.seq = c.p2p.haloSeq; f.counter = c.p2p.d_counter;
+      f.trace = deferRecv ? trace_slot(false) : nullptr;   // the SpMV of the column the next column kernel closes
       launch_spmv_fused(c.stream, kind, dof, f, c.d_rowPtr, c.d_col, K, U, KU, done);
     }
     if (deferRecv && c.uniqOrdered) {   // the next multidot_column on KU receives

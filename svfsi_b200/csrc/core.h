@@ -42,6 +42,7 @@ int host_allgather_i32(const int32_t *send, int32_t n, int32_t *recv);
 // multidot_column(..., recvPending = *deferRecv) on KU (set to true when it was deferred)
 int sparmul(int kind, int dof, const double *K, const double *U, double *KU, const int *done,
             bool *deferRecv = nullptr);
+void trace_dump();                 // SVFSI_TRACE_FILE: write the column time stamps (gpu_finalize_)
 int flush_val_scale();            // apply PRECONDDIAG's scaling of Val if it is still pending
 int row_dof(int kind, int dof);  // dof of KU
 int col_dof(int kind, int dof);  // dof of U

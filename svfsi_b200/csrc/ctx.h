@@ -80,6 +80,9 @@ struct Ctx {
   bool inited = false;
   int device = 0, rank = 0, nranks = 1;
   cudaStream_t stream = nullptr;
+  // side stream + events: small kernels that only need the INPUT of the running SpMV (face dots of ADDBCMUL)
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t evFork = nullptr, evJoin = nullptr;
   void *nccl = nullptr;  // ncclComm_t
   svfsi_allgather_i32_fn host_allgather = nullptr;
   void *host_allgather_ctx = nullptr;
@@ -104,6 +107,10 @@ struct Ctx {
   // halo
   int nShared = 0;           // total entries in pack buffers (sum of nbr.n)
   int *d_packIdx = nullptr;  // [nShared] node id per pack slot
+  // SVFSI_TRACE_FILE=<path>: device time stamps (globaltimer ns) of the column kernels, 8 per column, written
+  // to <path>.<rank> at gpu_finalize_ (tools/trace_columns.py reads them)
+  unsigned long long *d_trace = nullptr;
+  int traceCol = 0;
   bool uniqOrdered = false;  // uniqNode = [0..shnNo) then nodes >= mynNo (what the fused receive assumes)
   int pendRecvDof = 0;       // dof of the vector whose halo receive a sparmul left pending
   unsigned int *d_ticket = nullptr;  // CTA ticket of the fused multi-dot kernel

@@ -70,6 +70,7 @@ struct SpmvFuse {
   P2PDev pd;
   int seq;
   unsigned int *counter;
+  unsigned long long *trace;   // SVFSI_TRACE_FILE: 8 time stamps of this column (NULL: off)
 };
 void launch_spmv_fused(cudaStream_t st, int kind, int dof, SpmvFuse f, const int *rowPtr,
                        const int *col, const double *K, const double *U, double *KU,
@@ -115,6 +116,7 @@ struct DotTail {
   double *out;            // [k] the reduced inner products
   unsigned int *counter;  // CTA ticket (zero between launches)
   ColArgs col;            // col.ctl == NULL: no column step
+  unsigned long long *trace;   // SVFSI_TRACE_FILE: 8 time stamps of this column (NULL: off)
 };
 void launch_multidot_fused(cudaStream_t st, const double *U, size_t stride, double *w, size_t nOwned,
                            int k, double *partial, const int *done, const HaloRecv &hr,
@@ -187,10 +189,12 @@ void launch_face_dot(cudaStream_t st, int nFaceNo, int fdof, int dof, const int 
 void launch_face_axpy(cudaStream_t st, int nFaceNo, int fdof, int dof, const int *glob,
                       const double *valM, double coef, const double *S, double *Y,
                       const int *done);
-// both in one launch (a face that lives on one rank: no all-reduce between the two)
-void launch_face_dot_axpy(cudaStream_t st, int nFaceNo, int fdof, int dof, const int *glob,
-                          const double *valM, const double *X, int ownedLimit, double coef, double *S,
-                          double *Y, const int *done);
+// a face that lives on one rank (no all-reduce between the dot and the update): both spread over 32 CTAs;
+// partial = 32 doubles of scratch
+void launch_face_dotp(cudaStream_t st, int nFaceNo, int fdof, int dof, const int *glob, const double *valM,
+                      const double *X, int ownedLimit, double *partial, const int *done);
+void launch_face_axpyp(cudaStream_t st, int nFaceNo, int fdof, int dof, const int *glob, const double *valM,
+                       double coef, const double *partial, double *S, double *Y, const int *done);
 // nS = sum valM^2 over nodes with glob < ownedLimit
 void launch_face_norm2(cudaStream_t st, int nFaceNo, int fdof, int nsd, const int *glob,
                        const double *valM, int ownedLimit, double *S);

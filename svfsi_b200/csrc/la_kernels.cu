@@ -249,6 +249,7 @@ void launch_spmv_vv4_scale(cudaStream_t st, int nNo, const int *rowPtr, const in
 // kernel of the same exchange waits on it).
 __device__ __forceinline__ bool fuse_map_row(const SpmvFuse &f, int rowsPerCta, int grp, int &row,
                                              int &bidx) {
+  if (f.trace && blockIdx.x == 0 && threadIdx.x == 0) f.trace[5] = global_ns();   // SpMV kernel start
   if ((int)blockIdx.x < f.bndCtas) {
     bidx = blockIdx.x * rowsPerCta + grp;
     if (bidx >= f.nBnd) return false;
@@ -278,6 +279,7 @@ __device__ __forceinline__ void fuse_publish(const SpmvFuse &f) {
     if ((int)threadIdx.x < f.nNbr)
       st_flag_sys(flag_ptr(f.pd.peer[f.nbrRank[threadIdx.x]], f.seq & 1, f.pd.rank), f.seq);
     if (threadIdx.x == 0) *f.counter = 0;
+    if (threadIdx.x == 0 && f.trace) f.trace[6] = global_ns();   // halo of this SpMV published
   }
 }
 
@@ -1222,6 +1224,7 @@ __global__ void __launch_bounds__(kDotThreads, MINB) multidot_fused_kernel(const
   const bool skip = (done != nullptr && *(volatile const int *)done != 0);
   size_t lo, hi;
   unsigned crank, ccount;
+  if (tail.trace && blockIdx.x == 0 && threadIdx.x == 0) tail.trace[0] = global_ns();   // kernel start
   if ((int)blockIdx.x < nRecv) {
     // ---- halo receive for this CTA's share of the shared rows (the flag protocol runs even when `skip`)
     const int slot = hr.seq & 1;
@@ -1229,6 +1232,7 @@ __global__ void __launch_bounds__(kDotThreads, MINB) multidot_fused_kernel(const
     if ((int)threadIdx.x < hr.nNbr)
       wait_flag_sys(flag_ptr(pd.peer[pd.rank], slot, hr.nbrRank[threadIdx.x]), hr.seq, pd);
     __syncthreads();
+    if (tail.trace && blockIdx.x == 0 && threadIdx.x == 0) tail.trace[1] = global_ns();   // neighbours' halos in
     const double *rbuf = (const double *)(pd.peer[pd.rank] + pd.offHalo) + (size_t)slot * pd.haloCap;
     const int dof = hr.dof;
     // rows [0, shnNo) are the first shnNo unique shared nodes, in order: contiguous chunks of them per CTA
@@ -1294,12 +1298,21 @@ __global__ void __launch_bounds__(kDotThreads, MINB) multidot_fused_kernel(const
   if (!last) return;
   if (threadIdx.x == 0) *tail.counter = 0;
   __threadfence();
+  if (tail.trace && threadIdx.x == 0) tail.trace[2] = global_ns();   // every CTA of this rank has finished
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int nblk = gridDim.x;
+  // block sums: the loads of a row first (nblk <= 444: at most 14 per lane, all in flight), then the adds in a
+  // fixed order
   for (int j = wid; j < k; j += nw) {
+    double pv[14];
+#pragma unroll
+    for (int q = 0; q < 14; q++) {
+      const int b = lane + 32 * q;
+      pv[q] = (!skip && b < nblk) ? __ldcg(partial + (size_t)j * nblk + b) : 0.0;
+    }
     double v = 0.0;
-    if (!skip)
-      for (int b = lane; b < nblk; b += 32) v += __ldcg(partial + (size_t)j * nblk + b);
+#pragma unroll
+    for (int q = 0; q < 14; q++) v += pv[q];
     v = warp_sum(v);
     if (lane == 0) sh[j] = v;
   }
@@ -1314,8 +1327,10 @@ __global__ void __launch_bounds__(kDotThreads, MINB) multidot_fused_kernel(const
     __threadfence_system();
     __syncthreads();
     if ((int)threadIdx.x < pd.nranks) st_flag_sys(flag_ptr(pd.peer[threadIdx.x], 2 + slot, pd.rank), tail.arSeq);
+    if (tail.trace && threadIdx.x == 0) tail.trace[7] = global_ns();   // own contribution flagged to the peers
     if ((int)threadIdx.x < pd.nranks) wait_flag_sys(flag_ptr(pd.peer[pd.rank], 2 + slot, threadIdx.x), tail.arSeq, pd);
     __syncthreads();
+    if (tail.trace && threadIdx.x == 0) tail.trace[3] = global_ns();   // every peer's contribution has arrived
     const double *mb = (const double *)(pd.peer[pd.rank] + pd.offMail) + (size_t)slot * pd.nranks * kArMax;
     for (int j = threadIdx.x; j < k; j += blockDim.x) {
       double v = 0.0;
@@ -1329,6 +1344,7 @@ __global__ void __launch_bounds__(kDotThreads, MINB) multidot_fused_kernel(const
     __syncthreads();
     column_step_block(tail.col, sh, sc, ss, sv);
   }
+  if (tail.trace && threadIdx.x == 0) tail.trace[4] = global_ns();   // end of the column kernel
 }
 
 void launch_multidot_fused(cudaStream_t st, const double *U, size_t stride, double *w, size_t nOwned,
@@ -1669,43 +1685,74 @@ __global__ void __launch_bounds__(1024) face_dot_kernel(int nFaceNo, int fdof, i
     *S = t;
   }
 }
-// ADDBCMUL for a face that lives on one rank: S = valM . X and Y += coef S valM in ONE launch (single CTA:
-// a face has O(10^3..10^4) nodes)
-__global__ void __launch_bounds__(1024) face_dot_axpy_kernel(int nFaceNo, int fdof, int dof,
-                                                             const int *__restrict__ glob,
-                                                             const double *__restrict__ valM,
-                                                             const double *__restrict__ X, int ownedLimit,
-                                                             double coef, double *__restrict__ S,
-                                                             double *__restrict__ Y, const int *done) {
+// ADDBCMUL for a face that lives on one rank (L/ADDBCMUL.f:80-92): S = valM . X, then Y += coef S valM.  It sits
+// on the critical path of every Gram-Schmidt column of the rank that holds the face (the other ranks wait for it
+// in the all-reduce).  A single CTA is bound by ONE SM's L1 pipe -- the face nodes are ~13 KB apart in X, so every
+// lane of every load touches its own line: 23 us for 4225 nodes (ncu, profiles/r02_launches_10M.md) -- so the
+// face is spread over kFaceCtas CTAs: partial dots (fixed order inside a CTA), then every CTA of the update
+// kernel adds the kFaceCtas partials in the same fixed order and updates its share of the nodes.
+static constexpr int kFaceCtas = 32;
+__global__ void __launch_bounds__(256) face_dotp_kernel(int nFaceNo, int fdof, int dof,
+                                                        const int *__restrict__ glob,
+                                                        const double *__restrict__ valM,
+                                                        const double *__restrict__ X, int ownedLimit,
+                                                        double *__restrict__ partial, const int *done) {
   DONE_GUARD(done);
-  __shared__ double smem[32];
-  __shared__ double tot;
+  __shared__ double smem[8];
   const int m = fdof < dof ? fdof : dof;
+  const int chunk = (nFaceNo + gridDim.x - 1) / gridDim.x;
+  const int a0 = blockIdx.x * chunk, a1 = min(a0 + chunk, nFaceNo);
   double v = 0.0;
-  for (int a = threadIdx.x; a < nFaceNo; a += blockDim.x) {
-    const int Ac = glob[a];
+  for (int a = a0 + threadIdx.x; a < a1; a += blockDim.x) {
+    const int Ac = __ldg(glob + a);
     if (Ac >= ownedLimit) continue;
-    for (int i = 0; i < m; i++) v += valM[(size_t)a * fdof + i] * X[(size_t)Ac * dof + i];
+    for (int i = 0; i < m; i++) v += __ldg(valM + (size_t)a * fdof + i) * X[(size_t)Ac * dof + i];
   }
   v = warp_sum(v);
   if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = v;
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0.0;
-    for (int wq = 0; wq < (int)(blockDim.x >> 5); wq++) t += smem[wq];
-    *S = t;
-    tot = t;
+    for (int wq = 0; wq < 8; wq++) t += smem[wq];
+    partial[blockIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(256) face_axpyp_kernel(int nFaceNo, int fdof, int dof,
+                                                         const int *__restrict__ glob,
+                                                         const double *__restrict__ valM, double coef,
+                                                         const double *__restrict__ partial, double *__restrict__ S,
+                                                         double *__restrict__ Y, const int *done) {
+  DONE_GUARD(done);
+  __shared__ double tot;
+  if (threadIdx.x < 32) {
+    double t = ((int)threadIdx.x < (int)gridDim.x) ? partial[threadIdx.x] : 0.0;
+    t = warp_sum(t);          // the same fixed tree in every CTA
+    if (threadIdx.x == 0) {
+      tot = t;
+      if (blockIdx.x == 0) *S = t;
+    }
   }
   __syncthreads();
+  const int m = fdof < dof ? fdof : dof;
   const double s = coef * tot;
-  for (int a = threadIdx.x; a < nFaceNo; a += blockDim.x)
-    for (int i = 0; i < m; i++) Y[(size_t)glob[a] * dof + i] += valM[(size_t)a * fdof + i] * s;
+  const int chunk = (nFaceNo + gridDim.x - 1) / gridDim.x;
+  const int a0 = blockIdx.x * chunk, a1 = min(a0 + chunk, nFaceNo);
+  for (int a = a0 + threadIdx.x; a < a1; a += blockDim.x) {
+    const size_t at = (size_t)__ldg(glob + a) * dof;
+    for (int i = 0; i < m; i++) Y[at + i] += __ldg(valM + (size_t)a * fdof + i) * s;
+  }
 }
-void launch_face_dot_axpy(cudaStream_t st, int nFaceNo, int fdof, int dof, const int *glob,
-                          const double *valM, const double *X, int ownedLimit, double coef, double *S,
-                          double *Y, const int *done) {
+// partial: kFaceCtas doubles of scratch.  The two halves are separate launchers so that the dot (which only
+// needs X = u(i)) can run on a side stream under the SpMV that produces Y = u(i+1).
+void launch_face_dotp(cudaStream_t st, int nFaceNo, int fdof, int dof, const int *glob, const double *valM,
+                      const double *X, int ownedLimit, double *partial, const int *done) {
   count_launch();
-  face_dot_axpy_kernel<<<1, 1024, 0, st>>>(nFaceNo, fdof, dof, glob, valM, X, ownedLimit, coef, S, Y, done);
+  face_dotp_kernel<<<kFaceCtas, 256, 0, st>>>(nFaceNo, fdof, dof, glob, valM, X, ownedLimit, partial, done);
+}
+void launch_face_axpyp(cudaStream_t st, int nFaceNo, int fdof, int dof, const int *glob, const double *valM,
+                       double coef, const double *partial, double *S, double *Y, const int *done) {
+  count_launch();
+  face_axpyp_kernel<<<kFaceCtas, 256, 0, st>>>(nFaceNo, fdof, dof, glob, valM, coef, partial, S, Y, done);
 }
 
 __global__ void face_axpy_kernel(int nFaceNo, int fdof, int dof, const int *__restrict__ glob,

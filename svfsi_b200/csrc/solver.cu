@@ -182,8 +182,30 @@ bool any_coupled() {
 }
 
 // ADDBCMUL (L/ADDBCMUL.f:53-114).  sS = device scratch scalars (one per face).
-int addbcmul(int op, int dof, const double *X, double *Y, double *sS, const int *done) {
+// The dot half of ADDBCMUL(ADD) for the faces that live on this rank alone, on the SIDE stream: it only needs
+// X = u(i), so it runs under the SpMV that produces u(i+1); addbcmul(..., dotsDone = true) then joins and only
+// launches the updates.  Returns true if anything was forked.
+bool addbcmul_fork_dots(int dof, const double *X, const int *done) {
   Ctx &c = ctx();
+  bool any = false;
+  for (size_t fi = 0; fi < c.face.size(); fi++) {
+    Face &f = c.face[fi];
+    if (!f.created || !f.coupled || f.shared || f.nNo == 0) continue;
+    if (!any) {
+      cudaEventRecord(c.evFork, c.stream);          // u(i) is complete
+      cudaStreamWaitEvent(c.stream2, c.evFork, 0);
+      any = true;
+    }
+    launch_face_dotp(c.stream2, f.nNo, f.dof, dof, f.d_glob, f.d_valM, X, c.nNo,
+                     c.d_partial + c.partialDoubles - 64 * (fi + 1), done);
+  }
+  if (any) cudaEventRecord(c.evJoin, c.stream2);
+  return any;
+}
+
+int addbcmul(int op, int dof, const double *X, double *Y, double *sS, const int *done, bool dotsDone) {
+  Ctx &c = ctx();
+  if (dotsDone) cudaStreamWaitEvent(c.stream, c.evJoin, 0);
   for (size_t fi = 0; fi < c.face.size(); fi++) {
     Face &f = c.face[fi];
     if (!f.created || !f.coupled) continue;
@@ -194,8 +216,12 @@ int addbcmul(int op, int dof, const double *X, double *Y, double *sS, const int 
       if (int rc = allreduce_dev(S, 1)) return rc;
     } else {
       // the face lives on one rank (L/ADDBCMUL.f:80-92, not sharedFlag): nothing to do elsewhere, one launch here
-      if (f.nNo > 0)
-        launch_face_dot_axpy(c.stream, f.nNo, f.dof, dof, f.d_glob, f.d_valM, X, c.nNo, coef, S, Y, done);
+      if (f.nNo > 0) {   // scratch for the per-CTA partials: behind the multi-dot partials (never live together)
+        double *part = c.d_partial + c.partialDoubles - 64 * (fi + 1);
+        if (!(dotsDone && op == 0))
+          launch_face_dotp(c.stream, f.nNo, f.dof, dof, f.d_glob, f.d_valM, X, c.nNo, part, done);
+        launch_face_axpyp(c.stream, f.nNo, f.dof, dof, f.d_glob, f.d_valM, coef, part, S, Y, done);
+      }
       continue;
     }
     launch_face_axpy(c.stream, f.nNo, f.dof, dof, f.d_glob, f.d_valM, coef, S, Y, done);
@@ -310,10 +336,11 @@ int arnoldi_cycle(int kind, int dof, const double *Val, double *u, size_t stride
     // and add what arrived) unless something reads the whole of u(i+1) before: the BCOP_TYPE_PRE step
     const bool preStep = (kind == 0) && pre && any_coupled();
     bool pend = false;
+    const bool forked = (kind == 0) && addbcmul_fork_dots(dof, um, done);   // valM . u(i) under the SpMV
     if (int rc = sparmul(kind, dof, Val, um, ui, done, preStep ? nullptr : &pend)) return rc;
     if (kind == 0) {
       // rank-one face term: reads u(i), adds to u(i+1) on the face nodes (sums commute with the receive)
-      if (int rc = addbcmul(0, dof, um, ui, g.faceS, done)) return rc;
+      if (int rc = addbcmul(0, dof, um, ui, g.faceS, done, forked)) return rc;
       if (preStep) {
         launch_vecop(c.stream, VOP_COPY, unCondU, ui, nullptr, n, nullptr, 0.0, done);
         if (int rc = addbcmul(1, dof, unCondU, ui, g.faceS, done)) return rc;

@@ -42,7 +42,8 @@ GmresScal gmres_scal(double *base, int sD, int nFaces);
 int ensure_small_n(size_t nd);
 
 bool any_coupled();
-int addbcmul(int op, int dof, const double *X, double *Y, double *sS, const int *done);
+int addbcmul(int op, int dof, const double *X, double *Y, double *sS, const int *done, bool dotsDone = false);
+bool addbcmul_fork_dots(int dof, const double *X, const int *done);
 int bcpre(int nsd, double *sS);
 int dot_dev(const double *U, const double *V, size_t nOwned, double *out, const int *done);
 double now_s();

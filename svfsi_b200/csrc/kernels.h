@@ -72,9 +72,10 @@ struct SpmvFuse {
   unsigned int *counter;
   unsigned long long *trace;   // SVFSI_TRACE_FILE: 8 time stamps of this column (NULL: off)
 };
+// scaleW != NULL (kind 0, dof 4 only): K <- (W_row K) W_col on the way (K is written)
 void launch_spmv_fused(cudaStream_t st, int kind, int dof, SpmvFuse f, const int *rowPtr,
                        const int *col, const double *K, const double *U, double *KU,
-                       const int *done);
+                       const int *done, const double *scaleW = nullptr);
 void launch_halo_send(cudaStream_t st, const P2PDev &pd, int dof, int nShared, int nNbr,
                       const int *packIdx, const int *slotNbr, const int *nbrRank, const int *nbrOff,
                       const int *nbrPeerOff, const double *R, int seq, unsigned int *counter);

@@ -74,12 +74,17 @@ __device__ __forceinline__ volatile int *flag_ptr(char *base, int which, int src
 // Column ids of 8 consecutive blocks are fetched by one coalesced load and
 // broadcast by shuffles, so the U gather does not wait on a dependent load per
 // block.
+// SCALE: K <- (W_row K) W_col on the way (PRECONDDIAG's scaling fused into the first product of a solve; the
+// same two multiplications per entry as scale_val4_kernel), W = the scaling vector
+template <bool SCALE = false>
 __device__ __forceinline__ double spmv_vv4_row(int row, int q, int h, unsigned gmask,
                                                const int *__restrict__ rowPtr,
                                                const int *__restrict__ col,
-                                               const double2 *__restrict__ K,
-                                               const double2 *__restrict__ U) {
+                                               const double2 *K,
+                                               const double2 *__restrict__ U,
+                                               const double *__restrict__ W = nullptr) {
   const int s = __ldg(rowPtr + row), e = __ldg(rowPtr + row + 1);
+  const double wr = SCALE ? __ldg(W + (size_t)row * 4 + (q >> 1)) : 1.0;
   double acc = 0.0;
   for (int base = s; base < e; base += 8) {
     const int mine = base + q;
@@ -89,8 +94,14 @@ __device__ __forceinline__ double spmv_vv4_row(int row, int q, int h, unsigned g
     for (int k = 0; k < 8; k++) {
       const int c = __shfl_sync(gmask, cq, k, 8);
       if (k < cnt) {
-        const double2 kv = ldg_stream2(K + (size_t)(base + k) * 8 + q);
+        double2 kv = ldg_stream2(K + (size_t)(base + k) * 8 + q);
         const double2 uv = __ldg(U + (size_t)c * 2 + h);
+        if (SCALE) {
+          const double2 wc = __ldg((const double2 *)W + (size_t)c * 2 + h);
+          kv.x = (kv.x * wr) * wc.x;
+          kv.y = (kv.y * wr) * wc.y;
+          __stcs(const_cast<double2 *>(K) + (size_t)(base + k) * 8 + q, kv);
+        }
         acc = fma(kv.x, uv.x, acc);
         acc = fma(kv.y, uv.y, acc);
       }
@@ -283,20 +294,21 @@ __device__ __forceinline__ void fuse_publish(const SpmvFuse &f) {
   }
 }
 
+template <bool SCALE>
 __global__ void __launch_bounds__(256) spmv_vv4_fused_kernel(SpmvFuse f,
                                                               const int *__restrict__ rowPtr,
                                                               const int *__restrict__ col,
-                                                              const double2 *__restrict__ K,
+                                                              const double2 *K,
                                                               const double2 *__restrict__ U,
                                                               double *__restrict__ KU,
-                                                              const int *done) {
+                                                              const int *done, const double *__restrict__ W) {
   const bool skip = (done != nullptr && *(volatile const int *)done != 0);
   const int lane = threadIdx.x & 31, q = lane & 7, h = q & 1;
   const unsigned gmask = 0xFFu << (lane & 24);
   int row, bidx;
   const bool have = fuse_map_row(f, 32, threadIdx.x >> 3, row, bidx);
   if (have && !skip) {
-    const double acc = spmv_vv4_row(row, q, h, gmask, rowPtr, col, K, U);
+    const double acc = spmv_vv4_row<SCALE>(row, q, h, gmask, rowPtr, col, K, U, W);
     if (h == 0) {
       KU[(size_t)row * 4 + (q >> 1)] = acc;
       if (bidx >= 0) fuse_send(f, bidx, 4, q >> 1, acc);
@@ -764,7 +776,7 @@ static void launch_generic_fused(cudaStream_t st, const SpmvFuse &f, int blocks,
 // f.bndCtas is filled in here (it depends on the rows per CTA of the kernel shape).
 void launch_spmv_fused(cudaStream_t st, int kind, int dof, SpmvFuse f, const int *rowPtr,
                        const int *col, const double *K, const double *U, double *KU,
-                       const int *done) {
+                       const int *done, const double *scaleW) {
   count_launch();
   const bool vv4 = (kind == 0 && dof == 4);
   if (!vv4 && use_flat()) {
@@ -776,7 +788,7 @@ void launch_spmv_fused(cudaStream_t st, int kind, int dof, SpmvFuse f, const int
     StreamMap mp{0, f.shnNo, f.mynNo, f.nNo, f.shnNo, f.mynNo, 0, 0};
     if (stream_dispatch(st, kind, dof, mp, 1, f, rowPtr, col, K, U, KU, done)) return;
   }
-  const bool quad = vv4 && spmv_fused_quad();
+  const bool quad = vv4 && spmv_fused_quad() && !scaleW;
   const int rpc = (vv4 && !quad) ? 32 : 64;
   f.bndCtas = (f.nBnd + rpc - 1) / rpc;
   const int inner = f.mynNo - f.shnNo;
@@ -787,8 +799,12 @@ void launch_spmv_fused(cudaStream_t st, int kind, int dof, SpmvFuse f, const int
     return;
   }
   if (vv4) {
-    spmv_vv4_fused_kernel<<<blocks, 256, 0, st>>>(f, rowPtr, col, (const double2 *)K,
-                                                  (const double2 *)U, KU, done);
+    if (scaleW)   // first product of a solve: carries PRECONDDIAG's K <- W K W
+      spmv_vv4_fused_kernel<true><<<blocks, 256, 0, st>>>(f, rowPtr, col, (const double2 *)K,
+                                                          (const double2 *)U, KU, done, scaleW);
+    else
+      spmv_vv4_fused_kernel<false><<<blocks, 256, 0, st>>>(f, rowPtr, col, (const double2 *)K,
+                                                           (const double2 *)U, KU, done, nullptr);
     return;
   }
 #define GENF(BR, BC) launch_generic_fused<BR, BC>(st, f, blocks, rowPtr, col, K, U, KU, done)

@@ -772,7 +772,8 @@ int fsils_solve_dev(svfsi_ls_t *ls, int dof, int prec, const int32_t *incL, cons
       const char *e = getenv("SVFSI_FUSE_SCALE");
       fuseScale = e ? atoi(e) : 1;
     }
-    const bool defer = fuseScale && ls->LS_type == SVFSI_LS_TYPE_GMRES && dof == 4 && c.nranks == 1;
+    const bool fusedComm = c.nranks > 1 && !c.nbr.empty() && c.p2p.on && c.p2p.fuse;
+    const bool defer = fuseScale && ls->LS_type == SVFSI_LS_TYPE_GMRES && dof == 4 && (c.nranks == 1 || fusedComm);
     if (int rc = preconddiag(dof, c.d_Val, c.d_R, d_W, defer)) return rc;
   } else {
     double *&d_rcs = g_dRcs;

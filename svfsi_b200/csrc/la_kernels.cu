@@ -22,6 +22,38 @@ static constexpr int kSMs = 148;
 #define DONE_GUARD(done) \
   if ((done) != nullptr && *(volatile const int *)(done) != 0) return;
 
+// Programmatic dependent launch (sm_90+): the kernels of a Gram-Schmidt column are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, trigger their successor as soon as all their CTAs have
+// started (PDL_TRIGGER at the top), and wait for their predecessor's completion + memory flush (PDL_WAIT) before
+// the first access to anything it wrote -- the successor's launch latency and prologue overlap the
+// predecessor's last wave (~3 us per kernel boundary, three to four boundaries per column).  Without the launch
+// attribute both instructions are no-ops.  SVFSI_PDL=0 turns the attribute off.
+#define PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;")
+#define PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+static bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("SVFSI_PDL");
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
+}
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 __device__ __forceinline__ double2 ldg_stream2(const double2 *p) {
   // streaming 128-bit load: matrix values are read exactly once per SpMV
   return __ldcs(p);
@@ -186,6 +218,8 @@ __global__ void __launch_bounds__(256) spmv_vv4_quad_kernel(int r0, int r1, int 
                                                              const double *__restrict__ U,
                                                              double *__restrict__ KU,
                                                              const int *done) {
+  PDL_TRIGGER();
+  PDL_WAIT();
   DONE_GUARD(done);
   const int lane = threadIdx.x & 31, r = lane & 3;
   const unsigned gmask = 0xFu << (lane & 28);
@@ -302,6 +336,8 @@ __global__ void __launch_bounds__(256) spmv_vv4_fused_kernel(SpmvFuse f,
                                                               const double2 *__restrict__ U,
                                                               double *__restrict__ KU,
                                                               const int *done, const double *__restrict__ W) {
+  PDL_TRIGGER();
+  PDL_WAIT();
   const bool skip = (done != nullptr && *(volatile const int *)done != 0);
   const int lane = threadIdx.x & 31, q = lane & 7, h = q & 1;
   const unsigned gmask = 0xFFu << (lane & 24);
@@ -734,7 +770,7 @@ void launch_spmv2(cudaStream_t st, int kind, int dof, int r0, int r1, int r2, in
   if (kind == 0 && dof == 4) {
     if (spmv_quad()) {
       const int blocks = (int)(((size_t)rows * 4 + 255) / 256);
-      spmv_vv4_quad_kernel<<<blocks, 256, 0, st>>>(r0, r1, r2, r3, rowPtr, col, K, U, KU, done);
+      launch_pdl(spmv_vv4_quad_kernel, dim3(blocks), dim3(256), 0, st, r0, r1, r2, r3, rowPtr, col, K, U, KU, done);
       return;
     }
     const int blocks = (int)(((size_t)rows * 8 + 255) / 256);
@@ -800,11 +836,11 @@ void launch_spmv_fused(cudaStream_t st, int kind, int dof, SpmvFuse f, const int
   }
   if (vv4) {
     if (scaleW)   // first product of a solve: carries PRECONDDIAG's K <- W K W
-      spmv_vv4_fused_kernel<true><<<blocks, 256, 0, st>>>(f, rowPtr, col, (const double2 *)K,
-                                                          (const double2 *)U, KU, done, scaleW);
+      launch_pdl(spmv_vv4_fused_kernel<true>, dim3(blocks), dim3(256), 0, st, f, rowPtr, col, (const double2 *)K,
+                 (const double2 *)U, KU, done, scaleW);
     else
-      spmv_vv4_fused_kernel<false><<<blocks, 256, 0, st>>>(f, rowPtr, col, (const double2 *)K,
-                                                           (const double2 *)U, KU, done, nullptr);
+      launch_pdl(spmv_vv4_fused_kernel<false>, dim3(blocks), dim3(256), 0, st, f, rowPtr, col, (const double2 *)K,
+                 (const double2 *)U, KU, done, (const double *)nullptr);
     return;
   }
 #define GENF(BR, BC) launch_generic_fused<BR, BC>(st, f, blocks, rowPtr, col, K, U, KU, done)
@@ -1237,6 +1273,8 @@ __global__ void __launch_bounds__(kDotThreads, MINB) multidot_fused_kernel(const
   __shared__ double smem[(kDotThreads / 32) * 8];
   __shared__ double sh[kArMax], sc[kArMax], ss[kArMax], sv[kArMax];
   __shared__ bool last;
+  PDL_TRIGGER();
+  PDL_WAIT();
   const bool skip = (done != nullptr && *(volatile const int *)done != 0);
   size_t lo, hi;
   unsigned crank, ccount;
@@ -1385,8 +1423,8 @@ void launch_multidot_fused(cudaStream_t st, const double *U, size_t stride, doub
     multidot_fused_kernel<3><<<kSMs * 3, kDotThreads, 0, st>>>(U, stride, w, nOwned, k, partial, done, hr,
                                                                tail, nRecv);
   else
-    multidot_fused_kernel<2><<<kSMs * 2, kDotThreads, 0, st>>>(U, stride, w, nOwned, k, partial, done, hr,
-                                                               tail, nRecv);
+    launch_pdl(multidot_fused_kernel<2>, dim3(kSMs * 2), dim3(kDotThreads), 0, st, U, stride, w, nOwned, k, partial,
+               done, hr, tail, nRecv);
 }
 
 void launch_multidot(cudaStream_t st, const double *U, size_t stride, const double *w, size_t n,
@@ -1409,6 +1447,8 @@ __global__ void __launch_bounds__(256) multi_axpy_scale_kernel(const double *__r
                                                                const double *__restrict__ coef,
                                                                const double *__restrict__ scale,
                                                                const int *done) {
+  PDL_TRIGGER();
+  PDL_WAIT();
   DONE_GUARD(done);
   extern __shared__ double sc[];
   for (int j = threadIdx.x; j < k; j += blockDim.x) sc[j] = coef[j];
@@ -1439,8 +1479,8 @@ __global__ void __launch_bounds__(256) multi_axpy_scale_kernel(const double *__r
 void launch_multi_axpy_scale(cudaStream_t st, const double *U, size_t stride, double *w, size_t n,
                              int k, const double *coef, const double *scale, const int *done) {
   count_launch();
-  multi_axpy_scale_kernel<<<kSMs * 8, 256, (size_t)(k > 0 ? k : 1) * sizeof(double), st>>>(
-      U, stride, w, n, k, coef, scale, done);
+  launch_pdl(multi_axpy_scale_kernel, dim3(kSMs * 8), dim3(256), (size_t)(k > 0 ? k : 1) * sizeof(double), st, U,
+             stride, w, n, k, coef, scale, done);
 }
 
 // X += sum_{j<k} y[j] U_j with k read from the device (number of Krylov vectors
@@ -1738,6 +1778,8 @@ __global__ void __launch_bounds__(256) face_axpyp_kernel(int nFaceNo, int fdof, 
                                                          const double *__restrict__ valM, double coef,
                                                          const double *__restrict__ partial, double *__restrict__ S,
                                                          double *__restrict__ Y, const int *done) {
+  PDL_TRIGGER();
+  PDL_WAIT();
   DONE_GUARD(done);
   __shared__ double tot;
   if (threadIdx.x < 32) {
@@ -1768,7 +1810,8 @@ void launch_face_dotp(cudaStream_t st, int nFaceNo, int fdof, int dof, const int
 void launch_face_axpyp(cudaStream_t st, int nFaceNo, int fdof, int dof, const int *glob, const double *valM,
                        double coef, const double *partial, double *S, double *Y, const int *done) {
   count_launch();
-  face_axpyp_kernel<<<kFaceCtas, 256, 0, st>>>(nFaceNo, fdof, dof, glob, valM, coef, partial, S, Y, done);
+  launch_pdl(face_axpyp_kernel, dim3(kFaceCtas), dim3(256), 0, st, nFaceNo, fdof, dof, glob, valM, coef, partial, S,
+             Y, done);
 }
 
 __global__ void face_axpy_kernel(int nFaceNo, int fdof, int dof, const int *__restrict__ glob,

@@ -183,7 +183,8 @@ int p2p_setup() {
   for (int v : all) maxShared = v > maxShared ? v : maxShared;
   p.haloCap = ((maxShared * 4 + 31) / 32) * 32;
   p.offMail = 4096;
-  p.offHalo = p.offMail + sizeof(double) * 2 * (size_t)c.nranks * kArMax;
+  p.offMailLL = p.offMail + sizeof(double) * 2 * (size_t)c.nranks * kArMax;
+  p.offHalo = p.offMailLL + 16 * 2 * (size_t)c.nranks * kArMax;
   p.bytes = p.offHalo + sizeof(double) * 2 * (size_t)(p.haloCap > 0 ? p.haloCap : 32);
   CUDA_TRY(cudaMalloc((void **)&p.arena, p.bytes));
   CUDA_TRY(cudaMemset(p.arena, 0, p.bytes));
@@ -275,6 +276,7 @@ static P2PDev p2p_dev() {
   pd.peer = c.p2p.d_peer;
   pd.offMail = c.p2p.offMail;
   pd.offHalo = c.p2p.offHalo;
+  pd.offMailLL = c.p2p.offMailLL;
   pd.haloCap = c.p2p.haloCap;
   pd.rank = c.rank;
   pd.nranks = c.nranks;

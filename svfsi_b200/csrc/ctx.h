@@ -49,14 +49,14 @@ struct Neighbor {
 
 // Peer-memory communication arena (one cudaMalloc per rank, IPC-mapped by every peer).
 //   [flags: 4 x 64 ints][all-reduce mailbox: 2 slots x nranks x kArMax doubles]
-//   [halo receive buffer: 2 slots x haloCap doubles]
+//   [flag-in-data mailbox: 2 slots x nranks x kArMax x 16 bytes][halo receive buffer: 2 slots x haloCap doubles]
 // Identical layout on every rank so a peer address is base(peer) + the local offset.
 struct P2P {
   bool on = false;
   char *arena = nullptr;
   size_t bytes = 0;
   std::vector<char *> peer;      // [nranks] mapped base of every rank's arena (own = arena)
-  size_t offMail = 0, offHalo = 0;
+  size_t offMail = 0, offHalo = 0, offMailLL = 0;
   int haloCap = 0;               // doubles per halo slot
   std::vector<int> peerOff;      // [nbr] offset (nodes) of MY slab inside neighbour i's receive buffer
   int arSeq = 0, haloSeq = 0;    // advance identically on every rank

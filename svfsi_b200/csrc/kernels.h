@@ -52,7 +52,7 @@ void launch_unpack_add(cudaStream_t st, int dof, int nUniq, const int *uniqNode,
 // peer-memory versions (NVLink stores into the neighbour's IPC-mapped receive buffer + flag)
 struct P2PDev {
   char **peer;          // [nranks] arena bases
-  size_t offMail, offHalo;
+  size_t offMail, offHalo, offMailLL;   // offMailLL: flag-in-data mailboxes of the fused column kernel
   int haloCap, rank, nranks;
   int *errDev;              // sticky "a flag wait timed out" word in device memory (Ctx::d_flag + 2)
   volatile int *errHost;    // the same in mapped pinned host memory (Ctx::h_status[0])

@@ -1372,26 +1372,53 @@ __global__ void __launch_bounds__(kDotThreads, MINB) multidot_fused_kernel(const
   }
   __syncthreads();
   if (tail.nranks > 1) {
+    // All-reduce with the flag IN the data (the "LL" protocol of NCCL): every value travels as one 16-byte store
+    // (low word, seq, high word, seq) into the mailbox of every peer; a receiver spins on the two sequence words
+    // of each value.  No system-scope fence, no separate flag store, no second round trip: the latency is ONE
+    // NVLink store.  8-byte halves carry their own tag, so the protocol does not rely on 16-byte atomicity.
+    // Values are summed in rank order: bit-identical on all ranks.
     const P2PDev &pd = tail.pd;
     const int slot = tail.arSeq & 1;
-    for (int p = 0; p < pd.nranks; p++) {
-      double *mb = (double *)(pd.peer[p] + pd.offMail) + ((size_t)slot * pd.nranks + pd.rank) * kArMax;
-      for (int j = threadIdx.x; j < k; j += blockDim.x) mb[j] = sh[j];
+    const unsigned tag = (unsigned)tail.arSeq;
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(sh[j]);
+      const uint4 pkt = make_uint4((unsigned)(bits & 0xffffffffull), tag, (unsigned)(bits >> 32), tag);
+      for (int p = 0; p < pd.nranks; p++) {
+        uint4 *mb = (uint4 *)(pd.peer[p] + pd.offMailLL) + ((size_t)slot * pd.nranks + pd.rank) * kArMax;
+        asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(mb + j), "r"(pkt.x), "r"(pkt.y),
+                     "r"(pkt.z), "r"(pkt.w) : "memory");
+      }
     }
-    __threadfence_system();
-    __syncthreads();
-    if ((int)threadIdx.x < pd.nranks) st_flag_sys(flag_ptr(pd.peer[threadIdx.x], 2 + slot, pd.rank), tail.arSeq);
-    if (tail.trace && threadIdx.x == 0) tail.trace[7] = global_ns();   // own contribution flagged to the peers
-    if ((int)threadIdx.x < pd.nranks) wait_flag_sys(flag_ptr(pd.peer[pd.rank], 2 + slot, threadIdx.x), tail.arSeq, pd);
-    __syncthreads();
-    if (tail.trace && threadIdx.x == 0) tail.trace[3] = global_ns();   // every peer's contribution has arrived
-    const double *mb = (const double *)(pd.peer[pd.rank] + pd.offMail) + (size_t)slot * pd.nranks * kArMax;
+    if (tail.trace && threadIdx.x == 0) tail.trace[7] = global_ns();   // own contribution on its way to the peers
+    const uint4 *mbIn = (const uint4 *)(pd.peer[pd.rank] + pd.offMailLL) + (size_t)slot * pd.nranks * kArMax;
+    const int e0 = *(volatile int *)pd.errDev;
     for (int j = threadIdx.x; j < k; j += blockDim.x) {
       double v = 0.0;
-      for (int r = 0; r < pd.nranks; r++) v += __ldcv(mb + (size_t)r * kArMax + j);
+      for (int r = 0; r < pd.nranks; r++) {
+        const uint4 *src = mbIn + (size_t)r * kArMax + j;
+        uint4 pkt;
+        unsigned long long t0 = 0;
+        unsigned it = 0;
+        for (;;) {
+          asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(pkt.x), "=r"(pkt.y), "=r"(pkt.z), "=r"(pkt.w) : "l"(src) : "memory");
+          if ((pkt.y == tag && pkt.w == tag) || e0) break;
+          if ((++it & 255u) == 0) {     // bounded like every peer wait (wait_flag_sys)
+            if (t0 == 0) t0 = global_ns();
+            if (*(volatile int *)pd.errDev != 0) break;
+            if (global_ns() - t0 > (unsigned long long)pd.timeoutNs) {
+              *(volatile int *)pd.errDev = 1;
+              *pd.errHost = 1;
+              break;
+            }
+          }
+        }
+        v += __longlong_as_double((long long)(((unsigned long long)pkt.z << 32) | pkt.x));
+      }
       sh[j] = v;
     }
     __syncthreads();
+    if (tail.trace && threadIdx.x == 0) tail.trace[3] = global_ns();   // every peer's contribution has arrived
   }
   for (int j = threadIdx.x; j < k; j += blockDim.x) tail.out[j] = sh[j];
   if (tail.col.ctl) {

@@ -132,18 +132,22 @@ int build_pair_lists(cudaStream_t st, int nnz, const int *blkOrder, const int *r
   return 0;
 }
 
+// .w = row + 1 for a diagonal block (its group also sums the residual of that row), else 0
 __global__ void block_desc_kernel(int nnz, const int *__restrict__ blkOrder,
-                                  const int *__restrict__ adjPtr, int4 *__restrict__ desc) {
+                                  const int *__restrict__ adjPtr, const int *__restrict__ rowOf,
+                                  const int *__restrict__ col, int4 *__restrict__ desc) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= nnz) return;
   const int p = blkOrder[g];
-  desc[g] = make_int4(p, adjPtr[p], adjPtr[p + 1], 0);
+  const int r = rowOf ? rowOf[p] : -1;
+  desc[g] = make_int4(p, adjPtr[p], adjPtr[p + 1], (rowOf && col[p] == r) ? r + 1 : 0);
 }
-int build_block_desc(cudaStream_t st, int nnz, const int *blkOrder, const int *adjPtr, int4 **desc) {
+int build_block_desc(cudaStream_t st, int nnz, const int *blkOrder, const int *adjPtr, int4 **desc,
+                     const int *rowOf, const int *col) {
   *desc = nullptr;
   if (nnz <= 0) return 0;
   CUDA_TRY(cudaMalloc(desc, sizeof(int4) * (size_t)nnz));
-  block_desc_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(nnz, blkOrder, adjPtr, *desc);
+  block_desc_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(nnz, blkOrder, adjPtr, rowOf, col, *desc);
   count_launch();
   CUDA_TRY(cudaStreamSynchronize(st));
   return 0;

@@ -111,8 +111,11 @@ int fluid_gather_dispatch(int parts, const FluidPar &par, int tune) {
   if (!c.d_elemP) CUDA_TRY(cudaMalloc(&c.d_elemP, sizeof(double) * 80 * (size_t)c.nEl));
   if ((tune & kTuneVisit) && c.d_pairDesc && (double)c.nEl * 64 < 4.0e9) {
     int p2 = (parts & 1) | ((parts & 6) ? 2 : 0);
+    // bit 22: length-sorted processing order of the first generation (diagonal blocks flagged) instead of the
+    // paired order
+    const int4 *desc = (tune & (1 << 22)) ? c.d_blkDesc : c.d_pairDesc;
     launch_fluid_gather5(c.stream, p2, par, 0, c.nEl, 0, c.nnz, c.d_ien, c.d_x, c.d_Ag, c.d_Yg, bf, c.d_elemP,
-                         ~0u, c.d_pairDesc, c.d_blkAdj, c.d_R, c.d_Val, c.d_flag, (tune >> 21) & 7);
+                         ~0u, desc, c.d_blkAdj, c.d_R, c.d_Val, c.d_flag, (tune >> 21) & 1);
     return 0;
   }
   launch_fluid_gather_parts(c.stream, parts, par, c.nEl, c.nNo, c.nnz, c.d_ien, c.d_x, c.d_Ag, c.d_Yg, bf,
@@ -562,7 +565,8 @@ int32_t gpu_mesh_create_(const int32_t *nEl_, const int32_t *eNoN, const int32_t
   if (int rc = build_pair_lists(c.stream, c.nnz, c.d_blkOrder, c.d_rowOf, c.d_col, c.d_rowPtr,
                                 &c.d_pairList, &c.d_pairT, &c.nPair))
     return rc;
-  if (int rc = build_block_desc(c.stream, c.nnz, c.d_blkOrder, c.d_blkAdjPtr, &c.d_blkDesc)) return rc;
+  if (int rc = build_block_desc(c.stream, c.nnz, c.d_blkOrder, c.d_blkAdjPtr, &c.d_blkDesc, c.d_rowOf, c.d_col))
+    return rc;
   if (int rc = build_paired_desc(c.stream, c.nPair, c.d_pairList, c.d_pairT, c.d_blkAdjPtr, c.d_rowOf, c.nnz,
                                  &c.d_pairDesc, &c.nPairDescOff))
     return rc;

@@ -230,7 +230,8 @@ struct PairLists {
   // in ONE 16-byte load instead of the dependent pair blkOrder[g] -> adjPtr[p], adjPtr[p+1]
   const int4 *desc = nullptr;
 };
-int build_block_desc(cudaStream_t st, int nnz, const int *blkOrder, const int *adjPtr, int4 **desc);
+int build_block_desc(cudaStream_t st, int nnz, const int *blkOrder, const int *adjPtr, int4 **desc,
+                     const int *rowOf = nullptr, const int *col = nullptr);
 int build_pair_lists(cudaStream_t st, int nnz, const int *blkOrder, const int *rowOf, const int *col,
                      const int *rowPtr, int **pairList, int **pairT, int *nPair);
 // gather variant: element records + owner-computes accumulation (deterministic, no atomics)

@@ -532,8 +532,9 @@ def main():
     achieved = alg_bytes / (spmv_ms / max(spmv_ops, 1) * 1e-3) / 1e9 if spmv_n else None
     # DRAM traffic of the same kernel from the committed ncu --set full capture (same mesh only)
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_spmv_traffic.json")
-    if os.path.exists(tp) and dof == 4 and SOLVER == "gmres":
+    tp = next((q for q in (os.path.join(ROOT, "profiles", "r02_spmv_traffic.json"),
+                           os.path.join(ROOT, "profiles", "r01_spmv_traffic.json")) if os.path.exists(q)), None)
+    if tp and dof == 4 and SOLVER == "gmres":
         with open(tp) as fh:
             tj = json.load(fh)
         kname = "spmv_vv4_quad_kernel" if api.spmv_variant() & 1 else "spmv_vv4_kernel"

@@ -384,8 +384,10 @@ __global__ void __launch_bounds__(NE, 4) fluid_record2_kernel(FluidPar par, int 
 //    incremental (slot, pair) indices (the 80-iteration loop with a division by 80 was ~20% of the
 //    kernel's instructions),
 //  * the ten distinct Nx_a.Nx_b products computed once.
+template <int STRIDE = NEP>
 __device__ __forceinline__ void fluid_elem_store_pairs(const FluidPar &par, const ElemAcc &acc,
                                                        double2 *rec2) {
+  constexpr int NEP = STRIDE;   // (shadows the file-scope stride: slots per field in the staging buffer)
   const double rho = par.rho, mu = par.mu;
   double nn[4][4];
 #pragma unroll
@@ -437,6 +439,40 @@ __global__ void __launch_bounds__(NE) fluid_record3_kernel(FluidPar par, int n,
   const int nHere = min(NE, n - blockIdx.x * NE);
   double2 *out = (double2 *)(elemP + (size_t)blockIdx.x * NE * F_COUNT);
   // thread t copies pairs t, t + NE, ...: (slot, pair) advance by (NE / NP, NE % NP) with carry
+  int s = threadIdx.x / NP, k = threadIdx.x - s * NP;
+#pragma unroll 4
+  for (int t = threadIdx.x; t < nHere * NP; t += NE) {
+    __stcg(out + t, sm2[k * NEP + s]);
+    s += NE / NP;
+    k += NE % NP;
+    if (k >= NP) { k -= NP; s++; }
+  }
+}
+
+// Kernel A, fourth version: the regrouped Gauss-point algebra of fluid_elem_compute2 (asm_elem.h), same record
+// and staging as v3.  UNR = unroll factor of the Gauss-point loop.
+template <int UNR>
+__global__ void __launch_bounds__(NE) fluid_record6_kernel(FluidPar par, int n,
+                                                           const int *__restrict__ ien,
+                                                           const double *__restrict__ x,
+                                                           const double *__restrict__ Ag,
+                                                           const double *__restrict__ Yg,
+                                                           const double *__restrict__ Bf,
+                                                           double *__restrict__ elemP,
+                                                           int *__restrict__ badJac) {
+  extern __shared__ double2 sm2[];  // [F_COUNT / 2][NEP]
+  constexpr int NP = F_COUNT / 2;
+  const int slot = threadIdx.x;
+  const int e = blockIdx.x * NE + slot;
+  int nodes[4];
+  if (e < n) {
+    ElemAcc acc;
+    fluid_elem_compute2<UNR>(par, e, ien, x, Ag, Yg, Bf, acc, nodes, badJac);
+    fluid_elem_store_pairs(par, acc, sm2 + slot);
+  }
+  __syncthreads();
+  const int nHere = min(NE, n - blockIdx.x * NE);
+  double2 *out = (double2 *)(elemP + (size_t)blockIdx.x * NE * F_COUNT);
   int s = threadIdx.x / NP, k = threadIdx.x - s * NP;
 #pragma unroll 4
   for (int t = threadIdx.x; t < nHere * NP; t += NE) {
@@ -952,6 +988,9 @@ static void fluid_attr_once() {
   cudaFuncSetAttribute(fluid_record2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)((size_t)40 * NEP * sizeof(double)));
   cudaFuncSetAttribute(fluid_record3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(fluid_record6_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(fluid_record6_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(fluid_record6_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   attr = true;
 }
 
@@ -978,16 +1017,19 @@ void launch_fluid_asm(cudaStream_t st, const FluidPar &par, int n, int e0, const
 // row, accumulation in shared memory); bit 6 (64): two visits in flight in it.
 // bit 7 (128): record kernel v3.  bits 10..13: pair-owner kernel for B + C (see the dispatch below).
 // bits 14..19: lean / prefetching / wide-load / quad block-owner kernels (see the dispatch below).
-// Default = 790656 = 128 + 262144 + 4096 + 524288: record kernel v3 + quad gather (four lanes per block,
-// 64-register cap, block descriptors), the fastest measured combination (profiles/r01_asm_variants.md:
-// 2.59 + 3.99 + 0.33 ms at 10M tets; the 8-lane kernel takes 6.15, the row-owner and pair-owner kernels
-// 6.9 and 7.2);
+// bit 23 (8388608): record kernel v4 (regrouped Gauss-point algebra, asm_elem.h fluid_elem_compute2), bits 24 / 25:
+// its Gauss-point loop unrolled by 2 / 4.
+// Default = 42733696 = 790656 + 8388608 + 33554432: record kernel v4 with the Gauss-point loop fully unrolled +
+// quad gather (four lanes per block, 64-register cap, block descriptors), the fastest measured combination
+// (profiles/r02_asm_experiments.md: 2.20 + 4.03 + 0.33 ms at 10M tets; round 1 default 790656: 2.59 + 3.99 +
+// 0.33; the 8-lane kernel takes 6.15, the row-owner and pair-owner kernels 6.9 and 7.2; 64-element CTAs with a
+// 170 / 128-register cap for more resident warps spill and take 3.5 / 4.7 ms);
 // SVFSI_ASM_TUNE overrides (kernel-variant timings in profiles/).
 int asm_tune() {
   static int t = -1;
   if (t < 0) {
     const char *e = getenv("SVFSI_ASM_TUNE");
-    t = e ? atoi(e) : 790656;
+    t = e ? atoi(e) : 42733696;
   }
   return t;
 }
@@ -1005,7 +1047,16 @@ void launch_fluid_gather_parts(cudaStream_t st, int parts, const FluidPar &par, 
   const bool rows = (tune & 32) && rowPtr && nodeSlots && maxRow > 0 && maxRow <= 64;
   if (parts & 1) {
     count_launch();
-    if (tune & 128) {
+    // bit 23 (8388608): records v4 = regrouped algebra; bits 24 / 25: Gauss-point loop unrolled by 2 / 4
+    if (tune & (1 << 23)) {
+      const size_t smem = (size_t)F_COUNT * NEP * sizeof(double);
+      if (tune & (1 << 25))
+        fluid_record6_kernel<4><<<(nEl + NE - 1) / NE, NE, smem, st>>>(par, nEl, ien, x, Ag, Yg, Bf, elemP, badJac);
+      else if (tune & (1 << 24))
+        fluid_record6_kernel<2><<<(nEl + NE - 1) / NE, NE, smem, st>>>(par, nEl, ien, x, Ag, Yg, Bf, elemP, badJac);
+      else
+        fluid_record6_kernel<1><<<(nEl + NE - 1) / NE, NE, smem, st>>>(par, nEl, ien, x, Ag, Yg, Bf, elemP, badJac);
+    } else if (tune & 128) {
       const size_t smem = (size_t)F_COUNT * NEP * sizeof(double);
       fluid_record3_kernel<<<(nEl + NE - 1) / NE, NE, smem, st>>>(par, nEl, ien, x, Ag, Yg, Bf,
                                                                   elemP, badJac);

@@ -71,7 +71,8 @@ ASM_TUNES = [0, 1, 8, 40, 104, 296, 552, 808, 128 + 8, 128 + 40, 128 + 104, 128 
              131072, 133120, 139264, 135168, 128 + 139264,                                     # wide-load
              262144, 264192, 270336, 272384, 266240, 128 + 262144, 128 + 270336, 128 + 266240,  # quad
              786432, 790528, 794624, 128 + 790528,                                              # quad + descriptors
-             1048576, 1048576 + 2097152, 1048576 + 4194304, 1048576 + 4194304 + 2097152]        # second generation (asm_gather5.cu)
+             1048576, 1048576 + 2097152, 1048576 + 4194304, 1048576 + 4194304 + 2097152,        # second generation (asm_gather5.cu)
+             790656 + 8388608, 790656 + 8388608 + 16777216, 790656 + 8388608 + 33554432]        # records v4 (regrouped algebra)
 
 
 @pytest.mark.parametrize("tune", ASM_TUNES)

@@ -12,7 +12,7 @@ import bench  # noqa: E402
 from svfsi_b200 import api, mesh  # noqa: E402
 
 api.init(device=0, rank=0, nranks=1)
-tune = int(os.environ.get("SVFSI_ASM_TUNE", "790656"))
+tune = int(os.environ.get("SVFSI_ASM_TUNE", "42733696"))
 res = []
 for nz in [int(a) for a in (sys.argv[1:] or ["2", "4", "8", "16", "64"])]:
     gnNo, p = bench.setup_rank(api, mesh, (64, 64, nz), 0, 1)

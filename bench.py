@@ -173,11 +173,11 @@ PHYSICS = "fluid"      # --physics heat switches to BASELINE.json configs[3] (he
 SOLVER = "gmres"       # --solver ns switches to FSILS_NSSOLVER with the FSILS defaults (configs[4])
 HEAT = dict(nu=1.0, s=0.0, rho=1.0)
 HEAT_LS = dict(relTol=1e-6, absTol=1e-12, maxItr=1000)
-# FP64 operations per element of the default (gather) fluid assembly, 2 x DFMA + DMUL + DADD: records kernel v4
-# 909 / 308 / 135 per element (SASS of the fully unrolled kernel = ncu's smsp__sass_thread_inst_executed_op_d*),
-# tangent gather 12 DFMA + 5 DMUL per lane and contribution x 4 lanes x 16, residual gather 16 adds
-# (profiles/r02_ncu_asm.md); the reference's loop needs ~15 kflop
-ASM_FLOP_PER_ELEM = 4133
+# FP64 operations per element of the default (gather) fluid assembly, 2 x DFMA + DMUL + DADD, from ncu's
+# smsp__sass_thread_inst_executed_op_dfma/dmul/dadd_pred_on on the kernels of this commit at 10.03M tets
+# (profiles/r02_ncu_asm.md): records kernel v4 883 / 297 / 122 per element = 2186 flop, tangent gather 768 / 320
+# / 0 = 1857, residual gather 16 adds; the reference's loop needs ~15 kflop
+ASM_FLOP_PER_ELEM = 4059
 FP64_PEAK_TFLOPS = 37.2
 
 

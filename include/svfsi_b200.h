@@ -187,9 +187,15 @@ int32_t gpu_dot_(const int32_t *dof, const double *U, const double *V, double *r
 /* timing: device time (ms, CUDA events on the library stream) of `reps`
  * back-to-back launches of one kernel on the resident system.
  * what: 0 = SPARMULVV kernel (dof), 1 = fluid assembly, 2 = heat assembly,
- * 3 = fused multi-dot (k vectors), 4 = fused multi-axpy (k vectors). */
+ * 3 = fused multi-dot (k vectors), 4 = fused multi-axpy (k vectors),
+ * 5 = one kernel of the gather assembly (k = part mask, variant = kernel-variant mask),
+ * 6 = small-shape SpMV (k = kind 0 VV / 1 VS / 2 SV / 3 SS, variant = kernel family, see below). */
 int32_t gpu_time_kernel_(const int32_t *what, const int32_t *dof, const int32_t *k,
                          const int32_t *reps, const int32_t *variant, double *ms_total);
+/* kernel family of the small-block SpMV shapes (FSILS_SPARMULVV dof <= 3, VS, SV, SS; L/SPARMUL.f:135-297):
+ * -1 = per-shape default, 0 = lane-per-block, 1..6 = contiguous-run / asynchronous-run / hoisted configurations
+ * (same switch as the environment variable SVFSI_SPMV_SMALL).  Results differ by summation order only. */
+int32_t gpu_set_spmv_small_(const int32_t *mode);
 /* per-phase device times (ms) and launch counts accumulated since the last
  * reset; see svfsi_b200/csrc/ctx.h for the slot names. */
 #define SVFSI_NTIMERS 16

@@ -80,7 +80,7 @@ EXPORTS = [
     "gpu_pic_init_", "gpu_pic_free_", "gpu_picp_", "gpu_setbcdir_", "gpu_pici_", "gpu_picc_",
     "gpu_pic_advance_", "gpu_pic_get_",
     "gpu_face_create_", "gpu_face_free_", "gpu_bassem_neu_fluid_", "gpu_face_integ_v_",
-    "gpu_prof_spmv_", "gpu_set_comm_timeout_",
+    "gpu_prof_spmv_", "gpu_set_comm_timeout_", "gpu_set_spmv_small_",
 ]
 
 
@@ -396,6 +396,11 @@ def time_kernel(what, dof=4, k=1, reps=10, variant=0):
     _check(lib().gpu_time_kernel_(_ci(what), _ci(dof), _ci(k), _ci(reps), _ci(variant),
                                   C.byref(ms)))
     return ms.value
+
+
+def set_spmv_small(mode):
+    """kernel family of the small-block SpMV shapes: -1 per-shape default, 0 lane-per-block, 1..4 (SVFSI_SPMV_SMALL)"""
+    _check(lib().gpu_set_spmv_small_(_ci(mode)))
 
 
 def prof_enable(on=True):

@@ -768,6 +768,21 @@ int32_t gpu_time_kernel_(const int32_t *what, const int32_t *dof, const int32_t 
       launch_spmv(c.stream, d == 1 ? 3 : 0, d, 0, c.nNo, c.d_rowPtr, c.d_col, c.d_Val, U, KU, nullptr);
     CUDA_TRY(cudaEventRecord(b, c.stream));
     if (prevQuad >= 0) set_spmv_quad(prevQuad);
+  } else if (*what == 6) {
+    // small-shape SpMV: k = kind (0 VV, 1 VS, 2 SV, 3 SS), variant = SVFSI_SPMV_SMALL mode (0 = lane-per-block,
+    // 1..6 = the run / run-async / hoisted configurations); K = the resident Val buffer (any contents), one rank's rows only
+    if (!c.d_Val) { if ((rc = ensure_system(4))) return rc; }
+    if (*k < 0 || *k > 3 || d < 1 || d > 4) return fail(SVFSI_ERR_ARG, "gpu_time_kernel_(6): kind / dof");
+    if ((rc = ensure_ws(2 * stride * sizeof(double)))) return rc;
+    double *U = c.d_ws, *KU = c.d_ws + stride;
+    launch_vecop(c.stream, VOP_ZERO, U, nullptr, nullptr, 2 * stride, nullptr, 0.0, nullptr);
+    const int prev = set_spmv_small(*variant);
+    launch_spmv(c.stream, *k, d, 0, c.nNo, c.d_rowPtr, c.d_col, c.d_Val, U, KU, nullptr);
+    CUDA_TRY(cudaEventRecord(a, c.stream));
+    for (int r = 0; r < *reps; r++)
+      launch_spmv(c.stream, *k, d, 0, c.nNo, c.d_rowPtr, c.d_col, c.d_Val, U, KU, nullptr);
+    CUDA_TRY(cudaEventRecord(b, c.stream));
+    set_spmv_small(prev);
   } else if (*what == 3 || *what == 4) {
     const int kk = *k;
     if ((rc = ensure_ws((size_t)(kk + 1) * stride * sizeof(double)))) return rc;
@@ -830,6 +845,11 @@ int32_t gpu_prof_spmv_(double *bytes, int64_t *ops) {
 }
 int32_t gpu_launch_count_(int64_t *n) {
   *n = ctx().launches;
+  return 0;
+}
+int32_t gpu_set_spmv_small_(const int32_t *mode) {
+  if (*mode < -1 || *mode > 6) return fail(SVFSI_ERR_ARG, "gpu_set_spmv_small_: mode must be -1..6");
+  set_spmv_small(*mode);
   return 0;
 }
 int32_t gpu_spmv_variant_(int32_t *variant) {

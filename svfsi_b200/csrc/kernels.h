@@ -284,6 +284,7 @@ void launch_build_edest(cudaStream_t st, int nEl, const int *ien, const int *row
 
 int spmv_fused_quad_enabled();   // the fused SpMV + halo-send kernel runs 4 lanes per row
 int set_spmv_quad(int on);   // SPARMULVV dof=4 kernel variant on the unfused path (la_kernels.cu)
+int set_spmv_small(int mode); // small-shape SpMV kernel family (la_kernels.cu, SVFSI_SPMV_SMALL); returns the previous mode
 
 void count_launch(int n = 1);
 

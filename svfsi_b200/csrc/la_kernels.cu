@@ -722,6 +722,405 @@ static bool stream_dispatch(cudaStream_t st, int kind, int dof, StreamMap mp, in
 #undef STR
 }
 
+// ---------------------------------------------------------------------------
+// Small block shapes (NSSOLVER: K 3x3, G 3x1, D 1x3, L 1x1; heat CG: 1x1; L/SPARMUL.f:135-297), third attempt.
+// What the two measured negative results above have in common with the lane-per-block kernel is the length of
+// the DEPENDENT chain a thread walks: row pointers -> (column id -> values and U) once per block it owns, i.e.
+// 9-12 serialised memory round trips per thread with 12-76 bytes in flight each.  The dof = 4 quad kernel got to
+// the HBM roofline by keeping whole rows in flight; the two families below do the same for the small shapes:
+// every load a lane needs for the whole row is ISSUED BEFORE the first one is used (fixed unroll, predicated
+// on the row length; longer rows take another trip), so a thread's chain is row pointers -> column ids +
+// values -> U: three round trips whatever the row length.
+//  * hoist<L, UNR>: lane-per-block as before (L lanes per row, lane q owns blocks q, q+L, ...), UNR blocks per
+//    lane per trip.  With L = 4 the summation order -- per lane ascending j, then the xor tree -- is the
+//    generic kernel's: bit-identical results.
+//  * run<T, STEPS>: the T lanes of a row read the row's values as ONE contiguous run of doubles (lane t takes
+//    entries t, t+T, ...: every warp-level load covers whole 128-byte lines, where lane-per-block touches a
+//    different line per lane), entry d belongs to block d / (BR BC), component (l, m) = ((d % BB) / BC, d % BC);
+//    per-lane partial sums of output row l meet by an xor tree (fixed order: deterministic).
+// volatile asm: the compiler keeps these loads in program order -- all of a row's loads are issued before the
+// first use (left to itself it sinks every load next to its FMA to save registers, which serialises them)
+__device__ __forceinline__ double ldv_cs(const double *p) {
+  double v;
+  asm volatile("ld.global.cs.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double ldv_nc(const double *p) {
+  double v;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ldv_nc_i(const int *p) {
+  int v;
+  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+template <int T>
+__device__ __forceinline__ unsigned lane_group_mask(int lane) {
+  return T >= 32 ? 0xffffffffu : (((1u << (T & 31)) - 1u) << (lane & ~(T - 1)));
+}
+template <int BR, int BC, int L, int UNR>
+__device__ __forceinline__ void spmv_hoist_row(int row, int q, unsigned gmask,
+                                               const int *__restrict__ rowPtr,
+                                               const int *__restrict__ col,
+                                               const double *__restrict__ K,
+                                               const double *__restrict__ U, double (&acc)[BR]) {
+  constexpr int BB = BR * BC;
+  const int s = __ldg(rowPtr + row), e = __ldg(rowPtr + row + 1);
+#pragma unroll
+  for (int l = 0; l < BR; l++) acc[l] = 0.0;
+  for (int base = s; base < e; base += L * UNR) {   // one trip for rows of up to L*UNR blocks
+    int c[UNR];
+    double kv[UNR][BB], u[UNR][BC];
+    // a lane without a block in this trip reads the row's first block (a line the group touches anyway) and
+    // drops the values
+#pragma unroll
+    for (int k = 0; k < UNR; k++) {
+      const int j = base + q + k * L;
+      c[k] = ldv_nc_i(col + (j < e ? j : s));
+    }
+#pragma unroll
+    for (int k = 0; k < UNR; k++) {
+      const int j = base + q + k * L;
+      const double *kp = K + (size_t)(j < e ? j : s) * BB;
+#pragma unroll
+      for (int i = 0; i < BB; i++) kv[k][i] = ldv_cs(kp + i);
+    }
+#pragma unroll
+    for (int k = 0; k < UNR; k++) {
+      const double *up = U + (size_t)c[k] * BC;
+#pragma unroll
+      for (int m = 0; m < BC; m++) u[k][m] = ldv_nc(up + m);
+    }
+#pragma unroll
+    for (int k = 0; k < UNR; k++) {
+      const bool ok = base + q + k * L < e;
+#pragma unroll
+      for (int l = 0; l < BR; l++)
+#pragma unroll
+        for (int m = 0; m < BC; m++) acc[l] = fma(ok ? kv[k][l * BC + m] : 0.0, u[k][m], acc[l]);
+    }
+  }
+#pragma unroll
+  for (int l = 0; l < BR; l++)
+#pragma unroll
+    for (int o = 1; o < L; o <<= 1) acc[l] += __shfl_xor_sync(gmask, acc[l], o, L);
+}
+template <int BR, int BC, int T, int STEPS>
+__device__ __forceinline__ void spmv_run_row(int row, int t, unsigned gmask,
+                                             const int *__restrict__ rowPtr,
+                                             const int *__restrict__ col,
+                                             const double *__restrict__ K,
+                                             const double *__restrict__ U, double (&acc)[BR]) {
+  constexpr unsigned BB = BR * BC;
+  const int s = __ldg(rowPtr + row), e = __ldg(rowPtr + row + 1);
+  const unsigned n = (unsigned)(e - s) * BB;   // doubles in this row's run
+  const double *kb = K + (size_t)s * BB;
+  const int *cb = col + s;
+#pragma unroll
+  for (int l = 0; l < BR; l++) acc[l] = 0.0;
+  for (unsigned d0 = 0; d0 < n; d0 += T * STEPS) {   // one trip for rows of up to T*STEPS doubles
+    int c[STEPS];
+    double kv[STEPS], uv[STEPS];
+    // a lane past the end of the run reads the row's first entry and drops it
+#pragma unroll
+    for (int k = 0; k < STEPS; k++) {
+      const unsigned d = d0 + (unsigned)(k * T + t);
+      c[k] = ldv_nc_i(cb + (d < n ? d / BB : 0u));
+    }
+#pragma unroll
+    for (int k = 0; k < STEPS; k++) {
+      const unsigned d = d0 + (unsigned)(k * T + t);
+      kv[k] = ldv_cs(kb + (d < n ? d : 0u));
+    }
+#pragma unroll
+    for (int k = 0; k < STEPS; k++) {
+      const unsigned d = d0 + (unsigned)(k * T + t);
+      const unsigned m = (d % BB) % (unsigned)BC;
+      uv[k] = ldv_nc(U + (size_t)c[k] * BC + m);
+    }
+#pragma unroll
+    for (int k = 0; k < STEPS; k++) {
+      const unsigned d = d0 + (unsigned)(k * T + t);
+      const int l = (int)((d % BB) / (unsigned)BC);
+      const double kk = (d < n) ? kv[k] : 0.0;
+#pragma unroll
+      for (int ll = 0; ll < BR; ll++) {
+        const double v = fma(kk, uv[k], acc[ll]);
+        acc[ll] = (BR == 1 || l == ll) ? v : acc[ll];
+      }
+    }
+  }
+#pragma unroll
+  for (int l = 0; l < BR; l++)
+#pragma unroll
+    for (int o = 1; o < T; o <<= 1) acc[l] += __shfl_xor_sync(gmask, acc[l], o, T);
+}
+//  * run-async<T, STEPS> (FAM = 2): the run kernel with every global read made an ASYNCHRONOUS copy into shared
+//    memory (cp.async / LDGSTS: no destination register, so neither the compiler nor ptxas can serialise the loads
+//    to save registers -- the SASS of the two families above shows them sinking every load next to its FMA).  A
+//    row's chain is: row pointers -> [column ids and values in flight together] -> [U in flight] -> sums out of
+//    shared memory.  Each lane reads back only the value / U slots it copied itself; column ids cross lanes and
+//    are fenced by a group-wide __syncwarp.
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+template <int BR, int BC, int T, int STEPS>
+struct RunAsyncCfg {
+  static constexpr int BB = BR * BC;
+  static constexpr int SPAN = T * STEPS;                 // doubles of a row handled per trip
+  static constexpr int CB = (SPAN + BB - 1) / BB + 1;    // blocks a trip can touch (a trip may start mid-block)
+  static constexpr int RPC = 256 / T;                    // rows per CTA
+  static constexpr size_t SMEM = (size_t)RPC * (2 * SPAN * sizeof(double) + CB * sizeof(int));
+};
+template <int BR, int BC, int T, int STEPS>
+__device__ __forceinline__ void spmv_run_async_row(int row, int t, unsigned gmask, const int *__restrict__ rowPtr,
+                                                   const int *__restrict__ col, const double *__restrict__ K,
+                                                   const double *__restrict__ U, double *sK, double *sU, int *sC,
+                                                   double (&acc)[BR]) {
+  using C = RunAsyncCfg<BR, BC, T, STEPS>;
+  constexpr unsigned BB = C::BB;
+  const int s = __ldg(rowPtr + row), e = __ldg(rowPtr + row + 1);
+  const unsigned n = (unsigned)(e - s) * BB;
+  const double *kb = K + (size_t)s * BB;
+  const int *cb = col + s;
+#pragma unroll
+  for (int l = 0; l < BR; l++) acc[l] = 0.0;
+  for (unsigned d0 = 0; d0 < n; d0 += C::SPAN) {
+    const unsigned b0 = d0 / BB;                               // first block of this trip
+    const unsigned nbt = min((unsigned)C::CB, (unsigned)(e - s) - b0);
+    for (unsigned i = t; i < nbt; i += T) cp_async4(sC + i, cb + b0 + i);
+    cp_async_commit();
+#pragma unroll
+    for (int k = 0; k < STEPS; k++) {
+      const unsigned d = d0 + (unsigned)(k * T + t);
+      if (d < n) cp_async8(sK + k * T + t, kb + d);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();          // my column-id copies have landed ...
+    __syncwarp(gmask);           // ... and so have those of the other lanes of the row
+#pragma unroll
+    for (int k = 0; k < STEPS; k++) {
+      const unsigned d = d0 + (unsigned)(k * T + t);
+      if (d < n) {
+        const int c = sC[d / BB - b0];
+        cp_async8(sU + k * T + t, U + (size_t)c * BC + (d % BB) % (unsigned)BC);
+      }
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+#pragma unroll
+    for (int k = 0; k < STEPS; k++) {
+      const unsigned d = d0 + (unsigned)(k * T + t);
+      if (d < n) {
+        const int l = (int)((d % BB) / (unsigned)BC);
+        const double kk = sK[k * T + t], uu = sU[k * T + t];
+#pragma unroll
+        for (int ll = 0; ll < BR; ll++) {
+          const double v = fma(kk, uu, acc[ll]);
+          acc[ll] = (BR == 1 || l == ll) ? v : acc[ll];
+        }
+      }
+    }
+    __syncwarp(gmask);           // the next trip overwrites the column ids
+  }
+#pragma unroll
+  for (int l = 0; l < BR; l++)
+#pragma unroll
+    for (int o = 1; o < T; o <<= 1) acc[l] += __shfl_xor_sync(gmask, acc[l], o, T);
+}
+template <int BR, int BC, int T, int STEPS>
+__global__ void __launch_bounds__(256) spmv_run_async_kernel(int fused, int r0, int r1, int r2, int r3, SpmvFuse f,
+                                                             const int *__restrict__ rowPtr,
+                                                             const int *__restrict__ col,
+                                                             const double *__restrict__ K,
+                                                             const double *__restrict__ U,
+                                                             double *__restrict__ KU, const int *done) {
+  using C = RunAsyncCfg<BR, BC, T, STEPS>;
+  extern __shared__ double2 sm2[];
+  const bool skip = (done != nullptr && *(volatile const int *)done != 0);
+  if (skip && !fused) return;
+  const int lane = threadIdx.x & 31, t = lane & (T - 1), grp = threadIdx.x / T;
+  const unsigned gmask = lane_group_mask<T>(lane);
+  double *sK = (double *)sm2 + (size_t)grp * (2 * C::SPAN);
+  double *sU = sK + C::SPAN;
+  int *sC = (int *)((double *)sm2 + (size_t)C::RPC * 2 * C::SPAN) + grp * C::CB;
+  int row = 0, bidx = -1;
+  bool have;
+  if (fused) {
+    have = fuse_map_row(f, C::RPC, grp, row, bidx);
+  } else {
+    row = r0 + (int)blockIdx.x * C::RPC + grp;
+    if (row >= r1) row += r2 - r1;
+    have = row < r3;
+  }
+  if (have && !skip) {
+    double acc[BR];
+    spmv_run_async_row<BR, BC, T, STEPS>(row, t, gmask, rowPtr, col, K, U, sK, sU, sC, acc);
+#pragma unroll
+    for (int l = 0; l < BR; l++)
+      if (t == l % T) {
+        KU[(size_t)row * BR + l] = acc[l];
+        if (bidx >= 0) fuse_send(f, bidx, BR, l, acc[l]);
+      }
+  }
+  if (fused) fuse_publish(f);
+}
+template <int BR, int BC, int T, int STEPS>
+static void launch_run_async(cudaStream_t st, int fused, int r0, int r1, int r2, int r3, SpmvFuse f,
+                             const int *rowPtr, const int *col, const double *K, const double *U, double *KU,
+                             const int *done) {
+  using C = RunAsyncCfg<BR, BC, T, STEPS>;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(spmv_run_async_kernel<BR, BC, T, STEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)C::SMEM);
+    attr = true;
+  }
+  int blocks;
+  if (fused) {
+    f.bndCtas = (f.nBnd + C::RPC - 1) / C::RPC;
+    blocks = f.bndCtas + (f.mynNo - f.shnNo + C::RPC - 1) / C::RPC;
+  } else {
+    blocks = ((r1 - r0) + (r3 - r2) + C::RPC - 1) / C::RPC;
+  }
+  if (blocks <= 0) return;
+  spmv_run_async_kernel<BR, BC, T, STEPS><<<blocks, 256, C::SMEM, st>>>(fused, r0, r1, r2, r3, f, rowPtr, col, K, U,
+                                                                       KU, done);
+}
+// FAM = 0: hoist (LPR lanes per row, P = blocks per lane and trip); FAM = 1: run (LPR lanes per row, P = steps)
+template <int FAM, int BR, int BC, int LPR, int P>
+__device__ __forceinline__ void spmv_small_row(int row, int t, unsigned gmask, const int *__restrict__ rowPtr,
+                                               const int *__restrict__ col, const double *__restrict__ K,
+                                               const double *__restrict__ U, double (&acc)[BR]) {
+  if (FAM == 0) spmv_hoist_row<BR, BC, LPR, P>(row, t, gmask, rowPtr, col, K, U, acc);
+  else spmv_run_row<BR, BC, LPR, P>(row, t, gmask, rowPtr, col, K, U, acc);
+}
+template <int FAM, int BR, int BC, int LPR, int P>
+__global__ void __launch_bounds__(256) spmv_small_kernel(int r0, int r1, int r2, int r3,
+                                                          const int *__restrict__ rowPtr,
+                                                          const int *__restrict__ col,
+                                                          const double *__restrict__ K,
+                                                          const double *__restrict__ U,
+                                                          double *__restrict__ KU, const int *done) {
+  DONE_GUARD(done);
+  const int lane = threadIdx.x & 31, t = lane & (LPR - 1);
+  const unsigned gmask = lane_group_mask<LPR>(lane);
+  int row = r0 + (int)((blockIdx.x * 256u + threadIdx.x) / (unsigned)LPR);
+  if (row >= r1) row += r2 - r1;
+  if (row >= r3) return;   // whole LPR-lane groups leave together
+  double acc[BR];
+  spmv_small_row<FAM, BR, BC, LPR, P>(row, t, gmask, rowPtr, col, K, U, acc);
+#pragma unroll
+  for (int l = 0; l < BR; l++)
+    if (t == l % LPR) KU[(size_t)row * BR + l] = acc[l];   // every lane holds the full sums
+}
+template <int FAM, int BR, int BC, int LPR, int P>
+__global__ void __launch_bounds__(256) spmv_small_fused_kernel(SpmvFuse f, const int *__restrict__ rowPtr,
+                                                                const int *__restrict__ col,
+                                                                const double *__restrict__ K,
+                                                                const double *__restrict__ U,
+                                                                double *__restrict__ KU, const int *done) {
+  const bool skip = (done != nullptr && *(volatile const int *)done != 0);
+  const int lane = threadIdx.x & 31, t = lane & (LPR - 1);
+  const unsigned gmask = lane_group_mask<LPR>(lane);
+  int row, bidx;
+  const bool have = fuse_map_row(f, 256 / LPR, threadIdx.x / LPR, row, bidx);
+  if (have && !skip) {
+    double acc[BR];
+    spmv_small_row<FAM, BR, BC, LPR, P>(row, t, gmask, rowPtr, col, K, U, acc);
+#pragma unroll
+    for (int l = 0; l < BR; l++)
+      if (t == l % LPR) {
+        KU[(size_t)row * BR + l] = acc[l];
+        if (bidx >= 0) fuse_send(f, bidx, BR, l, acc[l]);
+      }
+  }
+  fuse_publish(f);
+}
+template <int FAM, int BR, int BC, int LPR, int P>
+static void launch_small(cudaStream_t st, int r0, int r1, int r2, int r3, const int *rowPtr, const int *col,
+                         const double *K, const double *U, double *KU, const int *done) {
+  if constexpr (FAM == 2) {
+    SpmvFuse none;
+    memset(&none, 0, sizeof(none));
+    launch_run_async<BR, BC, LPR, P>(st, 0, r0, r1, r2, r3, none, rowPtr, col, K, U, KU, done);
+  } else {
+    const int rows = (r1 - r0) + (r3 - r2);
+    const int blocks = (int)(((size_t)rows * LPR + 255) / 256);
+    spmv_small_kernel<FAM, BR, BC, LPR, P><<<blocks, 256, 0, st>>>(r0, r1, r2, r3, rowPtr, col, K, U, KU, done);
+  }
+}
+template <int FAM, int BR, int BC, int LPR, int P>
+static void launch_small_fused(cudaStream_t st, SpmvFuse f, const int *rowPtr, const int *col, const double *K,
+                               const double *U, double *KU, const int *done) {
+  if constexpr (FAM == 2) {
+    launch_run_async<BR, BC, LPR, P>(st, 1, 0, 0, 0, 0, f, rowPtr, col, K, U, KU, done);
+  } else {
+    constexpr int rpc = 256 / LPR;
+    f.bndCtas = (f.nBnd + rpc - 1) / rpc;
+    const int inner = f.mynNo - f.shnNo;
+    const int blocks = f.bndCtas + (inner + rpc - 1) / rpc;
+    if (blocks <= 0) return;
+    spmv_small_fused_kernel<FAM, BR, BC, LPR, P><<<blocks, 256, 0, st>>>(f, rowPtr, col, K, U, KU, done);
+  }
+}
+// SVFSI_SPMV_SMALL = 0: lane-per-block kernels (round 1); 1..6: the configurations below (applied to every
+// shape); unset / -1: the per-shape choice measured on a B200 at 10M tets (profiles/r02_spmv_small.md).
+static int g_spmv_small = -2;
+static int spmv_small_mode() {
+  if (g_spmv_small == -2) {
+    const char *e = getenv("SVFSI_SPMV_SMALL");
+    g_spmv_small = e ? atoi(e) : -1;
+  }
+  return g_spmv_small;
+}
+int set_spmv_small(int mode) {
+  const int prev = spmv_small_mode();
+  g_spmv_small = mode;
+  return prev;
+}
+// per-shape default (mode -1): index = shape class (0: 1x1, 1: 3x3, 2: 3x1, 3: 1x3, 4: everything else)
+static const int kSmallDefault[5] = {0, 0, 0, 0, 0};
+// CALL(FAM, BR, BC, LPR, P): FAM 0 hoist (P blocks per lane), 1 run (P steps), 2 run-async (P steps).
+// Modes: 1, 2 = run; 3, 4, 6 = run-async; 5 = hoist.  Returns from the enclosing function after a launch.
+#define SMALL_SHAPE(BR, BC, T1, S1, T2, S2, T6, S6)                                               \
+  do {                                                                                            \
+    if (md == 1) { CALL_(1, BR, BC, T1, S1); return; }                                            \
+    if (md == 2) { CALL_(1, BR, BC, T2, S2); return; }                                            \
+    if (md == 3) { CALL_(2, BR, BC, T1, S1); return; }                                            \
+    if (md == 4) { CALL_(2, BR, BC, T2, S2); return; }                                            \
+    if (md == 5) { CALL_(0, BR, BC, 4, 4); return; }                                              \
+    CALL_(2, BR, BC, T6, S6); return;                                                             \
+  } while (0)
+#define SMALL_DISPATCH()                                                                          \
+  do {                                                                                            \
+    const bool ss = (kind == 3 || dof == 1);                                                      \
+    const int cls = ss ? 0 : (dof == 3 ? (kind == 0 ? 1 : (kind == 2 ? 2 : 3)) : 4);              \
+    int md = spmv_small_mode();                                                                   \
+    if (md < 0) md = kSmallDefault[cls];                                                          \
+    if (md >= 1 && md <= 6) {                                                                     \
+      if (cls == 0) SMALL_SHAPE(1, 1, 4, 4, 8, 2, 16, 1);                                         \
+      if (cls == 1) SMALL_SHAPE(3, 3, 16, 9, 32, 5, 8, 17);                                       \
+      if (cls == 2) SMALL_SHAPE(3, 1, 8, 6, 16, 3, 4, 12);                                        \
+      if (cls == 3) SMALL_SHAPE(1, 3, 8, 6, 16, 3, 4, 12);                                        \
+      /* the 2-D shapes and dof = 4 VS / SV: hoisted lane-per-block */                            \
+      if (kind == 0 && dof == 2) { CALL_(0, 2, 2, 4, 4); return; }                                \
+      if (kind == 1 && dof == 2) { CALL_(0, 1, 2, 4, 4); return; }                                \
+      if (kind == 2 && dof == 2) { CALL_(0, 2, 1, 4, 4); return; }                                \
+      if (kind == 1 && dof == 4) { CALL_(0, 1, 4, 4, 4); return; }                                \
+      if (kind == 2 && dof == 4) { CALL_(0, 4, 1, 4, 4); return; }                                \
+    }                                                                                             \
+  } while (0)
+
 template <int BR, int BC>
 static void launch_generic(cudaStream_t st, int r0, int r1, int r2, int r3, const int *rowPtr,
                            const int *col, const double *K, const double *U, double *KU,
@@ -789,6 +1188,9 @@ void launch_spmv2(cudaStream_t st, int kind, int dof, int r0, int r1, int r2, in
     memset(&none, 0, sizeof(none));
     if (stream_dispatch(st, kind, dof, mp, 0, none, rowPtr, col, K, U, KU, done)) return;
   }
+#define CALL_(FAM, BR, BC, LPR, P) launch_small<FAM, BR, BC, LPR, P>(st, r0, r1, r2, r3, rowPtr, col, K, U, KU, done)
+  SMALL_DISPATCH();
+#undef CALL_
 #define GEN(BR, BC) launch_generic<BR, BC>(st, r0, r1, r2, r3, rowPtr, col, K, U, KU, done)
   if (kind == 3 || dof == 1) {
     GEN(1, 1);
@@ -823,6 +1225,11 @@ void launch_spmv_fused(cudaStream_t st, int kind, int dof, SpmvFuse f, const int
   if (!vv4) {
     StreamMap mp{0, f.shnNo, f.mynNo, f.nNo, f.shnNo, f.mynNo, 0, 0};
     if (stream_dispatch(st, kind, dof, mp, 1, f, rowPtr, col, K, U, KU, done)) return;
+  }
+  if (!vv4) {
+#define CALL_(FAM, BR, BC, LPR, P) launch_small_fused<FAM, BR, BC, LPR, P>(st, f, rowPtr, col, K, U, KU, done)
+    SMALL_DISPATCH();
+#undef CALL_
   }
   const bool quad = vv4 && spmv_fused_quad() && !scaleW;
   const int rpc = (vv4 && !quad) ? 32 : 64;

@@ -130,6 +130,40 @@ def test_sparmul(prob, kind, dof):
     assert cm.rel_err(got.reshape(ref.shape), ref) <= 1e-14
 
 
+SMALL_SHAPES = [("VV", 3), ("VS", 3), ("SV", 3), ("SS", 1), ("VV", 2), ("VS", 2), ("SV", 2)]
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3, 4, 5, 6])
+def test_sparmul_small_shape_families(prob, mode):
+    """Every kernel family of the small block shapes (SVFSI_SPMV_SMALL / gpu_set_spmv_small_: contiguous-run,
+    asynchronous-run, hoisted lane-per-block) against the oracle's FSILS_SPARMUL* (L/SPARMUL.f:135-297); the
+    families differ from the lane-per-block kernel by summation order only."""
+    m, p = prob
+    rng = np.random.default_rng(100 + mode)
+    nnz, nNo = p.colPtr.size, p.rm.nNo
+    w = cm.oracle_world([p], m.nNo, with_faces=False)
+    api.set_spmv_small(mode)
+    try:
+        for kind, dof in SMALL_SHAPES:
+            br = dof if kind in ("VV", "SV") else 1
+            bc = dof if kind in ("VV", "VS") else 1
+            K = rng.standard_normal((nnz, br * bc)); U = rng.standard_normal((nNo, bc))
+            if kind == "VV":
+                ref = w.sparmul_vv(dof, [K], [U])[0]
+            elif kind == "VS":
+                ref = w.sparmul_vs(dof, [K], [U])[0]
+            elif kind == "SV":
+                ref = w.sparmul_sv(dof, [K], [U.reshape(-1)])[0]
+            else:
+                ref = w.sparmul_ss([K.reshape(-1)], [U.reshape(-1)])[0]
+            got = api.FSILS_SPARMUL("SS" if dof == 1 else kind, dof, K, U)
+            err = cm.rel_err(got.reshape(ref.shape), ref)
+            cm.log_parity(f"SPARMUL small-shape family mode={mode} {kind} dof={dof}", err=err)
+            assert err <= 1e-14, (mode, kind, dof, err)
+    finally:
+        api.set_spmv_small(-1)
+
+
 def test_dot(prob):
     m, p = prob
     rng = np.random.default_rng(5)

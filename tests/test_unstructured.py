@@ -87,6 +87,25 @@ def test_gpu_assembly_and_solve_on_irregular_mesh(gpu_lib, name):
         KU_o = w.sparmul_vv(4, [Vr], [U])[0]
         KU = api.FSILS_SPARMUL("VV", 4, V, U)
         assert cm.rel_err(KU, KU_o) <= 1e-13
+        # the small block shapes, every kernel family (rows of up to 91 blocks: several trips per row, trips
+        # that start in the middle of a block)
+        for mode in (0, 1, 2, 3, 4, 5, 6):
+            api.set_spmv_small(mode)
+            for kind, dof in (("VV", 3), ("VS", 3), ("SV", 3), ("SS", 1)):
+                br = dof if kind in ("VV", "SV") else 1
+                bc = dof if kind in ("VV", "VS") else 1
+                Ks = rng.standard_normal((colPtr.size, br * bc)); Us = rng.standard_normal((nNo, bc))
+                if kind == "VV":
+                    ref = w.sparmul_vv(dof, [Ks], [Us])[0]
+                elif kind == "VS":
+                    ref = w.sparmul_vs(dof, [Ks], [Us])[0]
+                elif kind == "SV":
+                    ref = w.sparmul_sv(dof, [Ks], [Us.reshape(-1)])[0]
+                else:
+                    ref = w.sparmul_ss([Ks.reshape(-1)], [Us.reshape(-1)])[0]
+                got = api.FSILS_SPARMUL(kind, dof, Ks, Us)
+                assert cm.rel_err(got.reshape(ref.shape), ref) <= 1e-13, (name, mode, kind, dof)
+        api.set_spmv_small(-1)
         # Jacobi + GMRES Newton step (no Dirichlet face: the mass term keeps the matrix regular)
         api.CONSTRUCT_FLUID(Ag, Yg, None, cm.RHO, cm.MU, cm.F, cm.DT, cm.GA["af"], cm.GA["am"],
                             cm.GA["gam"], api.ASM_GATHER)

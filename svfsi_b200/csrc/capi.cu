@@ -770,7 +770,7 @@ int32_t gpu_time_kernel_(const int32_t *what, const int32_t *dof, const int32_t 
     if (prevQuad >= 0) set_spmv_quad(prevQuad);
   } else if (*what == 6) {
     // small-shape SpMV: k = kind (0 VV, 1 VS, 2 SV, 3 SS), variant = SVFSI_SPMV_SMALL mode (0 = lane-per-block,
-    // 1..6 = the run / run-async / hoisted configurations); K = the resident Val buffer (any contents), one rank's rows only
+    // 1..8 = the run / run-async / hoisted configurations); K = the resident Val buffer (any contents), one rank's rows only
     if (!c.d_Val) { if ((rc = ensure_system(4))) return rc; }
     if (*k < 0 || *k > 3 || d < 1 || d > 4) return fail(SVFSI_ERR_ARG, "gpu_time_kernel_(6): kind / dof");
     if ((rc = ensure_ws(2 * stride * sizeof(double)))) return rc;
@@ -848,7 +848,7 @@ int32_t gpu_launch_count_(int64_t *n) {
   return 0;
 }
 int32_t gpu_set_spmv_small_(const int32_t *mode) {
-  if (*mode < -1 || *mode > 6) return fail(SVFSI_ERR_ARG, "gpu_set_spmv_small_: mode must be -1..6");
+  if (*mode < -1 || *mode > 8) return fail(SVFSI_ERR_ARG, "gpu_set_spmv_small_: mode must be -1..8");
   set_spmv_small(*mode);
   return 0;
 }

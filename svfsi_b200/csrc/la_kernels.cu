@@ -750,6 +750,9 @@ __device__ __forceinline__ double ldv_nc(const double *p) {
   asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
+__device__ __forceinline__ void ldv_cs2(const double *p, double &x, double &y) {   // 16-byte aligned
+  asm volatile("ld.global.cs.v2.f64 {%0,%1}, [%2];" : "=d"(x), "=d"(y) : "l"(p));
+}
 __device__ __forceinline__ int ldv_nc_i(const int *p) {
   int v;
   asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
@@ -759,7 +762,25 @@ template <int T>
 __device__ __forceinline__ unsigned lane_group_mask(int lane) {
   return T >= 32 ? 0xffffffffu : (((1u << (T & 31)) - 1u) << (lane & ~(T - 1)));
 }
-template <int BR, int BC, int L, int UNR>
+// WIDE (blocks of 9 or 3 doubles, 8-byte aligned): the values of a block are fetched with 128-bit loads from the
+// 16-byte aligned window that contains it -- block j starts on a 16-byte boundary iff j is even, and a lane's blocks
+// j = base + q + k L all have the parity of s + q when L is even -- 5 / 2 loads per block instead of 9 / 3 and as many
+// fewer L1 tag look-ups (the lane-per-block kernels are bound by those: every load touches ~24 lines per warp).  The
+// window of an odd block starts one double early; an even block's last load is 64 bits wide (nothing is read past
+// the end of K).
+template <int BB>
+__device__ __forceinline__ void ld_block_wide(const double *p, int odd, double (&v)[BB]) {
+  static_assert(BB == 9 || BB == 3, "wide loads: 3x3, 3x1, 1x3 blocks");
+  const double *a = p - odd;
+  double w[BB + 1];
+#pragma unroll
+  for (int i = 0; i + 2 < BB + 1; i += 2) ldv_cs2(a + i, w[i], w[i + 1]);
+  if (odd) ldv_cs2(a + BB - 1, w[BB - 1], w[BB]);
+  else { w[BB - 1] = ldv_cs(a + BB - 1); w[BB] = 0.0; }
+#pragma unroll
+  for (int i = 0; i < BB; i++) v[i] = odd ? w[i + 1] : w[i];
+}
+template <int BR, int BC, int L, int UNR, bool WIDE = false>
 __device__ __forceinline__ void spmv_hoist_row(int row, int q, unsigned gmask,
                                                const int *__restrict__ rowPtr,
                                                const int *__restrict__ col,
@@ -782,9 +803,14 @@ __device__ __forceinline__ void spmv_hoist_row(int row, int q, unsigned gmask,
 #pragma unroll
     for (int k = 0; k < UNR; k++) {
       const int j = base + q + k * L;
-      const double *kp = K + (size_t)(j < e ? j : s) * BB;
+      const int jj = j < e ? j : s;
+      const double *kp = K + (size_t)jj * BB;
+      if constexpr (WIDE && (BB == 9 || BB == 3)) {
+        ld_block_wide<BB>(kp, jj & 1, kv[k]);
+      } else {
 #pragma unroll
-      for (int i = 0; i < BB; i++) kv[k][i] = ldv_cs(kp + i);
+        for (int i = 0; i < BB; i++) kv[k][i] = ldv_cs(kp + i);
+      }
     }
 #pragma unroll
     for (int k = 0; k < UNR; k++) {
@@ -996,12 +1022,14 @@ static void launch_run_async(cudaStream_t st, int fused, int r0, int r1, int r2,
   spmv_run_async_kernel<BR, BC, T, STEPS><<<blocks, 256, C::SMEM, st>>>(fused, r0, r1, r2, r3, f, rowPtr, col, K, U,
                                                                        KU, done);
 }
-// FAM = 0: hoist (LPR lanes per row, P = blocks per lane and trip); FAM = 1: run (LPR lanes per row, P = steps)
+// FAM = 0: hoist (LPR lanes per row, P = blocks per lane and trip); FAM = 3: hoist with wide loads; FAM = 1: run (LPR
+// lanes per row, P = steps); FAM = 2 (run-async) has its own kernel
 template <int FAM, int BR, int BC, int LPR, int P>
 __device__ __forceinline__ void spmv_small_row(int row, int t, unsigned gmask, const int *__restrict__ rowPtr,
                                                const int *__restrict__ col, const double *__restrict__ K,
                                                const double *__restrict__ U, double (&acc)[BR]) {
-  if (FAM == 0) spmv_hoist_row<BR, BC, LPR, P>(row, t, gmask, rowPtr, col, K, U, acc);
+  if constexpr (FAM == 0) spmv_hoist_row<BR, BC, LPR, P>(row, t, gmask, rowPtr, col, K, U, acc);
+  else if constexpr (FAM == 3) spmv_hoist_row<BR, BC, LPR, P, true>(row, t, gmask, rowPtr, col, K, U, acc);
   else spmv_run_row<BR, BC, LPR, P>(row, t, gmask, rowPtr, col, K, U, acc);
 }
 template <int FAM, int BR, int BC, int LPR, int P>
@@ -1073,7 +1101,7 @@ static void launch_small_fused(cudaStream_t st, SpmvFuse f, const int *rowPtr, c
     spmv_small_fused_kernel<FAM, BR, BC, LPR, P><<<blocks, 256, 0, st>>>(f, rowPtr, col, K, U, KU, done);
   }
 }
-// SVFSI_SPMV_SMALL = 0: lane-per-block kernels (round 1); 1..6: the configurations below (applied to every
+// SVFSI_SPMV_SMALL = 0: lane-per-block kernels (round 1); 1..8: the configurations below (applied to every
 // shape); unset / -1: the per-shape choice measured on a B200 at 10M tets (profiles/r02_spmv_small.md).
 static int g_spmv_small = -2;
 static int spmv_small_mode() {
@@ -1091,7 +1119,8 @@ int set_spmv_small(int mode) {
 // per-shape default (mode -1): index = shape class (0: 1x1, 1: 3x3, 2: 3x1, 3: 1x3, 4: everything else)
 static const int kSmallDefault[5] = {0, 0, 0, 0, 0};
 // CALL(FAM, BR, BC, LPR, P): FAM 0 hoist (P blocks per lane), 1 run (P steps), 2 run-async (P steps).
-// Modes: 1, 2 = run; 3, 4, 6 = run-async; 5 = hoist.  Returns from the enclosing function after a launch.
+// Modes: 1, 2 = run; 3, 4, 6 = run-async; 5 = hoist (4 lanes x 4 blocks); 7, 8 = hoist with wide loads (4 x 4,
+// 8 x 2; 1x1: plain hoist 8 x 2, 2 x 8).  Returns from the enclosing function after a launch.
 #define SMALL_SHAPE(BR, BC, T1, S1, T2, S2, T6, S6)                                               \
   do {                                                                                            \
     if (md == 1) { CALL_(1, BR, BC, T1, S1); return; }                                            \
@@ -1099,7 +1128,13 @@ static const int kSmallDefault[5] = {0, 0, 0, 0, 0};
     if (md == 3) { CALL_(2, BR, BC, T1, S1); return; }                                            \
     if (md == 4) { CALL_(2, BR, BC, T2, S2); return; }                                            \
     if (md == 5) { CALL_(0, BR, BC, 4, 4); return; }                                              \
-    CALL_(2, BR, BC, T6, S6); return;                                                             \
+    if (md == 6) { CALL_(2, BR, BC, T6, S6); return; }                                            \
+    if (BR * BC == 1) {                                                                           \
+      if (md == 7) { CALL_(0, 1, 1, 8, 2); return; }                                              \
+      CALL_(0, 1, 1, 2, 8); return;                                                               \
+    }                                                                                             \
+    if (md == 7) { CALL_(3, BR, BC, 4, 4); return; }                                              \
+    CALL_(3, BR, BC, 8, 2); return;                                                               \
   } while (0)
 #define SMALL_DISPATCH()                                                                          \
   do {                                                                                            \
@@ -1107,7 +1142,7 @@ static const int kSmallDefault[5] = {0, 0, 0, 0, 0};
     const int cls = ss ? 0 : (dof == 3 ? (kind == 0 ? 1 : (kind == 2 ? 2 : 3)) : 4);              \
     int md = spmv_small_mode();                                                                   \
     if (md < 0) md = kSmallDefault[cls];                                                          \
-    if (md >= 1 && md <= 6) {                                                                     \
+    if (md >= 1 && md <= 8) {                                                                     \
       if (cls == 0) SMALL_SHAPE(1, 1, 4, 4, 8, 2, 16, 1);                                         \
       if (cls == 1) SMALL_SHAPE(3, 3, 16, 9, 32, 5, 8, 17);                                       \
       if (cls == 2) SMALL_SHAPE(3, 1, 8, 6, 16, 3, 4, 12);                                        \

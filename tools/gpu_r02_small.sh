@@ -17,7 +17,7 @@ for k, v in d["timing"].items():
     print(k, f"{v['ms']*1e3:.1f} us  {v['frac']:.3f}")
 PY
 if [ -n "$NCU_MODES" ]; then
-  SMALL_MODES=$NCU_MODES timeout 300 ncu --set full --clock-control none -k regex:spmv_ -c 40 -f -o gpurun_out/r02small_ncu \
+  SMALL_MODES=$NCU_MODES timeout 300 ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --section MemoryWorkloadAnalysis_Tables --section WarpStateStats --section Occupancy --section LaunchStats --section SchedulerStats --clock-control none -k regex:spmv_ -c 40 -f -o gpurun_out/r02small_ncu \
     python tools/bench_spmv_small.py 408 --ncu > gpurun_out/r02small_ncu.log 2>&1
   echo "ncu rc=$?"
   ncu -i gpurun_out/r02small_ncu.ncu-rep --page raw --csv > gpurun_out/r02small_ncu_raw.csv 2>/dev/null

@@ -193,7 +193,7 @@ int32_t gpu_dot_(const int32_t *dof, const double *U, const double *V, double *r
 int32_t gpu_time_kernel_(const int32_t *what, const int32_t *dof, const int32_t *k,
                          const int32_t *reps, const int32_t *variant, double *ms_total);
 /* kernel family of the small-block SpMV shapes (FSILS_SPARMULVV dof <= 3, VS, SV, SS; L/SPARMUL.f:135-297):
- * -1 = per-shape default, 0 = lane-per-block, 1..8 = contiguous-run / asynchronous-run / hoisted configurations
+ * -1 = per-shape default, 0 = lane-per-block, 1..13 = contiguous-run / asynchronous-run / hoisted configurations
  * (same switch as the environment variable SVFSI_SPMV_SMALL).  Results differ by summation order only. */
 int32_t gpu_set_spmv_small_(const int32_t *mode);
 /* per-phase device times (ms) and launch counts accumulated since the last

@@ -848,7 +848,7 @@ int32_t gpu_launch_count_(int64_t *n) {
   return 0;
 }
 int32_t gpu_set_spmv_small_(const int32_t *mode) {
-  if (*mode < -1 || *mode > 8) return fail(SVFSI_ERR_ARG, "gpu_set_spmv_small_: mode must be -1..8");
+  if (*mode < -1 || *mode > 13) return fail(SVFSI_ERR_ARG, "gpu_set_spmv_small_: mode must be -1..13");
   set_spmv_small(*mode);
   return 0;
 }

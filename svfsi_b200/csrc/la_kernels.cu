@@ -9,6 +9,7 @@
 // grids sized as multiples of the 148 SMs, reductions by warp shuffles, and no
 // host synchronisation inside the Krylov loop (kernels test a device flag).
 #include <cuda_runtime.h>
+#include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -753,6 +754,17 @@ __device__ __forceinline__ double ldv_nc(const double *p) {
 __device__ __forceinline__ void ldv_cs2(const double *p, double &x, double &y) {   // 16-byte aligned
   asm volatile("ld.global.cs.v2.f64 {%0,%1}, [%2];" : "=d"(x), "=d"(y) : "l"(p));
 }
+__device__ __forceinline__ void ldv_nc2(const double *p, double &x, double &y) {   // 16-byte aligned
+  asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(x), "=d"(y) : "l"(p));
+}
+__device__ __forceinline__ void ldv_nc_i2(const int *p, int &x, int &y) {            // 8-byte aligned
+  asm volatile("ld.global.nc.v2.s32 {%0,%1}, [%2];" : "=r"(x), "=r"(y) : "l"(p));
+}
+// matrix values: streaming (evict-first) or plain read-only loads
+template <bool NC> __device__ __forceinline__ double ldk(const double *p) { return NC ? ldv_nc(p) : ldv_cs(p); }
+template <bool NC> __device__ __forceinline__ void ldk2(const double *p, double &x, double &y) {
+  if (NC) ldv_nc2(p, x, y); else ldv_cs2(p, x, y);
+}
 __device__ __forceinline__ int ldv_nc_i(const int *p) {
   int v;
   asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
@@ -768,19 +780,22 @@ __device__ __forceinline__ unsigned lane_group_mask(int lane) {
 // fewer L1 tag look-ups (the lane-per-block kernels are bound by those: every load touches ~24 lines per warp).  The
 // window of an odd block starts one double early; an even block's last load is 64 bits wide (nothing is read past
 // the end of K).
-template <int BB>
+template <int BB, bool NC>
 __device__ __forceinline__ void ld_block_wide(const double *p, int odd, double (&v)[BB]) {
   static_assert(BB == 9 || BB == 3, "wide loads: 3x3, 3x1, 1x3 blocks");
   const double *a = p - odd;
   double w[BB + 1];
 #pragma unroll
-  for (int i = 0; i + 2 < BB + 1; i += 2) ldv_cs2(a + i, w[i], w[i + 1]);
-  if (odd) ldv_cs2(a + BB - 1, w[BB - 1], w[BB]);
-  else { w[BB - 1] = ldv_cs(a + BB - 1); w[BB] = 0.0; }
+  for (int i = 0; i + 2 < BB + 1; i += 2) ldk2<NC>(a + i, w[i], w[i + 1]);
+  if (odd) ldk2<NC>(a + BB - 1, w[BB - 1], w[BB]);
+  else { w[BB - 1] = ldk<NC>(a + BB - 1); w[BB] = 0.0; }
 #pragma unroll
   for (int i = 0; i < BB; i++) v[i] = odd ? w[i + 1] : w[i];
 }
-template <int BR, int BC, int L, int UNR, bool WIDE = false>
+// OPT bits: 1 = wide loads of the values, 2 = wide loads of U(:,col) for BC = 3 (U(1:3,c) starts on a 16-byte
+// boundary iff c is even: one 128-bit + one 64-bit load in the order the parity dictates, nothing over-read),
+// 4 = plain read-only loads of the values instead of streaming (evict-first) ones
+template <int BR, int BC, int L, int UNR, int OPT = 0>
 __device__ __forceinline__ void spmv_hoist_row(int row, int q, unsigned gmask,
                                                const int *__restrict__ rowPtr,
                                                const int *__restrict__ col,
@@ -805,18 +820,23 @@ __device__ __forceinline__ void spmv_hoist_row(int row, int q, unsigned gmask,
       const int j = base + q + k * L;
       const int jj = j < e ? j : s;
       const double *kp = K + (size_t)jj * BB;
-      if constexpr (WIDE && (BB == 9 || BB == 3)) {
-        ld_block_wide<BB>(kp, jj & 1, kv[k]);
+      if constexpr ((OPT & 1) && (BB == 9 || BB == 3)) {
+        ld_block_wide<BB, (OPT & 4) != 0>(kp, jj & 1, kv[k]);
       } else {
 #pragma unroll
-        for (int i = 0; i < BB; i++) kv[k][i] = ldv_cs(kp + i);
+        for (int i = 0; i < BB; i++) kv[k][i] = ldk<(OPT & 4) != 0>(kp + i);
       }
     }
 #pragma unroll
     for (int k = 0; k < UNR; k++) {
       const double *up = U + (size_t)c[k] * BC;
+      if constexpr ((OPT & 2) && BC == 3) {
+        if (c[k] & 1) { u[k][0] = ldv_nc(up); ldv_nc2(up + 1, u[k][1], u[k][2]); }
+        else { ldv_nc2(up, u[k][0], u[k][1]); u[k][2] = ldv_nc(up + 2); }
+      } else {
 #pragma unroll
-      for (int m = 0; m < BC; m++) u[k][m] = ldv_nc(up + m);
+        for (int m = 0; m < BC; m++) u[k][m] = ldv_nc(up + m);
+      }
     }
 #pragma unroll
     for (int k = 0; k < UNR; k++) {
@@ -831,6 +851,47 @@ __device__ __forceinline__ void spmv_hoist_row(int row, int q, unsigned gmask,
   for (int l = 0; l < BR; l++)
 #pragma unroll
     for (int o = 1; o < L; o <<= 1) acc[l] += __shfl_xor_sync(gmask, acc[l], o, L);
+}
+// 1x1 blocks, two entries per load: lane q takes the entry PAIRS q, q+L, ... of the row's window -- the row's
+// entries extended down to an even index, so that every pair is one 128-bit load of values and one 64-bit load of
+// column ids (half the L1 wavefronts of the one-entry-per-lane kernels, which is what bounds them).  The entry
+// before an odd row start and the one after an odd row end are read and dropped (they exist: the value and
+// column-id arrays are 16- and 8-byte aligned and at least nnz + (nnz & 1) entries long).
+template <int L, int UNR, bool NC>
+__device__ __forceinline__ void spmv_pair_row(int row, int q, unsigned gmask, const int *__restrict__ rowPtr,
+                                              const int *__restrict__ col, const double *__restrict__ K,
+                                              const double *__restrict__ U, double (&acc)[1]) {
+  const int s = __ldg(rowPtr + row), e = __ldg(rowPtr + row + 1);
+  const int s2 = s & ~1;
+  double a = 0.0;
+  for (int base = s2; base < e; base += 2 * L * UNR) {
+    int c0[UNR], c1[UNR];
+    double k0[UNR], k1[UNR], u0[UNR], u1[UNR];
+#pragma unroll
+    for (int k = 0; k < UNR; k++) {
+      const int j = base + 2 * (q + k * L);
+      ldv_nc_i2(col + (j < e ? j : s2), c0[k], c1[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < UNR; k++) {
+      const int j = base + 2 * (q + k * L);
+      ldk2<NC>(K + (j < e ? j : s2), k0[k], k1[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < UNR; k++) {
+      u0[k] = ldv_nc(U + c0[k]);
+      u1[k] = ldv_nc(U + c1[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < UNR; k++) {
+      const int j = base + 2 * (q + k * L);
+      a = fma((j >= s && j < e) ? k0[k] : 0.0, u0[k], a);
+      a = fma((j + 1 >= s && j + 1 < e) ? k1[k] : 0.0, u1[k], a);
+    }
+  }
+#pragma unroll
+  for (int o = 1; o < L; o <<= 1) a += __shfl_xor_sync(gmask, a, o, L);
+  acc[0] = a;
 }
 template <int BR, int BC, int T, int STEPS>
 __device__ __forceinline__ void spmv_run_row(int row, int t, unsigned gmask,
@@ -1022,15 +1083,17 @@ static void launch_run_async(cudaStream_t st, int fused, int r0, int r1, int r2,
   spmv_run_async_kernel<BR, BC, T, STEPS><<<blocks, 256, C::SMEM, st>>>(fused, r0, r1, r2, r3, f, rowPtr, col, K, U,
                                                                        KU, done);
 }
-// FAM = 0: hoist (LPR lanes per row, P = blocks per lane and trip); FAM = 3: hoist with wide loads; FAM = 1: run (LPR
-// lanes per row, P = steps); FAM = 2 (run-async) has its own kernel
+// FAM = 0: hoist (LPR lanes per row, P = blocks per lane and trip); 3: hoist with wide value loads; 10 + OPT: hoist
+// with the OPT bits of spmv_hoist_row; 20 / 21: entry pairs (1x1 only; 21 = plain instead of streaming loads);
+// 1: run (LPR lanes per row, P = steps); 2 (run-async) has its own kernel
 template <int FAM, int BR, int BC, int LPR, int P>
 __device__ __forceinline__ void spmv_small_row(int row, int t, unsigned gmask, const int *__restrict__ rowPtr,
                                                const int *__restrict__ col, const double *__restrict__ K,
                                                const double *__restrict__ U, double (&acc)[BR]) {
-  if constexpr (FAM == 0) spmv_hoist_row<BR, BC, LPR, P>(row, t, gmask, rowPtr, col, K, U, acc);
-  else if constexpr (FAM == 3) spmv_hoist_row<BR, BC, LPR, P, true>(row, t, gmask, rowPtr, col, K, U, acc);
-  else spmv_run_row<BR, BC, LPR, P>(row, t, gmask, rowPtr, col, K, U, acc);
+  if constexpr (FAM == 1) spmv_run_row<BR, BC, LPR, P>(row, t, gmask, rowPtr, col, K, U, acc);
+  else if constexpr (FAM >= 20 && BR * BC == 1) spmv_pair_row<LPR, P, (FAM & 1) != 0>(row, t, gmask, rowPtr, col, K, U, acc);
+  else if constexpr (FAM >= 10) spmv_hoist_row<BR, BC, LPR, P, FAM - 10>(row, t, gmask, rowPtr, col, K, U, acc);
+  else spmv_hoist_row<BR, BC, LPR, P, FAM == 3 ? 1 : 0>(row, t, gmask, rowPtr, col, K, U, acc);
 }
 template <int FAM, int BR, int BC, int LPR, int P>
 __global__ void __launch_bounds__(256) spmv_small_kernel(int r0, int r1, int r2, int r3,
@@ -1077,6 +1140,12 @@ __global__ void __launch_bounds__(256) spmv_small_fused_kernel(SpmvFuse f, const
 template <int FAM, int BR, int BC, int LPR, int P>
 static void launch_small(cudaStream_t st, int r0, int r1, int r2, int r3, const int *rowPtr, const int *col,
                          const double *K, const double *U, double *KU, const int *done) {
+  if constexpr (FAM == 3 || FAM >= 10) {   // 128-bit loads need 16-byte aligned arrays (column ids: 8)
+    if ((((uintptr_t)K | (uintptr_t)U) & 15) || ((uintptr_t)col & 7)) {
+      launch_small<0, BR, BC, 4, 4>(st, r0, r1, r2, r3, rowPtr, col, K, U, KU, done);
+      return;
+    }
+  }
   if constexpr (FAM == 2) {
     SpmvFuse none;
     memset(&none, 0, sizeof(none));
@@ -1090,6 +1159,12 @@ static void launch_small(cudaStream_t st, int r0, int r1, int r2, int r3, const 
 template <int FAM, int BR, int BC, int LPR, int P>
 static void launch_small_fused(cudaStream_t st, SpmvFuse f, const int *rowPtr, const int *col, const double *K,
                                const double *U, double *KU, const int *done) {
+  if constexpr (FAM == 3 || FAM >= 10) {
+    if ((((uintptr_t)K | (uintptr_t)U) & 15) || ((uintptr_t)col & 7)) {
+      launch_small_fused<0, BR, BC, 4, 4>(st, f, rowPtr, col, K, U, KU, done);
+      return;
+    }
+  }
   if constexpr (FAM == 2) {
     launch_run_async<BR, BC, LPR, P>(st, 1, 0, 0, 0, 0, f, rowPtr, col, K, U, KU, done);
   } else {
@@ -1131,10 +1206,20 @@ static const int kSmallDefault[5] = {0, 0, 0, 0, 0};
     if (md == 6) { CALL_(2, BR, BC, T6, S6); return; }                                            \
     if (BR * BC == 1) {                                                                           \
       if (md == 7) { CALL_(0, 1, 1, 8, 2); return; }                                              \
-      CALL_(0, 1, 1, 2, 8); return;                                                               \
+      if (md == 8) { CALL_(0, 1, 1, 2, 8); return; }                                              \
+      if (md == 9) { CALL_(14, 1, 1, 4, 4); return; }        /* plain loads */                    \
+      if (md == 10) { CALL_(20, 1, 1, 4, 3); return; }       /* entry pairs */                    \
+      if (md == 11) { CALL_(21, 1, 1, 4, 3); return; }       /* entry pairs, plain loads */       \
+      if (md == 12) { CALL_(20, 1, 1, 8, 2); return; }                                            \
+      CALL_(20, 1, 1, 2, 5); return;                                                              \
     }                                                                                             \
     if (md == 7) { CALL_(3, BR, BC, 4, 4); return; }                                              \
-    CALL_(3, BR, BC, 8, 2); return;                                                               \
+    if (md == 8) { CALL_(3, BR, BC, 8, 2); return; }                                              \
+    if (md == 9) { CALL_(15, BR, BC, 8, 2); return; }        /* wide values, plain loads */       \
+    if (md == 10) { CALL_(13, BR, BC, 8, 2); return; }       /* wide values + wide U */           \
+    if (md == 11) { CALL_(17, BR, BC, 8, 2); return; }       /* wide values + wide U, plain */    \
+    if (md == 12) { CALL_(13, BR, BC, 4, 4); return; }                                            \
+    CALL_(12, BR, BC, 4, 4); return;                         /* 13: wide U only */                \
   } while (0)
 #define SMALL_DISPATCH()                                                                          \
   do {                                                                                            \
@@ -1142,7 +1227,7 @@ static const int kSmallDefault[5] = {0, 0, 0, 0, 0};
     const int cls = ss ? 0 : (dof == 3 ? (kind == 0 ? 1 : (kind == 2 ? 2 : 3)) : 4);              \
     int md = spmv_small_mode();                                                                   \
     if (md < 0) md = kSmallDefault[cls];                                                          \
-    if (md >= 1 && md <= 8) {                                                                     \
+    if (md >= 1 && md <= 13) {                                                                    \
       if (cls == 0) SMALL_SHAPE(1, 1, 4, 4, 8, 2, 16, 1);                                         \
       if (cls == 1) SMALL_SHAPE(3, 3, 16, 9, 32, 5, 8, 17);                                       \
       if (cls == 2) SMALL_SHAPE(3, 1, 8, 6, 16, 3, 4, 12);                                        \

@@ -133,7 +133,7 @@ def test_sparmul(prob, kind, dof):
 SMALL_SHAPES = [("VV", 3), ("VS", 3), ("SV", 3), ("SS", 1), ("VV", 2), ("VS", 2), ("SV", 2)]
 
 
-@pytest.mark.parametrize("mode", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("mode", list(range(1, 14)))
 def test_sparmul_small_shape_families(prob, mode):
     """Every kernel family of the small block shapes (SVFSI_SPMV_SMALL / gpu_set_spmv_small_: contiguous-run,
     asynchronous-run, hoisted lane-per-block) against the oracle's FSILS_SPARMUL* (L/SPARMUL.f:135-297); the

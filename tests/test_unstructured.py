@@ -89,7 +89,7 @@ def test_gpu_assembly_and_solve_on_irregular_mesh(gpu_lib, name):
         assert cm.rel_err(KU, KU_o) <= 1e-13
         # the small block shapes, every kernel family (rows of up to 91 blocks: several trips per row, trips
         # that start in the middle of a block)
-        for mode in (0, 1, 2, 3, 4, 5, 6, 7, 8):
+        for mode in range(0, 14):
             api.set_spmv_small(mode)
             for kind, dof in (("VV", 3), ("VS", 3), ("SV", 3), ("SS", 1)):
                 br = dof if kind in ("VV", "SV") else 1

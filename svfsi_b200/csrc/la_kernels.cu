@@ -1192,7 +1192,10 @@ int set_spmv_small(int mode) {
   return prev;
 }
 // per-shape default (mode -1): index = shape class (0: 1x1, 1: 3x3, 2: 3x1, 3: 1x3, 4: everything else)
-static const int kSmallDefault[5] = {0, 0, 0, 0, 0};
+// Measured at 10.03M tets on a B200 (profiles/r02_spmv_small.md; lane-per-block = 0.56 / 0.58 / 0.60 / 0.53):
+//   1x1: hoisted 4 lanes x 4 entries 0.78;  3x3: wide value loads, 8 lanes x 2 blocks, plain loads 0.89;
+//   3x1: the same 0.76;  1x3: hoisted 4 x 4 0.71;  the other shapes: hoisted 4 x 4 (not measured at scale)
+static const int kSmallDefault[5] = {5, 9, 9, 5, 5};
 // CALL(FAM, BR, BC, LPR, P): FAM 0 hoist (P blocks per lane), 1 run (P steps), 2 run-async (P steps).
 // Modes: 1, 2 = run; 3, 4, 6 = run-async; 5 = hoist (4 lanes x 4 blocks); 7, 8 = hoist with wide loads (4 x 4,
 // 8 x 2; 1x1: plain hoist 8 x 2, 2 x 8).  Returns from the enclosing function after a launch.

@@ -1,0 +1,262 @@
+#!/usr/bin/env python
+"""Golden vectors from the REFERENCE'S OWN SOURCE TEXT (this container only: needs /root/reference).
+
+The reference (Fortran + MPI) cannot be compiled in this image.  `oracle/refexec.py` translates its procedures to
+Python/NumPy on the fly, statement by statement, and this script runs the hot path through them on small cases:
+
+  element loop   SELECTELE, GETGIP, GETGNN, INITFSMSH, GETTHOODFS, CONSTRUCT_FLUID, GNN, GNNxx, FLUID3D_M, FLUID3D_C,
+                 GETVISCOSITY, DOMAIN, ISZERO, DOASSEM                      (svFSI/NN.f, FS.f, FLUID.f, ALLFUN.f, UTIL.f, LHSA.f)
+  linear solver  FSILS_LHS_CREATE, FSILS_BC_CREATE, FSILS_SOLVE, PRECONDDIAG, PRECONDRCS, GMRESV / GMRESS / GMRES,
+                 CGRADV / CGRADS / SCHUR, BICGSV / BICGSS, NSSOLVER, DEPART, GE, ADDBCMUL, FSILS_SPARMUL*, FSILS_DOT*,
+                 FSILS_NORM*, OMP* , FSILS_BCAST*                            (svFSILS/*.f, one task)
+
+Nothing is copied: the sources are read where they lie.  Output: tests/golden/ref_*.npz (inputs + the reference's
+results), which `tests/test_reference_golden.py` compares the oracle with (CPU) and `-m gpu` tests the CUDA path with.
+
+    python tests/golden/make_ref_golden.py            # regenerate all
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from oracle import refexec as rx  # noqa: E402
+
+REF = os.environ.get("SVFSI_REFERENCE", "/root/reference")
+S = os.path.join(REF, "Code", "Source", "svFSI")
+LS = os.path.join(REF, "Code", "Source", "svFSILS")
+
+
+# ------------------------------------------------------------------------------------------------ svFSI side
+def svfsi_gen():
+    lib = rx.Library()
+    for f in ("CONSTS.f", "TYPEMOD.f", "UTIL.f", "MOD.f", "ALLFUN.f", "NN.f", "FS.f", "FLUID.f", "HEATS.f", "LHSA.f"):
+        lib.add_file(os.path.join(S, f))
+
+    def destroy(obj):       # generic DESTROY (ALLFUN.f interface): deallocate the components of a function space
+        for c, (kind, dims, alloc, init) in lib.types[obj._tname].items():
+            if alloc:
+                object.__setattr__(obj, c, None)
+
+    def dgesv(n, nrhs, a, lda, ipiv, b, ldb, info):
+        """LAPACK DGESV (the reference links LAPACK): A <- LU, B <- solution, INFO handed back"""
+        from scipy.linalg import lapack
+        lu, piv, xsol, inf = lapack.dgesv(a[:n, :n], b[:n, :nrhs])
+        a[:n, :n] = lu
+        b[:n, :nrhs] = xsol
+        ipiv[:n] = piv + 1
+        return (int(inf),)
+
+    gen = rx.CodeGen(lib, externals={"destroy": destroy, "dgesv": dgesv})
+    gen.ext_outs["dgesv"] = [7]
+    gen.M.ikind, gen.M.rkind = 4, 8     # kind numbers (only ever passed as KIND= arguments)
+    return gen
+
+
+def element_loop(gen, x, IEN, rowPtr, colPtr, Ag, Yg, rho, mu, f, dt, af, am, gam, physics="fluid", heat=None, Bf=None):
+    """CONSTRUCT_FLUID / CONSTRUCT_HEATS of the reference on one mesh; returns (R[nNo, dof], Val[nnz, dof*dof])"""
+    M, rt = gen.M, gen.rt
+    nNo, nEl = x.shape[0], IEN.shape[0]
+    dof = 4 if physics == "fluid" else 1
+    M.nsd, M.nsymd, M.tdof, M.dof, M.tnno = 3, 6, Ag.shape[1], dof, nNo
+    M.x = np.asfortranarray(x.T.copy())
+    M.bf = np.zeros((3, nNo), order="F") if Bf is None else np.asfortranarray(Bf.T.copy())
+    M.ceq, M.cdmn, M.dt, M.mvmsh, M.nmsh = 1, 1, float(dt), False, 1
+    eq = rt.new("eqtype")
+    eq.af, eq.am, eq.gam = float(af), float(am), float(gam)
+    eq.phys = M.phys_fluid if physics == "fluid" else M.phys_heats
+    eq.ndmn = 1
+    dmn = rt.new("dmntype")
+    dmn.phys, dmn.id = eq.phys, -1
+    dmn.prop = np.zeros(int(M.maxnprop), order="F")
+    if physics == "fluid":
+        dmn.prop[M.fluid_density - 1] = rho
+        dmn.prop[M.f_x - 1], dmn.prop[M.f_y - 1], dmn.prop[M.f_z - 1] = f
+        dmn.visc.visctype = M.visctype_const
+        dmn.visc.mu_i = float(mu)
+    else:
+        dmn.prop[M.conductivity - 1] = heat["nu"]
+        dmn.prop[M.source_term - 1] = heat["s"]
+        dmn.prop[M.solid_density - 1] = heat["rho"]
+    eq.dmn = rx.FList([dmn])
+    eq.s, eq.e, eq.dof = 1, dof, dof
+    M.eq = rx.FList([eq])
+    # COMMOD's assembled system (S/LHSA.f DOASSEM works on these)
+    M.rowptr = np.asfortranarray(rowPtr.astype(np.int64))
+    M.colptr = np.asfortranarray(colPtr.astype(np.int64))
+    M.r = np.zeros((dof, nNo), order="F")
+    M.val = np.zeros((dof * dof, colPtr.size), order="F")
+    # the mesh: SELECTELE fills the element tables, INITFSMSH the function space
+    lM = rt.new("mshtype")
+    lM.lshl, lM.lfib = False, False
+    lM.enon, lM.nel, lM.gnel, lM.nno, lM.nfs = 4, nEl, nEl, nNo, 1
+    lM.ien = np.asfortranarray(IEN.T.astype(np.int64))
+    gen.get("selectele")(lM)
+    gen.get("initfsmsh")(lM)
+    M.msh = rx.FList([lM])
+    Agf, Ygf = np.asfortranarray(Ag.T.copy()), np.asfortranarray(Yg.T.copy())
+    gen.get("construct_fluid" if physics == "fluid" else "construct_heats")(lM, Agf, Ygf)
+    tables = dict(w=np.array(lM.w), xi=np.array(lM.xi), N=np.array(lM.n), Nx=np.array(lM.nx))
+    return np.ascontiguousarray(M.r.T), np.ascontiguousarray(M.val.T), tables
+
+
+# ------------------------------------------------------------------------------------------------ FSILS side
+def fsils_gen():
+    lib = rx.Library()
+    for h in ("FSILS_TYPEDEF.h", "FSILS_STRUCT.h"):
+        lib.add_include(os.path.join(LS, h))
+    for f in sorted(os.listdir(LS)):
+        if f.endswith(".f"):
+            lib.add_file(os.path.join(LS, f))
+
+    def cput():
+        return 0.0
+
+    gen = rx.CodeGen(lib, externals={"fsils_cput": cput, "cpu_time": lambda t: (0.0,)})
+    gen.ext_outs["cpu_time"] = [0]
+    # mpif.h is not part of the reference tree: the handles are never used with one task, only their names appear
+    for n in ("mpint", "mpreal", "mplog", "mpchar", "mpi_sum", "mpi_max", "mpi_min", "mpi_lor", "mpi_comm_world",
+              "mpi_integer", "mpi_double_precision", "mpi_logical", "mpi_character", "mpi_in_place", "stdout"):
+        setattr(gen.M, n, 0)
+    gen.M.mpsts = gen.M.mpi_status_size = 6
+    gen.M.lsip, gen.M.lsrp = 4, 8       # kind numbers (only ever passed as KIND= arguments)
+    return gen
+
+
+def fsils_lhs(gen, gnNo, rowPtr, colPtr, faces):
+    """FSILS_COMMU (one task, built by hand: FSILS_COMMU_CREATE only wraps MPI calls), FSILS_LHS_CREATE,
+    FSILS_BC_CREATE.  faces: list of (gN 1-based, dof, bc_type, val[nNo_face, dof] | None)"""
+    rt, M = gen.rt, gen.M
+    commu = rt.new("fsils_commutype")
+    commu.foc, commu.masf, commu.master, commu.task, commu.tf, commu.ntasks, commu.comm = True, True, 0, 0, 1, 1, 0
+    lhs = rt.new("fsils_lhstype")
+    nNo = rowPtr.size - 1
+    gN = np.arange(1, nNo + 1, dtype=np.int64)
+    gen.get("fsils_lhs_create")(lhs, commu, int(gnNo), nNo, int(colPtr.size), gN, rowPtr.astype(np.int64),
+                                colPtr.astype(np.int64), len(faces))
+    for fi, (g, dof, bc, val) in enumerate(faces, start=1):
+        v = None if val is None else np.asfortranarray(np.asarray(val, dtype=np.float64).T.copy())
+        gen.get("fsils_bc_create")(lhs, fi, int(g.size), int(dof), int(bc), g.astype(np.int64), v)
+    return lhs
+
+
+def fsils_solve(gen, lhs, ls_type, dof, R, Val, prec, incL=None, res=None, **lskw):
+    """FSILS_LS_CREATE + FSILS_SOLVE; returns (X[nNo, dof], scaled Val[nnz, dof*dof], counters)"""
+    rt, M = gen.rt, gen.M
+    ls = rt.new("fsils_lstype")
+    kw = {k.lower(): v for k, v in lskw.items() if v is not None}
+    for k in ("reltolin", "abstolin"):
+        if k in kw:
+            kw[k] = np.array(kw[k], dtype=np.float64)
+    if "maxitrin" in kw:
+        kw["maxitrin"] = np.array(kw["maxitrin"], dtype=np.int64)
+    gen.get("fsils_ls_create")(ls, int(ls_type), **kw)
+    Ri = np.asfortranarray(R.reshape(R.shape[0], -1).T.copy())
+    V = np.asfortranarray(Val.reshape(Val.shape[0], -1).T.copy())
+    gen.get("fsils_solve")(lhs, ls, int(dof), Ri, V, int(prec),
+                           None if incL is None else np.asarray(incL, dtype=np.int64),
+                           None if res is None else np.asarray(res, dtype=np.float64))
+    cnt = {}
+    for sub in ("ri", "gm", "cg"):
+        o = getattr(ls, sub)
+        for f in ("itr", "suc", "inorm", "fnorm", "db"):
+            v = getattr(o, f)
+            cnt[f"{sub}_{f}"] = float(v) if not isinstance(v, (bool, np.bool_)) else bool(v)
+    return np.ascontiguousarray(Ri.T), np.ascontiguousarray(V.T), cnt
+
+
+def main():
+    import common as cm
+    import unstructured as un
+    from svfsi_b200 import mesh
+    t0 = time.time()
+    gen = svfsi_gen()
+    out = {}
+    # ---- case A: 2x2x3 Kuhn-lattice pipe (the mesh family of the parity tests)
+    m, probs, _ = mesh.build_problem(2, 2, 3, nparts=1, L=1.5)
+    p = probs[0]
+    R, V, tab = element_loop(gen, p.rm.x, p.rm.IEN, p.rowPtr, p.colPtr, p.Ag, p.Yg, cm.RHO, cm.MU, cm.F, cm.DT,
+                             cm.GA["af"], cm.GA["am"], cm.GA["gam"])
+    print(f"lattice: nEl={p.rm.IEN.shape[0]} |R|={np.abs(R).max():.3e} |Val|={np.abs(V).max():.3e} {time.time()-t0:.1f}s")
+    np.savez_compressed(os.path.join(HERE, "ref_fluid_lattice.npz"), x=p.rm.x, IEN=p.rm.IEN, rowPtr=p.rowPtr,
+                        colPtr=p.colPtr, Ag=p.Ag, Yg=p.Yg, rho=cm.RHO, mu=cm.MU, f=np.array(cm.F), dt=cm.DT,
+                        af=cm.GA["af"], am=cm.GA["am"], gam=cm.GA["gam"], R=R, Val=V, **{"tab_" + k: v for k, v in tab.items()})
+    # ---- FSILS on that system: the three faces of the parity tests, every solver / preconditioner
+    fg = fsils_gen()
+    FM = fg.M
+    faces = []
+    for name in cm.FACE_ORDER:
+        fa = p.faces[name]
+        faces.append((fa["gN"], 3, FM.bc_type_neu if fa["bc"] == "Neu" else FM.bc_type_dir, fa["val"]))
+    cases = [
+        ("gmres_diag", FM.ls_type_gmres, FM.precond_fsils, dict(relTol=1e-6, absTol=1e-14, maxItr=10, dimKry=30), 0.0),
+        ("gmres_diag_res", FM.ls_type_gmres, FM.precond_fsils, dict(relTol=1e-6, absTol=1e-14, maxItr=10, dimKry=30), 0.7),
+        ("gmres_restart", FM.ls_type_gmres, FM.precond_fsils, dict(relTol=1e-8, absTol=1e-14, maxItr=20, dimKry=8), 0.0),
+        # PRECONDRCS with a COUPLED face is undefined in the reference: the valM update is commented out
+        # (L/PRECOND.f:352-362), so ADDBCMUL reads the never-initialised valM of FSILS_BC_CREATE (NaN here: refexec
+        # poisons uninitialised REALs).  The RCS cases therefore run without resistance.
+        ("gmres_rcs", FM.ls_type_gmres, FM.precond_rcs, dict(relTol=1e-6, absTol=1e-14, maxItr=10, dimKry=30), 0.0),
+        ("ns_default", FM.ls_type_ns, FM.precond_fsils, dict(), 0.0),
+        ("ns_tight_res", FM.ls_type_ns, FM.precond_fsils, dict(relTol=1e-4, absTol=1e-14, maxItr=10, dimKry=40,
+                                                                relTolIn=(1e-3, 1e-2), maxItrIn=(3, 100)), 3.0),
+        ("bicgs_diag", FM.ls_type_bicgs, FM.precond_fsils, dict(relTol=1e-6, absTol=1e-14, maxItr=300), 0.0),
+        ("bicgs_rcs_res", FM.ls_type_bicgs, FM.precond_rcs, dict(relTol=1e-5, absTol=1e-14, maxItr=300), 0.7),
+    ]
+    sol = {}
+    for name, lst, prec, kw, res_out in cases:
+        lhs = fsils_lhs(fg, p.rm.nNo, p.rowPtr, p.colPtr, faces)
+        t1 = time.time()
+        X, Vs, cnt = fsils_solve(fg, lhs, lst, 4, R, V, prec, incL=[1, 1, 1], res=[0.0, 0.0, res_out], **kw)
+        print(f"  FSILS {name}: RI itr={cnt['ri_itr']:.0f} suc={cnt['ri_suc']} iNorm={cnt['ri_inorm']:.6e} "
+              f"fNorm={cnt['ri_fnorm']:.3e} GM={cnt['gm_itr']:.0f} CG={cnt['cg_itr']:.0f} {time.time()-t1:.1f}s")
+        sol[name + "_X"] = X
+        sol[name + "_Vscaled"] = Vs
+        sol[name + "_cnt"] = np.array([cnt[k] for k in sorted(cnt)], dtype=np.float64)
+        sol[name + "_kw"] = np.array(repr(dict(ls_type=int(lst), prec=int(prec), res_out=res_out, **kw)))
+    sol["cnt_keys"] = np.array(sorted(cnt))
+    np.savez_compressed(os.path.join(HERE, "ref_fsils_lattice.npz"), **sol)
+
+    # ---- case B: irregular mesh (Delaunay box, shuffled elements), body force and nodal body force Bf
+    x, IEN = un.delaunay_box(n=70, seed=7)
+    rowPtr, colPtr, Ag, Yg = un.problem(x, IEN)
+    rng = np.random.default_rng(5)
+    Bf = 0.3 * rng.standard_normal((x.shape[0], 3))
+    fB = (0.1, -0.2, 0.3)
+    R, V, _ = element_loop(gen, x, IEN, rowPtr, colPtr, Ag, Yg, cm.RHO, cm.MU, fB, cm.DT, cm.GA["af"], cm.GA["am"],
+                           cm.GA["gam"], Bf=Bf)
+    print(f"delaunay: nEl={IEN.shape[0]} nNo={x.shape[0]} |R|={np.abs(R).max():.3e} |Val|={np.abs(V).max():.3e}")
+    np.savez_compressed(os.path.join(HERE, "ref_fluid_delaunay.npz"), x=x, IEN=IEN, rowPtr=rowPtr, colPtr=colPtr, Ag=Ag,
+                        Yg=Yg, Bf=Bf, rho=cm.RHO, mu=cm.MU, f=np.array(fB), dt=cm.DT, af=cm.GA["af"], am=cm.GA["am"],
+                        gam=cm.GA["gam"], R=R, Val=V)
+
+    # ---- case C: heat equation (CONSTRUCT_HEATS / HEATS3D) on the lattice + CGRADS / GMRESS / BICGSS
+    heat = dict(nu=0.7, s=0.3, rho=1.3)
+    Ah = np.ascontiguousarray(p.Yg[:, :1] * 0.1)
+    Yh = np.ascontiguousarray(p.Yg[:, 2:3])
+    Rh, Vh, _ = element_loop(gen, p.rm.x, p.rm.IEN, p.rowPtr, p.colPtr, Ah, Yh, 0.0, 0.0, (0, 0, 0), cm.DT, cm.GA["af"],
+                             cm.GA["am"], cm.GA["gam"], physics="heat", heat=heat)
+    print(f"heat: |R|={np.abs(Rh).max():.3e} |Val|={np.abs(Vh).max():.3e}")
+    hs = dict(x=p.rm.x, IEN=p.rm.IEN, rowPtr=p.rowPtr, colPtr=p.colPtr, Ag=Ah[:, 0], Yg=Yh[:, 0], dt=cm.DT, af=cm.GA["af"],
+              am=cm.GA["am"], gam=cm.GA["gam"], R=Rh[:, 0], Val=Vh[:, 0], **heat)
+    hfaces = [(p.faces[n]["gN"], 1, FM.bc_type_dir, None) for n in ("inlet", "outlet")]
+    for name, lst, prec, kw in (("cg", FM.ls_type_cg, FM.precond_fsils, dict(relTol=1e-8, absTol=1e-14, maxItr=200)),
+                                ("gmres", FM.ls_type_gmres, FM.precond_fsils, dict(relTol=1e-8, absTol=1e-14, maxItr=5, dimKry=20)),
+                                ("bicgs", FM.ls_type_bicgs, FM.precond_rcs, dict(relTol=1e-8, absTol=1e-14, maxItr=200))):
+        lhs = fsils_lhs(fg, p.rm.nNo, p.rowPtr, p.colPtr, hfaces)
+        X, Vs, cnt = fsils_solve(fg, lhs, lst, 1, Rh, Vh, prec, incL=[1, 1], res=[0.0, 0.0], **kw)
+        print(f"  FSILS heat {name}: itr={cnt['ri_itr']:.0f} suc={cnt['ri_suc']} iNorm={cnt['ri_inorm']:.6e} fNorm={cnt['ri_fnorm']:.3e}")
+        hs[name + "_X"] = X[:, 0]
+        hs[name + "_cnt"] = np.array([cnt[k] for k in sorted(cnt)], dtype=np.float64)
+        hs[name + "_kw"] = np.array(repr(dict(ls_type=int(lst), prec=int(prec), **kw)))
+    hs["cnt_keys"] = np.array(sorted(cnt))
+    np.savez_compressed(os.path.join(HERE, "ref_heat_lattice.npz"), **hs)
+    print(f"done in {time.time() - t0:.1f}s")
+
+
+if __name__ == "__main__":
+    main()

@@ -133,6 +133,7 @@ def _split_semicolons(s):
 
 _DOTOPS = (".and.", ".or.", ".not.", ".eqv.", ".neqv.", ".eq.", ".ne.", ".lt.", ".le.", ".gt.", ".ge.", ".true.",
            ".false.")
+_DOTRE = re.compile(r"\.\s*(and|or|not|eqv|neqv|eq|ne|lt|le|gt|ge|true|false)\s*\.")
 _TOK = re.compile(r"""
     (?P<num>(\d+\.?\d*|\.\d+)([ed][+-]?\d+)?(_\w+)?)
   | (?P<name>[a-z_]\w*)
@@ -146,6 +147,11 @@ def tokenize(s):
     toks, i, n = [], 0, len(s)
     while i < n:
         if s[i] == ".":
+            md = _DOTRE.match(s, i)          # blanks are insignificant in fixed form: ".OR ." is .OR.
+            if md:
+                toks.append(("dot", "." + md.group(1) + "."))
+                i = md.end()
+                continue
             for d in _DOTOPS:
                 if s.startswith(d, i):
                     toks.append(("dot", d))
@@ -830,6 +836,8 @@ class Library:
         self.type_src = {}
         self.const_src = []    # (name, init text) of PARAMETER declarations outside procedures, in file order
         self.global_arrays = set()   # module-level variables declared with dimensions
+        self.generics = {}           # generic name -> specific procedure names (INTERFACE ... MODULE PROCEDURE)
+        self.global_kinds = {}       # module-level variable -> kind letter (ALLOCATE of a module array needs it)
         self.includes = {}
 
     def add_file(self, path):
@@ -898,7 +906,11 @@ class Library:
                 stack.pop()
                 continue
             if re.match(r"^interface\b", t):
+                gname = t[len("interface"):].strip()
                 while i < n and not re.match(r"^end\s*interface\b", stmts[i].text):
+                    mm = re.match(r"^module\s+procedure\s+(.*)$", stmts[i].text)
+                    if mm and gname and not gname.startswith(("operator", "assignment")):
+                        self.generics.setdefault(gname, []).extend(x.strip() for x in mm.group(1).split(","))
                     i += 1
                 i += 1
                 continue
@@ -915,6 +927,8 @@ class Library:
                         self.const_src.append((v.name, v.init, v.kind))
                     elif v.is_array:
                         self.global_arrays.add(v.name)
+                    if not v.param:
+                        self.global_kinds[v.name] = v.kind
 
 
 # ------------------------------------------------------------------------------------------------ code generation
@@ -931,6 +945,7 @@ class CodeGen:
         self.rt = Runtime(lib.types)
         self.M = globals_ns if globals_ns is not None else type("Globals", (), {})()
         self.env = {"_rt": self.rt, "_m": self.M, "np": np, "math": math, "FList": FList}
+        self.M._kinds = lib.global_kinds
         self.externals = dict(externals or {})     # name -> python callable (same calling convention)
         self.ext_outs = {}                          # name -> list of positions handed back
         self.done = {}
@@ -976,10 +991,55 @@ class CodeGen:
             self._translate(self.lib.units[name])
         return self.env[_pyname(name)]
 
+    def generic(self, name):
+        """run-time resolution of a generic name: the first specific whose dummies accept the actual arguments
+        (count, rank, derived type, integer / real / logical)"""
+        specs = [self.lib.units[s] for s in self.lib.generics[name] if s in self.lib.units]
+        for u in specs:
+            analyse(u, self)
+
+        def fits(u, args):
+            if len(args) > len(u.dummies):
+                return False
+            for k, d in enumerate(u.dummies):
+                v = u.vars[d]
+                if k >= len(args) or args[k] is None:
+                    if not v.optional:
+                        return False
+                    continue
+                a = args[k]
+                if v.kind.startswith("t:"):
+                    if v.is_array:
+                        if not isinstance(a, list):
+                            return False
+                    elif getattr(a, "_tname", None) != v.kind[2:]:
+                        return False
+                    continue
+                if isinstance(a, (FObj, FList)):
+                    return False
+                nd = a.ndim if isinstance(a, np.ndarray) else 0
+                if nd != (len(v.dims) if v.is_array else 0):
+                    return False
+                if v.kind == "i" and not (isinstance(a, (int, np.integer)) or (nd and a.dtype.kind in "iu")):
+                    return False
+                if v.kind == "r" and (isinstance(a, (bool, np.bool_, str)) or (nd and a.dtype.kind != "f") or
+                                      (not nd and isinstance(a, (int, np.integer)))):
+                    return False
+            return True
+
+        def call(*args):
+            for u in specs:
+                if fits(u, args):
+                    return self.get(u.name)(*args)
+            raise TypeError(f"no specific procedure of generic {name} accepts {[type(a).__name__ for a in args]}")
+        return call
+
     def outs_of(self, name):
         """positions (0-based) of the scalar dummies that procedure `name` hands back"""
         if name in self.externals:
             return self.ext_outs.get(name, [])
+        if name in self.lib.generics and name not in self.lib.units:
+            name = next((s for s in self.lib.generics[name] if s in self.lib.units), name)
         u = self.lib.units.get(name)
         if u is None:
             return []
@@ -1032,7 +1092,8 @@ def analyse(u, gen):
     # "REAL FSILS_NORMV, ..." declares the TYPE of an external function, not a variable
     for name in list(u.vars):
         v = u.vars[name]
-        if (name in gen.lib.units or name in gen.externals) and not v.is_array and name not in u.dummies and \
+        if (name in gen.lib.units or name in gen.externals or name in gen.lib.generics) and not v.is_array and \
+                name not in u.dummies and \
                 not (u.kind == "function" and name == u.result):
             del u.vars[name]
     for d in u.dummies:
@@ -1084,7 +1145,7 @@ class Scope:
         return "global", None
 
     def is_proc(self, n):
-        if n in self.gen.externals or n in self.gen.lib.units:
+        if n in self.gen.externals or n in self.gen.lib.units or n in self.gen.lib.generics:
             return True
         u = self.u
         while u is not None:
@@ -1150,6 +1211,9 @@ class Scope:
         if k == "call":
             return self.call_or_index(node)
         if k == "comp":
+            if node[1] == ("name", "cm") and self.lookup("cm")[0] == "global" and node[3] is not None:
+                # type-bound procedures of svFSI's communicator object (cm%seq(), cm%reduce(x)): the driver's `cm`
+                return f"_m.cm.{node[2]}({', '.join(self.argval(a) for a in node[3])})"
             base = self.expr(node[1])
             s = f"{base}.{_pyname(node[2])}"
             if node[3] is not None:
@@ -1226,7 +1290,8 @@ class Scope:
     def funcall(self, n, args):
         self.need(n)
         call = f"{_pyname(n)}({', '.join(self.argval(a) for a in args)})"
-        outs = self.gen.outs_of(n) if n in self.gen.lib.units or n in self.gen.externals else []
+        outs = self.gen.outs_of(n) if (n in self.gen.lib.units or n in self.gen.externals or
+                                       n in self.gen.lib.generics) else []
         if outs:
             return f"{call}[0]"          # a function that also hands scalars back: value only
         return call
@@ -1234,6 +1299,10 @@ class Scope:
     def need(self, n):
         if n in self.gen.externals:
             self.gen.env[_pyname(n)] = self.gen.externals[n]
+            return
+        if n in self.gen.lib.generics and n not in self.gen.lib.units:
+            if _pyname(n) not in self.gen.env:
+                self.gen.env[_pyname(n)] = self.gen.generic(n)
             return
         if n in self.gen.lib.units and n not in self.gen.done:
             self.gen._translate(self.gen.lib.units[n])
@@ -1389,7 +1458,11 @@ class Scope:
 
     @staticmethod
     def _is_do(t):
-        return re.match(r"^(\w+\s*:\s*)?do(\s|$)", t) is not None
+        """a DO construct -- not an assignment to a variable called DO (Fortran has no reserved words)"""
+        if t == "do" or re.match(r"^do\s+while\s*\(", t):
+            return True
+        m = re.match(r"^do\s+(?:\d+\s+)?\w+\s*=(.*)$", t)
+        return m is not None and len(_split_top(m.group(1))) >= 2
 
     @staticmethod
     def _is_enddo(t):
@@ -1674,7 +1747,7 @@ class Scope:
         elif v is not None and v.dummy:
             outs = []
         else:
-            if not (n in self.gen.externals or n in self.gen.lib.units):
+            if not (n in self.gen.externals or n in self.gen.lib.units or n in self.gen.lib.generics):
                 L.append(f"{pad}_rt.missing({n!r})()")
                 return
             self.need(n)

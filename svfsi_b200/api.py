@@ -465,14 +465,19 @@ def PICI(eq: EqState, am, af):
 def PICC(eq: EqState, ls: "Ls", gam, beta, dt):
     """corrector + the convergence decision of S/PIC.f:262-275 (single, uncoupled equation)"""
     _check(lib().gpu_picc_(_cd(gam), _cd(beta), _cd(dt)))
+    return picc_decision(eq, ls.RI)
+
+
+def picc_decision(eq: EqState, RI):
+    """S/PIC.f:262-275: the scalar part of PICC (RI = the FSILS_subLsType of the solve that just ran)"""
     eps = float(np.finfo(np.float64).eps)
-    if _iszero(ls.RI.iNorm):
-        ls.RI.iNorm = eps
+    if _iszero(RI.iNorm):
+        RI.iNorm = eps
     if _iszero(eq.iNorm):
-        eq.iNorm = ls.RI.iNorm
+        eq.iNorm = RI.iNorm
     if eq.itr == 1:
-        eq.pNorm = ls.RI.iNorm / eq.iNorm
-    r1 = ls.RI.iNorm / eq.iNorm
+        eq.pNorm = RI.iNorm / eq.iNorm
+    r1 = RI.iNorm / eq.iNorm
     l1 = eq.iNorm <= eq.absTol
     l2 = eq.itr >= eq.maxItr
     l3 = r1 <= eq.tol

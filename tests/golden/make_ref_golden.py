@@ -35,13 +35,11 @@ LS = os.path.join(REF, "Code", "Source", "svFSILS")
 # ------------------------------------------------------------------------------------------------ svFSI side
 def svfsi_gen():
     lib = rx.Library()
-    for f in ("CONSTS.f", "TYPEMOD.f", "UTIL.f", "MOD.f", "ALLFUN.f", "NN.f", "FS.f", "FLUID.f", "HEATS.f", "LHSA.f"):
+    for h in ("FSILS_TYPEDEF.h", "FSILS_STRUCT.h"):          # eqType carries an FSILS_lsType
+        lib.add_include(os.path.join(LS, h))
+    for f in ("CONSTS.f", "TYPEMOD.f", "UTIL.f", "MOD.f", "ALLFUN.f", "NN.f", "FS.f", "FLUID.f", "HEATS.f", "LHSA.f",
+              "EQASSEM.f", "PIC.f"):
         lib.add_file(os.path.join(S, f))
-
-    def destroy(obj):       # generic DESTROY (ALLFUN.f interface): deallocate the components of a function space
-        for c, (kind, dims, alloc, init) in lib.types[obj._tname].items():
-            if alloc:
-                object.__setattr__(obj, c, None)
 
     def dgesv(n, nrhs, a, lda, ipiv, b, ldb, info):
         """LAPACK DGESV (the reference links LAPACK): A <- LU, B <- solution, INFO handed back"""
@@ -52,8 +50,18 @@ def svfsi_gen():
         ipiv[:n] = piv + 1
         return (int(inf),)
 
-    gen = rx.CodeGen(lib, externals={"destroy": destroy, "dgesv": dgesv})
+    gen = rx.CodeGen(lib, externals={"dgesv": dgesv})
     gen.ext_outs["dgesv"] = [7]
+
+    class Cm:                        # svFSI's communicator object (CMMOD, type-bound procedures), one task
+        @staticmethod
+        def seq():
+            return True
+
+        @staticmethod
+        def reduce(v, *a):
+            return v
+    gen.M.cm = Cm()
     gen.M.ikind, gen.M.rkind = 4, 8     # kind numbers (only ever passed as KIND= arguments)
     return gen
 
@@ -102,7 +110,56 @@ def element_loop(gen, x, IEN, rowPtr, colPtr, Ag, Yg, rho, mu, f, dt, af, am, ga
     Agf, Ygf = np.asfortranarray(Ag.T.copy()), np.asfortranarray(Yg.T.copy())
     gen.get("construct_fluid" if physics == "fluid" else "construct_heats")(lM, Agf, Ygf)
     tables = dict(w=np.array(lM.w), xi=np.array(lM.xi), N=np.array(lM.n), Nx=np.array(lM.nx))
-    return np.ascontiguousarray(M.r.T), np.ascontiguousarray(M.val.T), tables
+    return M.r.T.copy(), M.val.T.copy(), tables       # (copies: the face terms are added to COMMOD's R / Val later)
+
+
+def face_neumann(gen, gN, fIEN, gE, hg, Yg, bfStab):
+    """SELECTELEB + IntegV + BASSEMNEUBC (-> GNNB, BFLUID, DOASSEM) on one face of msh(1); works on the R / Val that
+    the element loop left in COMMOD.  Returns (flux of Yg(1:3), R, Val, face tables)"""
+    M, rt = gen.M, gen.rt
+    lM = M.msh[0]
+    lFa = rt.new("facetype")
+    lFa.im, lFa.enon, lFa.nel, lFa.nno = 1, 3, int(fIEN.shape[0]), int(gN.size)
+    lFa.ien = np.asfortranarray(fIEN.T.astype(np.int64))
+    lFa.ge = gE.astype(np.int64)
+    lFa.gn = gN.astype(np.int64)
+    gen.get("selecteleb")(lM, lFa)
+    M.eq[0].dmn[0].prop[M.backflow_stab - 1] = bfStab
+    M.ibflag = False
+    Ygf = np.asfortranarray(Yg.T.copy())
+    flux = gen.get("integv")(lFa, np.asfortranarray(Yg[:, :3].T.copy()))
+    gen.get("bassemneubc")(lFa, np.asarray(hg, dtype=np.float64), Ygf)
+    tab = dict(w=np.array(lFa.w), N=np.array(lFa.n), Nx=np.array(lFa.nx))
+    return float(flux), M.r.T.copy(), M.val.T.copy(), tab
+
+
+def pic_cycle(gen, Ao, Yo, Do, Rinc, gam, beta, am, af, dt, iNorm, tol, absTol, minItr, maxItr, itr0):
+    """PICP, PICI, PICC (S/PIC.f) for one equation of 4 dofs; Rinc = what the linear solver left in R.
+    Returns the arrays after each routine and PICC's bookkeeping."""
+    M, rt = gen.M, gen.rt
+    nNo = Ao.shape[0]
+    F = lambda a: np.asfortranarray(a.T.copy())
+    M.psteq, M.ibflag, M.eccpld, M.dflag, M.ssteq, M.cmminit, M.neq = False, False, False, False, False, False, 1
+    M.ao, M.yo, M.do = F(Ao), F(Yo), F(Do)
+    M.an, M.yn, M.dn = np.zeros_like(M.ao), np.zeros_like(M.ao), np.zeros_like(M.ao)
+    eq = M.eq[0]
+    eq.s, eq.e, eq.dof = 1, 4, 4
+    eq.gam, eq.beta, eq.am, eq.af = float(gam), float(beta), float(am), float(af)
+    eq.itr, eq.ok, eq.coupled = int(itr0), False, False
+    eq.tol, eq.abstol, eq.minitr, eq.maxitr, eq.inorm, eq.pnorm = float(tol), float(absTol), int(minItr), int(maxItr), 0.0, 0.0
+    M.dt, M.ceq, M.tnno, M.tdof, M.nsd = float(dt), 1, nNo, 4, 3
+    out = {}
+    gen.get("picp")()
+    out["picp_An"], out["picp_Yn"], out["picp_Dn"] = (a.T.copy() for a in (M.an, M.yn, M.dn))
+    Ag, Yg, Dg = (np.full((4, nNo), np.nan, order="F") for _ in range(3))
+    gen.get("pici")(Ag, Yg, Dg)
+    out["pici_Ag"], out["pici_Yg"], out["pici_Dg"] = (a.T.copy() for a in (Ag, Yg, Dg))
+    M.r = F(Rinc)
+    eq.fsils.ri.inorm = float(iNorm)
+    gen.get("picc")()
+    out["picc_An"], out["picc_Yn"], out["picc_Dn"] = (a.T.copy() for a in (M.an, M.yn, M.dn))
+    out["picc_book"] = np.array([eq.itr, float(eq.ok), eq.inorm, eq.pnorm, M.ceq], dtype=np.float64)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ FSILS side
@@ -167,7 +224,7 @@ def fsils_solve(gen, lhs, ls_type, dof, R, Val, prec, incL=None, res=None, **lsk
         for f in ("itr", "suc", "inorm", "fnorm", "db"):
             v = getattr(o, f)
             cnt[f"{sub}_{f}"] = float(v) if not isinstance(v, (bool, np.bool_)) else bool(v)
-    return np.ascontiguousarray(Ri.T), np.ascontiguousarray(V.T), cnt
+    return Ri.T.copy(), V.T.copy(), cnt
 
 
 def main():
@@ -220,6 +277,45 @@ def main():
         sol[name + "_kw"] = np.array(repr(dict(ls_type=int(lst), prec=int(prec), res_out=res_out, **kw)))
     sol["cnt_keys"] = np.array(sorted(cnt))
     np.savez_compressed(os.path.join(HERE, "ref_fsils_lattice.npz"), **sol)
+
+    # ---- LHSA (S/LHSA.f:40-264): the block-CSR pattern of the mesh the element loop just ran on
+    M = gen.M
+    M.shleq, M.neq = False, 1
+    M.eq[0].nbc = 0
+    (nnz,) = gen.get("lhsa")(0)
+    print(f"  LHSA: nnz={nnz} (harness pattern: {p.colPtr.size})")
+    np.savez_compressed(os.path.join(HERE, "ref_lhsa_lattice.npz"), IEN=p.rm.IEN, nNo=p.rm.nNo, nnz=nnz,
+                        rowPtr=np.array(M.rowptr), colPtr=np.array(M.colptr))
+
+    # ---- face terms on the lattice: outlet with the flow reversed (backflow stabilisation active), inlet as it is
+    fc = {}
+    for fname, flow, h in (("outlet", -1.0, 3.5), ("inlet", 1.0, -2.0), ("outlet", 1.0, 0.7)):
+        gN, fIEN, gE = cm.local_face(m, p.rm, fname)
+        Yg2 = p.Yg.copy(); Yg2[:, :3] *= flow
+        R0, V0, _ = element_loop(gen, p.rm.x, p.rm.IEN, p.rowPtr, p.colPtr, p.Ag, Yg2, cm.RHO, cm.MU, cm.F, cm.DT,
+                                 cm.GA["af"], cm.GA["am"], cm.GA["gam"])
+        hg = np.zeros(p.rm.nNo); hg[gN - 1] = -h
+        flux, R1, V1, ftab = face_neumann(gen, gN, fIEN, gE, hg, Yg2, 0.2)
+        key = f"{fname}_{'rev' if flow < 0 else 'fwd'}"
+        print(f"  face {key}: nEl={fIEN.shape[0]} flux={flux:.6e} |dR|={np.abs(R1 - R0).max():.3e} |dVal|={np.abs(V1 - V0).max():.3e}")
+        fc.update({f"{key}_gN": gN, f"{key}_fIEN": fIEN, f"{key}_gE": gE, f"{key}_hg": hg, f"{key}_Yg": Yg2,
+                   f"{key}_R0": R0, f"{key}_V0": V0, f"{key}_R1": R1, f"{key}_V1": V1, f"{key}_flux": flux})
+    fc.update({"tab_" + k: v for k, v in ftab.items()})
+    fc.update(bfStab=0.2, rho=cm.RHO, af=cm.GA["af"], gam=cm.GA["gam"], dt=cm.DT)
+    np.savez_compressed(os.path.join(HERE, "ref_face_lattice.npz"), **fc)
+
+    # ---- generalised-alpha predictor / initiator / corrector (S/PIC.f) on random states
+    rng = np.random.default_rng(17)
+    nN = p.rm.nNo
+    Ao, Yo, Do, Rinc = (rng.standard_normal((nN, 4)) for _ in range(4))
+    pc = dict(Ao=Ao, Yo=Yo, Do=Do, Rinc=Rinc, gam=cm.GA["gam"], beta=cm.GA["beta"], am=cm.GA["am"], af=cm.GA["af"], dt=cm.DT)
+    for tag, iNorm, tol, itr0 in (("first", 12.5, 1e-3, 0), ("conv", 1e-9, 1e-3, 2)):
+        o = pic_cycle(gen, Ao, Yo, Do, Rinc, cm.GA["gam"], cm.GA["beta"], cm.GA["am"], cm.GA["af"], cm.DT, iNorm, tol,
+                      1e-8, 1, 10, itr0)
+        print(f"  PIC {tag}: book(itr, ok, iNorm, pNorm, cEq)={o['picc_book']}")
+        pc.update({f"{tag}_{k}": v for k, v in o.items()})
+        pc[f"{tag}_in"] = np.array([iNorm, tol, 1e-8, 1, 10, itr0])
+    np.savez_compressed(os.path.join(HERE, "ref_pic.npz"), **pc)
 
     # ---- case B: irregular mesh (Delaunay box, shuffled elements), body force and nodal body force Bf
     x, IEN = un.delaunay_box(n=70, seed=7)

@@ -185,6 +185,174 @@ def fsils_gen():
     return gen
 
 
+class MpiEmu:
+    """The MPI calls of svFSILS for `n` tasks that run as THREADS of this process (threading.current_thread().rank):
+    ALLREDUCE (rank-ordered sum / max), ALLGATHER(V), SEND / RECV, ISEND / IRECV / WAIT.  Scalars that MPI would
+    store through a reference are handed back (refexec's convention); arrays are filled in place."""
+
+    def __init__(self, n):
+        import collections
+        import queue
+        import threading
+        self.n = n
+        self.bar = threading.Barrier(n)
+        self.slots = [None] * n
+        self.mail = collections.defaultdict(queue.Queue)
+        self.reqs = {}
+        self.lock = threading.Lock()
+        self.nreq = 0
+        self.threading = threading
+
+    def rank(self):
+        return self.threading.current_thread().rank
+
+    @staticmethod
+    def _flat(a, count):
+        return a.reshape(-1, order="F")[:int(count)] if isinstance(a, np.ndarray) else a
+
+    def _exchange(self, val):
+        r = self.rank()
+        self.slots[r] = np.array(val, copy=True) if isinstance(val, np.ndarray) else val
+        self.bar.wait()
+        allv = list(self.slots)
+        self.bar.wait()
+        return allv
+
+    def allreduce(self, send, recv, count, dtype, op, comm, ierr):
+        allv = self._exchange(self._flat(send, count))
+        res = allv[0]
+        for v in allv[1:]:                       # rank order
+            res = np.maximum(res, v) if op == "max" else res + v
+        if isinstance(recv, np.ndarray) and recv.ndim > 0:
+            self._flat(recv, count)[...] = res
+            return recv, 0
+        if isinstance(res, np.ndarray):
+            res = res.reshape(-1)[0]
+        return (int(res) if isinstance(send, (int, np.integer)) and not isinstance(send, bool) else res), 0
+
+    def allgatherv(self, send, scount, stype, recv, rcounts, displs, rtype, comm, ierr):
+        allv = self._exchange(self._flat(send, scount))
+        flat = recv.reshape(-1, order="F")
+        assert np.shares_memory(flat, recv)
+        for r, v in enumerate(allv):
+            flat[int(displs[r]):int(displs[r]) + int(rcounts[r])] = v[:int(rcounts[r])]
+        return (0,)
+
+    def allgather(self, send, scount, stype, recv, rcount, rtype, comm, ierr):
+        allv = self._exchange(send)
+        for r, v in enumerate(allv):
+            recv[r] = v
+        return (0,)
+
+    def send(self, buf, count, dtype, dest, tag, comm, *rest):
+        self.mail[(self.rank(), int(dest), int(tag))].put(np.array(self._flat(buf, count), copy=True))
+
+    def recv(self, buf, count, dtype, src, tag, comm, stat, ierr):
+        self._flat(buf, count)[...] = self.mail[(int(src), self.rank(), int(tag))].get(timeout=60)
+        return (0,)
+
+    def isend(self, buf, count, dtype, dest, tag, comm, req, ierr):
+        self.send(buf, count, dtype, dest, tag, comm)
+        return -1, 0
+
+    def irecv(self, buf, count, dtype, src, tag, comm, req, ierr):
+        with self.lock:
+            self.nreq += 1
+            rid = self.nreq
+            self.reqs[rid] = (buf, int(count), int(src), int(tag), self.rank())
+        return rid, 0
+
+    def wait(self, req, stat, ierr):
+        if int(req) > 0:
+            buf, count, src, tag, me = self.reqs.pop(int(req))
+            flat = buf.reshape(-1, order="F")
+            assert np.shares_memory(flat, buf)
+            flat[:count] = self.mail[(src, me, tag)].get(timeout=60)
+        return (0,)
+
+    def install(self, gen):
+        M = gen.M
+        M.mpi_sum, M.mpi_max = "sum", "max"
+        ext = {"mpi_allreduce": (self.allreduce, [1, 6]), "mpi_allgatherv": (self.allgatherv, [8]),
+               "mpi_allgather": (self.allgather, [7]), "mpi_send": (self.send, []), "mpi_recv": (self.recv, [7]),
+               "mpi_isend": (self.isend, [6, 7]), "mpi_irecv": (self.irecv, [6, 7]), "mpi_wait": (self.wait, [2])}
+        for k, (fn, outs) in ext.items():
+            gen.externals[k] = fn
+            gen.ext_outs[k] = outs
+
+    def run(self, fn):
+        """fn(rank) on every task; returns the list of results (exceptions are re-raised)"""
+        res, errs = [None] * self.n, []
+
+        def body(r):
+            try:
+                res[r] = fn(r)
+            except BaseException as ex:      # noqa: BLE001
+                errs.append((r, ex))
+                self.bar.abort()
+        ths = []
+        for r in range(self.n):
+            t = self.threading.Thread(target=body, args=(r,))
+            t.rank = r
+            ths.append(t)
+            t.start()
+        for t in ths:
+            t.join()
+        if errs:
+            raise errs[0][1]
+        return res
+
+
+def fsils_multitask(probs, gnNo, Rs, Vs, cases, face_order):
+    """FSILS on len(probs) emulated MPI tasks: FSILS_LHS_CREATE (reordering + communication lists), FSILS_BC_CREATE
+    (shared faces), FSILS_COMMUV on R, FSILS_SOLVE.  Returns per case and task the solution in svFSI's local order."""
+    n = len(probs)
+    fg = fsils_gen()
+    emu = MpiEmu(n)
+    emu.install(fg)
+    FM, rt = fg.M, fg.rt
+    # translate everything once, single-threaded (the translator itself is not re-entrant)
+    for name in ("fsils_lhs_create", "fsils_bc_create", "fsils_commuv", "fsils_commus", "fsils_ls_create", "fsils_solve"):
+        fg.get(name)
+
+    def make_lhs(r):
+        p = probs[r]
+        commu = rt.new("fsils_commutype")
+        commu.foc, commu.masf, commu.master, commu.task, commu.tf, commu.ntasks, commu.comm = True, r == 0, 0, r, r + 1, n, 0
+        lhs = rt.new("fsils_lhstype")
+        fg.get("fsils_lhs_create")(lhs, commu, int(gnNo), int(p.rm.nNo), int(p.colPtr.size), p.rm.ltg.astype(np.int64),
+                                   p.rowPtr.astype(np.int64), p.colPtr.astype(np.int64), len(face_order))
+        for fi, fname in enumerate(face_order, start=1):
+            fa = p.faces[fname]
+            bc = FM.bc_type_neu if fa["bc"] == "Neu" else FM.bc_type_dir
+            v = None if fa["val"] is None else np.asfortranarray(np.asarray(fa["val"], dtype=np.float64).reshape(-1, 3).T.copy())
+            fg.get("fsils_bc_create")(lhs, fi, int(fa["gN"].size), 3, int(bc), fa["gN"].astype(np.int64), v)
+        return lhs
+
+    def task(r):
+        out = {}
+        lhs = make_lhs(r)
+        mp = np.array(lhs.map) - 1
+        out["map"], out["mynNo"], out["shnNo"], out["nReq"] = np.array(lhs.map), lhs.mynno, lhs.shnno, lhs.nreq
+        out["cS_iP"] = np.array([c.ip for c in lhs.cs], dtype=np.int64)
+        out["cS_ptr"] = np.concatenate([np.array(c.ptr) for c in lhs.cs]) if lhs.cs else np.zeros(0, dtype=np.int64)
+        out["cS_n"] = np.array([c.n for c in lhs.cs], dtype=np.int64)
+        # COMMU(R) as S/ALLFUN.f:514-533 does it: permute, FSILS_COMMUV, unpermute
+        tmp = np.zeros((4, probs[r].rm.nNo), order="F")
+        tmp[:, mp] = Rs[r].T
+        fg.get("fsils_commuv")(lhs, 4, tmp)
+        Rc = tmp[:, mp].T.copy()
+        out["Rc"] = Rc
+        for name, lst, prec, kw, res_out in cases:
+            lhs = make_lhs(r)
+            X, _, cnt = fsils_solve(fg, lhs, lst, 4, Rc, Vs[r], prec, incL=[1, 1, 1], res=[0.0, 0.0, res_out], **kw)
+            out[name + "_X"] = X
+            out[name + "_cnt"] = np.array([cnt[k] for k in sorted(cnt)], dtype=np.float64)
+            out["cnt_keys"] = np.array(sorted(cnt))
+        return out
+    return emu.run(task), FM
+
+
 def fsils_lhs(gen, gnNo, rowPtr, colPtr, faces):
     """FSILS_COMMU (one task, built by hand: FSILS_COMMU_CREATE only wraps MPI calls), FSILS_LHS_CREATE,
     FSILS_BC_CREATE.  faces: list of (gN 1-based, dof, bc_type, val[nNo_face, dof] | None)"""
@@ -351,6 +519,23 @@ def main():
         hs[name + "_kw"] = np.array(repr(dict(ls_type=int(lst), prec=int(prec), **kw)))
     hs["cnt_keys"] = np.array(sorted(cnt))
     np.savez_compressed(os.path.join(HERE, "ref_heat_lattice.npz"), **hs)
+    # ---- FSILS on 2 and 3 MPI tasks (emulated): the same pipe, partitioned as svFSI would (axial slabs)
+    from oracle import oracle as ora
+    for nparts in (2, 3):
+        mm, pp, _ = mesh.build_problem(2, 2, 4, nparts=nparts, L=2.0)
+        Rs, Vs = cm.oracle_assemble(pp)          # per-task element loop (pinned above to the reference, bit for bit)
+        mcases = [("gmres_res", FM.ls_type_gmres, FM.precond_fsils, dict(relTol=1e-6, absTol=1e-14, maxItr=10, dimKry=30), 0.7),
+                  ("ns", FM.ls_type_ns, FM.precond_fsils, dict(relTol=1e-3, absTol=1e-14, maxItr=10, dimKry=30), 0.0),
+                  ("bicgs_rcs", FM.ls_type_bicgs, FM.precond_rcs, dict(relTol=1e-6, absTol=1e-14, maxItr=300), 0.0)]
+        res, _ = fsils_multitask(pp, mm.nNo, Rs, Vs, mcases, cm.FACE_ORDER)
+        mt = dict(nparts=nparts, dims=np.array([2, 2, 4]), L=2.0)
+        for r, o in enumerate(res):
+            mt.update({f"t{r}_{k}": v for k, v in o.items()})
+        for name, lst, prec, kw, res_out in mcases:
+            mt[name + "_kw"] = np.array(repr(dict(ls_type=int(lst), prec=int(prec), res_out=res_out, **kw)))
+            c = dict(zip(res[0]["cnt_keys"], res[0][name + "_cnt"]))
+            print(f"  FSILS {nparts} tasks {name}: itr={c['ri_itr']:.0f} GM={c['gm_itr']:.0f} CG={c['cg_itr']:.0f} iNorm={c['ri_inorm']:.6e} fNorm={c['ri_fnorm']:.3e}")
+        np.savez_compressed(os.path.join(HERE, f"ref_fsils_{nparts}tasks.npz"), **mt)
     print(f"done in {time.time() - t0:.1f}s")
 
 

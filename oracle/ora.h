@@ -6,12 +6,18 @@
  * bench.py's cpu_baseline / --impl reference legs may load this library; the
  * product (svfsi_b200/csrc) never links, imports or calls it.
  *
- * PARITY UNPINNED: the reference ships no golden vectors, no tests and cannot
- * be compiled in this image (no Fortran compiler, no MPI) -- SURVEY.md 8c.  The
+ * PARITY PIN: the reference ships no golden vectors and no tests and cannot be
+ * COMPILED in this image (no Fortran compiler, no MPI) -- SURVEY.md 8c.  The
  * restatement follows the cited Fortran lines statement by statement and is
- * pinned instead by independent checks (tests/test_oracle_*.py): tangent vs
- * finite differences of the residual, SpMV vs SciPy BSR, solver residual
- * checks, 1-rank vs k-rank agreement.
+ * pinned to the reference's own SOURCE TEXT: oracle/refexec.py executes the
+ * reference's routines from /root/reference/Code/Source (one and several MPI
+ * tasks), tests/golden/make_ref_golden.py commits their results, and
+ * tests/test_reference_golden.py requires this library to reproduce them --
+ * it does, bit for bit (element loops, FSILS solvers, time integrator).  Not
+ * covered by that pin: a compiled run's compiler and MPI-library rounding
+ * (1e-16 effects).  Independent checks on top (tests/test_oracle_*.py):
+ * tangent vs finite differences of the residual, SpMV vs SciPy BSR, solver
+ * residual checks, 1-rank vs k-rank agreement.
  *
  * All citations are relative to /root/reference/Code/Source
  * (S/ = svFSI/, L/ = svFSILS/).

@@ -5,7 +5,8 @@
  * viscosity / no mesh motion: TET4 tables, GNN, FLUID3D_M, FLUID3D_C, HEATS3D,
  * LHSA, DOASSEM, CONSTRUCT_FLUID, CONSTRUCT_HEATS.  Statement order follows
  * the Fortran so that rounding is the same when compiled with
- * -ffp-contract=off.  PARITY UNPINNED (no reference golden vectors exist).
+ * -ffp-contract=off.  Pinned to the reference's source text (see ora.h): bit-identical
+ * to CONSTRUCT_FLUID / CONSTRUCT_HEATS / LHSA executed from /root/reference.
  */
 #include "ora.h"
 

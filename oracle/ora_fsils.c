@@ -11,7 +11,7 @@
  * every SPMD statement becomes a loop over ranks; collectives (halo sum,
  * allreduce) are done in place between the per-rank arrays.  Control flow in
  * FSILS depends only on all-reduced scalars, so lock-step execution is exact.
- * PARITY UNPINNED (no reference golden vectors exist; see ora.h).
+ * Pinned to the reference's source text on 1, 2 and 3 MPI tasks (see ora.h).
  */
 #include "ora.h"
 

@@ -1,7 +1,8 @@
 """ctypes front-end of the CPU oracle (oracle/*.c) -- TEST INFRASTRUCTURE ONLY.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
-import this module.  It is the checker, never the product path.  PARITY UNPINNED: see ora.h.
+import this module.  It is the checker, never the product path.  How it is pinned to the reference: see ora.h
+(oracle/refexec.py + tests/golden/make_ref_golden.py + tests/test_reference_golden.py).
 """
 from __future__ import annotations
 

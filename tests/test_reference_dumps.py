@@ -4,8 +4,8 @@
 characters.  (ii) whenever a REAL dump exists (tests/golden/ref_Val_R_<nx>x<ny>x<nz>_<cTS>_<itr>_<rank>, produced
 off-box by baseline/run_reference.sh with SVFSI_DUMP=1 on the case of baseline/make_reference_case.py), the oracle
 -- and with -m gpu the CUDA path -- must reproduce it: R within 1e-12, Val within the printed precision.
-No such file can be produced in this image (no Fortran compiler): until one is committed the parity of this
-repo is UNPINNED against the real svFSI and (ii) is skipped."""
+No such file can be produced in this image (no Fortran compiler): until one is committed (ii) is skipped and the
+pin is the reference's source text executed by oracle/refexec.py (tests/test_reference_golden.py), not a compiled run."""
 import glob
 import os
 import re
@@ -54,7 +54,7 @@ def _case_of(path):
     return tuple(int(v) for v in mm.groups()) if mm else None
 
 
-@pytest.mark.skipif(not GOLD, reason="no PDEBUGVALR dump of the real svFSI under tests/golden/ (parity unpinned)")
+@pytest.mark.skipif(not GOLD, reason="no PDEBUGVALR dump of a compiled svFSI under tests/golden/")
 @pytest.mark.parametrize("path", GOLD)
 def test_oracle_reproduces_the_reference_dump(path):
     nx, ny, nz, cTS, itr, rank = _case_of(path)
@@ -70,7 +70,7 @@ def test_oracle_reproduces_the_reference_dump(path):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not GOLD, reason="no PDEBUGVALR dump of the real svFSI under tests/golden/ (parity unpinned)")
+@pytest.mark.skipif(not GOLD, reason="no PDEBUGVALR dump of a compiled svFSI under tests/golden/")
 @pytest.mark.parametrize("path", GOLD)
 def test_gpu_reproduces_the_reference_dump(path, gpu_lib):
     from svfsi_b200 import api

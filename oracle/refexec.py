@@ -576,6 +576,18 @@ class Runtime:
         return abs(a) if b >= 0 else -abs(a)
 
     @staticmethod
+    def f_btest(i, pos):
+        return bool((int(i) >> int(pos)) & 1)
+
+    @staticmethod
+    def f_ibset(i, pos):
+        return int(i) | (1 << int(pos))
+
+    @staticmethod
+    def f_ibclr(i, pos):
+        return int(i) & ~(1 << int(pos))
+
+    @staticmethod
     def f_int(x, kind=None):
         return int(x)
 
@@ -679,7 +691,7 @@ INTRINSICS = {
     "transpose": "_rt.f_transpose", "maxval": "_rt.f_maxval", "minval": "_rt.f_minval", "exp": "_rt.f_exp",
     "log": "_rt.f_log", "cos": "math.cos", "sin": "math.sin", "tan": "math.tan", "atan": "math.atan",
     "atan2": "math.atan2", "acos": "math.acos", "asin": "math.asin", "tanh": "math.tanh", "cosh": "math.cosh",
-    "sinh": "math.sinh", "log10": "math.log10", "floor": "math.floor", "trim": "str", "adjustl": "str", "len": "len",
+    "sinh": "math.sinh", "log10": "math.log10", "btest": "_rt.f_btest", "ibset": "_rt.f_ibset", "ibclr": "_rt.f_ibclr", "floor": "math.floor", "trim": "str", "adjustl": "str", "len": "len",
 }
 
 # ------------------------------------------------------------------------------------------------ declarations

@@ -38,7 +38,7 @@ def svfsi_gen():
     for h in ("FSILS_TYPEDEF.h", "FSILS_STRUCT.h"):          # eqType carries an FSILS_lsType
         lib.add_include(os.path.join(LS, h))
     for f in ("CONSTS.f", "TYPEMOD.f", "UTIL.f", "MOD.f", "ALLFUN.f", "NN.f", "FS.f", "FLUID.f", "HEATS.f", "LHSA.f",
-              "EQASSEM.f", "PIC.f"):
+              "EQASSEM.f", "PIC.f", "SETBC.f"):
         lib.add_file(os.path.join(S, f))
 
     def dgesv(n, nrhs, a, lda, ipiv, b, ldb, info):
@@ -468,6 +468,28 @@ def main():
         print(f"  face {key}: nEl={fIEN.shape[0]} flux={flux:.6e} |dR|={np.abs(R1 - R0).max():.3e} |dVal|={np.abs(V1 - V0).max():.3e}")
         fc.update({f"{key}_gN": gN, f"{key}_fIEN": fIEN, f"{key}_gE": gE, f"{key}_hg": hg, f"{key}_Yg": Yg2,
                    f"{key}_R0": R0, f"{key}_V0": V0, f"{key}_R1": R1, f"{key}_V1": V1, f"{key}_flux": flux})
+    # resistance outlet as svFSI applies it: SETBCNEUL (S/SETBC.f:251-311) -> h = r * Integ(lFa, Yn, 1, 3), hg = -h gx,
+    # BASSEMNEUBC -- on top of a fresh element loop
+    gN, fIEN, gE = cm.local_face(m, p.rm, "outlet")
+    R0, V0, _ = element_loop(gen, p.rm.x, p.rm.IEN, p.rowPtr, p.colPtr, p.Ag, p.Yg, cm.RHO, cm.MU, cm.F, cm.DT,
+                             cm.GA["af"], cm.GA["am"], cm.GA["gam"])
+    M, rt = gen.M, gen.rt
+    lFa = rt.new("facetype")
+    lFa.im, lFa.enon, lFa.nel, lFa.nno = 1, 3, int(fIEN.shape[0]), int(gN.size)
+    lFa.ien, lFa.ge, lFa.gn = np.asfortranarray(fIEN.T.astype(np.int64)), gE.astype(np.int64), gN.astype(np.int64)
+    gen.get("selecteleb")(M.msh[0], lFa)
+    lBc = rt.new("bctype")
+    lBc.btype = (1 << M.btype_neu) | (1 << M.btype_res)
+    lBc.r, lBc.g, lBc.flwp = 55.0, 0.0, False
+    lBc.gx = np.ones(gN.size)
+    M.eq[0].dmn[0].prop[M.backflow_stab - 1] = 0.2
+    M.ibflag = False
+    Ynf = np.asfortranarray(p.Yg.T.copy())
+    M.yn = Ynf                                     # the flux is taken from Yn (here: the same state)
+    gen.get("setbcneul")(lBc, lFa, Ynf, np.zeros_like(Ynf))
+    fc.update(res_r=55.0, res_gN=gN, res_fIEN=fIEN, res_gE=gE, res_Yg=p.Yg, res_R0=R0, res_V0=V0, res_R1=M.r.T.copy(),
+              res_V1=M.val.T.copy())
+    print(f"  SETBCNEUL resistance: |dR|={np.abs(M.r.T - R0).max():.3e}")
     fc.update({"tab_" + k: v for k, v in ftab.items()})
     fc.update(bfStab=0.2, rho=cm.RHO, af=cm.GA["af"], gam=cm.GA["gam"], dt=cm.DT)
     np.savez_compressed(os.path.join(HERE, "ref_face_lattice.npz"), **fc)

@@ -505,6 +505,32 @@ def main():
         print(f"  PIC {tag}: book(itr, ok, iNorm, pNorm, cEq)={o['picc_book']}")
         pc.update({f"{tag}_{k}": v for k, v in o.items()})
         pc[f"{tag}_in"] = np.array([iNorm, tol, 1e-8, 1, 10, itr0])
+    # strong Dirichlet: SETBCDIR + SETBCDIRL (S/SETBC.f:39-228), a steady parabolic inlet along the face normals and a
+    # no-slip wall, on the predictor's An / Yn
+    M, rt = gen.M, gen.rt
+    faces, bcs = [], []
+    for k, (fname, g) in enumerate((("inlet", -7.5), ("wall", 0.0)), start=1):
+        gN = p.faces[fname]["gN"]
+        fa = rt.new("facetype")
+        fa.nno, fa.gn = int(gN.size), gN.astype(np.int64)
+        nV = rng.standard_normal((3, gN.size)); nV /= np.linalg.norm(nV, axis=0)
+        fa.nv = np.asfortranarray(nV)
+        bc = rt.new("bctype")
+        bc.btype = (1 << M.btype_dir) | (1 << M.btype_std)
+        bc.weakdir, bc.ifa, bc.im, bc.g = False, k, 1, g
+        bc.edrn = np.zeros(int(M.maxnsd), dtype=np.int64)
+        bc.gx = rng.uniform(0.0, 1.0, gN.size)
+        faces.append(fa); bcs.append(bc)
+        pc.update({f"dir{k}_gN": gN, f"dir{k}_nV": nV.T.copy(), f"dir{k}_gx": np.array(bc.gx), f"dir{k}_g": g})
+    M.msh[0].fa = rx.FList(faces)
+    M.eq[0].bc, M.eq[0].nbc, M.neq = rx.FList(bcs), 2, 1
+    M.eq[0].s, M.eq[0].e, M.eq[0].dof, M.eq[0].phys = 1, 4, 4, M.phys_fluid
+    lA, lY, lD = (np.asfortranarray(rng.standard_normal((4, nN))) for _ in range(3))
+    pc.update(dir_A0=lA.T.copy(), dir_Y0=lY.T.copy())
+    gen.get("setbcdir")(lA, lY, lD)
+    pc.update(dir_A1=lA.T.copy(), dir_Y1=lY.T.copy())
+    M.eq[0].nbc = 0
+    print(f"  SETBCDIR: {int((pc['dir_A1'] != pc['dir_A0']).any(axis=1).sum())} nodes overwritten")
     np.savez_compressed(os.path.join(HERE, "ref_pic.npz"), **pc)
 
     # ---- case B: irregular mesh (Delaunay box, shuffled elements), body force and nodal body force Bf

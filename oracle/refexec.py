@@ -576,6 +576,19 @@ class Runtime:
         return abs(a) if b >= 0 else -abs(a)
 
     @staticmethod
+    def f_selected_real_kind(p=15, r=307, radix=2):
+        return 4 if int(p) <= 6 else (8 if int(p) <= 15 else 16)
+
+    @staticmethod
+    def f_selected_int_kind(r):
+        r = int(r)
+        return 1 if r <= 2 else (2 if r <= 4 else (4 if r <= 9 else 8))
+
+    @staticmethod
+    def f_kind(x):
+        return 8 if isinstance(x, float) else 4
+
+    @staticmethod
     def f_btest(i, pos):
         return bool((int(i) >> int(pos)) & 1)
 
@@ -691,7 +704,8 @@ INTRINSICS = {
     "transpose": "_rt.f_transpose", "maxval": "_rt.f_maxval", "minval": "_rt.f_minval", "exp": "_rt.f_exp",
     "log": "_rt.f_log", "cos": "math.cos", "sin": "math.sin", "tan": "math.tan", "atan": "math.atan",
     "atan2": "math.atan2", "acos": "math.acos", "asin": "math.asin", "tanh": "math.tanh", "cosh": "math.cosh",
-    "sinh": "math.sinh", "log10": "math.log10", "btest": "_rt.f_btest", "ibset": "_rt.f_ibset", "ibclr": "_rt.f_ibclr", "floor": "math.floor", "trim": "str", "adjustl": "str", "len": "len",
+    "sinh": "math.sinh", "log10": "math.log10", "btest": "_rt.f_btest", "selected_real_kind": "_rt.f_selected_real_kind",
+    "selected_int_kind": "_rt.f_selected_int_kind", "kind": "_rt.f_kind", "ibset": "_rt.f_ibset", "ibclr": "_rt.f_ibclr", "floor": "math.floor", "trim": "str", "adjustl": "str", "len": "len",
 }
 
 # ------------------------------------------------------------------------------------------------ declarations

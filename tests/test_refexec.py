@@ -235,3 +235,37 @@ def test_unknown_procedures_fail_only_when_reached(tmp_path):
     assert s(0, 0) == (1,)
     with pytest.raises(NotImplementedError):
         s(1, 0)
+
+
+REF = "/root/reference/Code/Source"
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir(REF), reason="the reference tree is not on this box")
+def test_reference_routines_with_known_answers():
+    """routines of the reference whose results are known independently, executed from their source: Gaussian
+    elimination (svFSILS/GE.f) against LAPACK, 3x3 inverse / determinant / trace (svFSI/MATFUN.f) against NumPy,
+    the scalar product and the cross product of svFSI/UTIL.f"""
+    import os
+    lib = rx.Library()
+    for h in ("FSILS_TYPEDEF.h", "FSILS_STRUCT.h"):
+        lib.add_include(os.path.join(REF, "svFSILS", h))
+    lib.add_file(os.path.join(REF, "svFSILS", "GE.f"))
+    for f in ("CONSTS.f", "TYPEMOD.f", "UTIL.f", "MATFUN.f"):
+        lib.add_file(os.path.join(REF, "svFSI", f))
+    g = rx.CodeGen(lib)
+    rng = np.random.default_rng(0)
+    n = 7
+    A = rng.standard_normal((n, n)) + n * np.eye(n)
+    b = rng.standard_normal(n)
+    B = b.copy()
+    ok = g.get("ge")(n, n, np.asfortranarray(A), B)
+    assert ok and np.allclose(B, np.linalg.solve(A, b), rtol=1e-12, atol=1e-14)
+    M3 = rng.standard_normal((3, 3)) + 2 * np.eye(3)
+    inv = g.get("mat_inv")(np.asfortranarray(M3), 3)
+    assert np.allclose(inv, np.linalg.inv(M3), rtol=1e-12, atol=1e-14)
+    assert abs(g.get("mat_det")(np.asfortranarray(M3), 3) - np.linalg.det(M3)) <= 1e-12 * abs(np.linalg.det(M3))
+    assert abs(g.get("mat_trace")(np.asfortranarray(M3), 3) - np.trace(M3)) <= 1e-14
+    u, v = rng.standard_normal(5), rng.standard_normal(5)
+    assert abs(g.get("norms")(u, v) - float(u @ v)) <= 1e-14
+    V = np.asfortranarray(rng.standard_normal((3, 2)))
+    assert np.allclose(g.get("cross")(V), np.cross(V[:, 0], V[:, 1]), rtol=1e-14, atol=1e-15)

@@ -176,8 +176,6 @@ def tokenize(s):
             if t.endswith(".") and any(s.startswith(d[1:], i) for d in _DOTOPS):
                 t = t[:-1]
                 i -= 1
-            elif re.fullmatch(r"\d+\.[ed]", t) is None and "." in t:
-                pass
             toks.append(("num", t))
         elif m.group("name"):
             toks.append(("name", m.group("name")))
@@ -1292,8 +1290,6 @@ class Scope:
             return f"({self.expr(args[0])} is not None)"
         if n == "allocated":
             return f"({self.expr(args[0])} is not None)"
-        if n == "iszero" and "iszero" not in self.gen.lib.units and "iszero" not in self.gen.externals:
-            raise KeyError("ISZERO is not indexed")
         if self.is_proc(n) and (v is None or not v.dummy):
             return self.funcall(n, args)       # (a scalar declaration of the same name is the function's type)
         if v is not None and v.dummy and not v.is_array:

@@ -401,7 +401,6 @@ def main():
     from svfsi_b200 import mesh
     t0 = time.time()
     gen = svfsi_gen()
-    out = {}
     # ---- case A: 2x2x3 Kuhn-lattice pipe (the mesh family of the parity tests)
     m, probs, _ = mesh.build_problem(2, 2, 3, nparts=1, L=1.5)
     p = probs[0]
@@ -568,7 +567,6 @@ def main():
     hs["cnt_keys"] = np.array(sorted(cnt))
     np.savez_compressed(os.path.join(HERE, "ref_heat_lattice.npz"), **hs)
     # ---- FSILS on 2 and 3 MPI tasks (emulated): the same pipe, partitioned as svFSI would (axial slabs)
-    from oracle import oracle as ora
     for nparts in (2, 3):
         mm, pp, _ = mesh.build_problem(2, 2, 4, nparts=nparts, L=2.0)
         Rs, Vs = cm.oracle_assemble(pp)          # per-task element loop (pinned above to the reference, bit for bit)

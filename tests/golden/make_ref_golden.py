@@ -566,15 +566,15 @@ def main():
         hs[name + "_kw"] = np.array(repr(dict(ls_type=int(lst), prec=int(prec), **kw)))
     hs["cnt_keys"] = np.array(sorted(cnt))
     np.savez_compressed(os.path.join(HERE, "ref_heat_lattice.npz"), **hs)
-    # ---- FSILS on 2 and 3 MPI tasks (emulated): the same pipe, partitioned as svFSI would (axial slabs)
-    for nparts in (2, 3):
-        mm, pp, _ = mesh.build_problem(2, 2, 4, nparts=nparts, L=2.0)
+    # ---- FSILS on 2, 3 and 4 MPI tasks (emulated): axial slabs, and quadrant blocks whose axis nodes belong to all four tasks
+    for nparts, dims, part in ((2, (2, 2, 4), "slabs"), (3, (2, 2, 4), "slabs"), (4, (4, 4, 2), "blocks")):
+        mm, pp, _ = mesh.build_problem(*dims, nparts=nparts, L=2.0, partition=part)
         Rs, Vs = cm.oracle_assemble(pp)          # per-task element loop (pinned above to the reference, bit for bit)
         mcases = [("gmres_res", FM.ls_type_gmres, FM.precond_fsils, dict(relTol=1e-6, absTol=1e-14, maxItr=10, dimKry=30), 0.7),
                   ("ns", FM.ls_type_ns, FM.precond_fsils, dict(relTol=1e-3, absTol=1e-14, maxItr=10, dimKry=30), 0.0),
                   ("bicgs_rcs", FM.ls_type_bicgs, FM.precond_rcs, dict(relTol=1e-6, absTol=1e-14, maxItr=300), 0.0)]
         res, _ = fsils_multitask(pp, mm.nNo, Rs, Vs, mcases, cm.FACE_ORDER)
-        mt = dict(nparts=nparts, dims=np.array([2, 2, 4]), L=2.0)
+        mt = dict(nparts=nparts, dims=np.array(dims), L=2.0, partition=np.array(part))
         for r, o in enumerate(res):
             mt.update({f"t{r}_{k}": v for k, v in o.items()})
         for name, lst, prec, kw, res_out in mcases:

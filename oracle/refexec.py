@@ -383,7 +383,11 @@ class FObj:
 
 
 class FList(list):
-    """rank-1 array of derived-type instances; `x%comp` on the array maps over its elements"""
+    """rank-1 array of derived-type instances; `x%comp` on the array (or on a section of it) maps over its elements"""
+    def __getitem__(self, i):
+        r = list.__getitem__(self, i)
+        return FList(r) if isinstance(i, slice) else r
+
     def __getattr__(self, name):
         if name.startswith("__"):
             raise AttributeError(name)
@@ -587,6 +591,10 @@ class Runtime:
         return 8 if isinstance(x, float) else 4
 
     @staticmethod
+    def f_isnan(x):
+        return bool(np.isnan(x))
+
+    @staticmethod
     def f_btest(i, pos):
         return bool((int(i) >> int(pos)) & 1)
 
@@ -702,7 +710,7 @@ INTRINSICS = {
     "transpose": "_rt.f_transpose", "maxval": "_rt.f_maxval", "minval": "_rt.f_minval", "exp": "_rt.f_exp",
     "log": "_rt.f_log", "cos": "math.cos", "sin": "math.sin", "tan": "math.tan", "atan": "math.atan",
     "atan2": "math.atan2", "acos": "math.acos", "asin": "math.asin", "tanh": "math.tanh", "cosh": "math.cosh",
-    "sinh": "math.sinh", "log10": "math.log10", "btest": "_rt.f_btest", "selected_real_kind": "_rt.f_selected_real_kind",
+    "sinh": "math.sinh", "log10": "math.log10", "btest": "_rt.f_btest", "isnan": "_rt.f_isnan", "selected_real_kind": "_rt.f_selected_real_kind",
     "selected_int_kind": "_rt.f_selected_int_kind", "kind": "_rt.f_kind", "ibset": "_rt.f_ibset", "ibclr": "_rt.f_ibclr", "floor": "math.floor", "trim": "str", "adjustl": "str", "len": "len",
 }
 

@@ -532,6 +532,28 @@ def main():
     print(f"  SETBCDIR: {int((pc['dir_A1'] != pc['dir_A0']).any(axis=1).sum())} nodes overwritten")
     np.savez_compressed(os.path.join(HERE, "ref_pic.npz"), **pc)
 
+    # ---- RCR (Windkessel) outlets: RCR_Integ_X (S/SETBC.f:1292-1372), two faces, three consecutive time steps
+    cpl = rt.new("cplbctype")
+    par = [(121.0, 1.5e-4, 1212.0, 0.0, 300.0), (80.0, 3.0e-4, 900.0, 50.0, 120.0)]      # Rp, C, Rd, Pd, X0
+    cpl.nfa = len(par)
+    cpl.fa = rx.FList(rt.new("cplfacetype") for _ in par)
+    for fa, (Rp, Cc, Rd, Pd, X0) in zip(cpl.fa, par):
+        fa.rcr.rp, fa.rcr.c, fa.rcr.rd, fa.rcr.pd = Rp, Cc, Rd, Pd
+    cpl.xo = np.array([q[4] for q in par]); cpl.xn = np.zeros(len(par)); cpl.xp = np.zeros(len(par) + 1)
+    M.cplbc, M.dt = cpl, 2.5e-3
+    rc = dict(par=np.array(par), dt=M.dt)
+    Q = np.array([[1.0, 0.4], [3.5, 1.1], [2.0, -0.3], [0.5, 0.2]])
+    for k in range(3):
+        M.time = (k + 1) * M.dt
+        for i, fa in enumerate(cpl.fa):
+            fa.qo, fa.qn = float(Q[k, i]), float(Q[k + 1, i])
+        (istat,) = gen.get("rcr_integ_x")(0)
+        rc[f"s{k}_xo"], rc[f"s{k}_xn"], rc[f"s{k}_y"] = np.array(cpl.xo), np.array(cpl.xn), np.array([fa.y for fa in cpl.fa])
+        rc[f"s{k}_Q"], rc[f"s{k}_time"] = Q[k:k + 2].copy(), M.time
+        cpl.xo = np.array(cpl.xn)
+        print(f"  RCR step {k}: istat={istat} X={rc[f's{k}_xn']} y={rc[f's{k}_y']}")
+    np.savez_compressed(os.path.join(HERE, "ref_rcr.npz"), **rc)
+
     # ---- case B: irregular mesh (Delaunay box, shuffled elements), body force and nodal body force Bf
     x, IEN = un.delaunay_box(n=70, seed=7)
     rowPtr, colPtr, Ag, Yg = un.problem(x, IEN)

@@ -350,7 +350,11 @@ def fsils_multitask(probs, gnNo, Rs, Vs, cases, face_order):
             out[name + "_cnt"] = np.array([cnt[k] for k in sorted(cnt)], dtype=np.float64)
             out["cnt_keys"] = np.array(sorted(cnt))
         return out
+    MT_GEN[0] = fg
     return emu.run(task), FM
+
+
+MT_GEN = [None]
 
 
 def fsils_lhs(gen, gnNo, rowPtr, colPtr, faces):
@@ -604,6 +608,18 @@ def main():
             c = dict(zip(res[0]["cnt_keys"], res[0][name + "_cnt"]))
             print(f"  FSILS {nparts} tasks {name}: itr={c['ri_itr']:.0f} GM={c['gm_itr']:.0f} CG={c['cg_itr']:.0f} iNorm={c['ri_inorm']:.6e} fNorm={c['ri_fnorm']:.3e}")
         np.savez_compressed(os.path.join(HERE, f"ref_fsils_{nparts}tasks.npz"), **mt)
+    # ---- manifest: every procedure of the reference that was translated from its source for the vectors above
+    lines = set()
+    for g in (gen, fg, MT_GEN[0]):
+        for name in g.done:
+            u = g.lib.units[name]
+            lines.add(f"{os.path.relpath(u.file, os.path.join(REF, 'Code', 'Source'))} : {name.upper()}"
+                      + (f" (+ internal {', '.join(i.name.upper() for i in u.internal)})" if u.internal else ""))
+    with open(os.path.join(HERE, "ref_routines.txt"), "w") as fh:
+        fh.write("# procedures of /root/reference/Code/Source that oracle/refexec.py translated from their source text for the\n"
+                 "# golden vectors (a procedure is translated when a translated caller references it; the branches taken by the\n"
+                 "# cases of tests/golden/make_ref_golden.py were executed).  file : procedure\n")
+        fh.write("\n".join(sorted(lines)) + "\n")
     print(f"done in {time.time() - t0:.1f}s")
 
 

@@ -590,6 +590,15 @@ def main():
         hs[name + "_X"] = X[:, 0]
         hs[name + "_cnt"] = np.array([cnt[k] for k in sorted(cnt)], dtype=np.float64)
         hs[name + "_kw"] = np.array(repr(dict(ls_type=int(lst), prec=int(prec), **kw)))
+    # CGRADV (L/CGRAD.f:52-123): a symmetric positive definite system with 3 dofs per node = the heat matrix x I3
+    V3 = np.zeros((Vh.shape[0], 9)); V3[:, 0] = V3[:, 4] = V3[:, 8] = Vh[:, 0]
+    R3 = np.random.default_rng(23).standard_normal((p.rm.nNo, 3))
+    lhs = fsils_lhs(fg, p.rm.nNo, p.rowPtr, p.colPtr, [(p.faces[n]["gN"], 3, FM.bc_type_dir, None) for n in ("inlet", "outlet")])
+    kw = dict(relTol=1e-8, absTol=1e-14, maxItr=200)
+    X, Vs, cnt = fsils_solve(fg, lhs, FM.ls_type_cg, 3, R3, V3, FM.precond_fsils, incL=[1, 1], res=[0.0, 0.0], **kw)
+    print(f"  FSILS CGRADV dof=3: itr={cnt['ri_itr']:.0f} suc={cnt['ri_suc']} iNorm={cnt['ri_inorm']:.6e} fNorm={cnt['ri_fnorm']:.3e}")
+    hs.update(cgv_R=R3, cgv_Val=V3, cgv_X=X, cgv_cnt=np.array([cnt[k] for k in sorted(cnt)], dtype=np.float64),
+              cgv_kw=np.array(repr(dict(ls_type=int(FM.ls_type_cg), prec=int(FM.precond_fsils), **kw))))
     hs["cnt_keys"] = np.array(sorted(cnt))
     np.savez_compressed(os.path.join(HERE, "ref_heat_lattice.npz"), **hs)
     # ---- FSILS on 2, 3 and 4 MPI tasks (emulated): axial slabs, and quadrant blocks whose axis nodes belong to all four tasks

@@ -38,8 +38,10 @@ def svfsi_gen():
     for h in ("FSILS_TYPEDEF.h", "FSILS_STRUCT.h"):          # eqType carries an FSILS_lsType
         lib.add_include(os.path.join(LS, h))
     for f in ("CONSTS.f", "TYPEMOD.f", "UTIL.f", "MOD.f", "ALLFUN.f", "NN.f", "FS.f", "FLUID.f", "HEATS.f", "LHSA.f",
-              "EQASSEM.f", "PIC.f", "SETBC.f"):
+              "EQASSEM.f", "PIC.f", "SETBC.f", "BAFINI.f"):
         lib.add_file(os.path.join(S, f))
+    for f in ("LHS.f", "BC.f", "INCOMMU.f"):                 # FSILSINI calls FSILS_BC_CREATE on COMMOD's lhs
+        lib.add_file(os.path.join(LS, f))
 
     def dgesv(n, nrhs, a, lda, ipiv, b, ldb, info):
         """LAPACK DGESV (the reference links LAPACK): A <- LU, B <- solution, INFO handed back"""
@@ -63,6 +65,9 @@ def svfsi_gen():
             return v
     gen.M.cm = Cm()
     gen.M.ikind, gen.M.rkind = 4, 8     # kind numbers (only ever passed as KIND= arguments)
+    for n in ("mpint", "mpreal", "mplog", "mpchar", "mpi_sum", "mpi_max", "mpi_min", "stdout"):
+        setattr(gen.M, n, 0)
+    gen.M.mpsts = 6
     return gen
 
 
@@ -496,6 +501,33 @@ def main():
     fc.update({"tab_" + k: v for k, v in ftab.items()})
     fc.update(bfStab=0.2, rho=cm.RHO, af=cm.GA["af"], gam=cm.GA["gam"], dt=cm.DT)
     np.savez_compressed(os.path.join(HERE, "ref_face_lattice.npz"), **fc)
+
+    # ---- FSILSINI (S/BAFINI.f:468-583): what svFSI hands to FSILS_BC_CREATE for a Dirichlet face (zero mask) and for a
+    # resistance face (val = int N n dGamma), on COMMOD's lhs
+    M, rt = gen.M, gen.rt
+    commu = rt.new("fsils_commutype")
+    commu.foc, commu.masf, commu.master, commu.task, commu.tf, commu.ntasks, commu.comm = True, True, 0, 0, 1, 1, 0
+    M.lhs = rt.new("fsils_lhstype")
+    gen.get("fsils_lhs_create")(M.lhs, commu, int(p.rm.nNo), int(p.rm.nNo), int(p.colPtr.size),
+                                np.arange(1, p.rm.nNo + 1, dtype=np.int64), p.rowPtr.astype(np.int64),
+                                p.colPtr.astype(np.int64), 3)
+    ini, lsPtr = {}, 0
+    for fname in cm.FACE_ORDER:
+        gN, fIEN, gE = cm.local_face(m, p.rm, fname)
+        lFa = rt.new("facetype")
+        lFa.im, lFa.enon, lFa.nel, lFa.nno = 1, 3, int(fIEN.shape[0]), int(gN.size)
+        lFa.ien, lFa.ge, lFa.gn = np.asfortranarray(fIEN.T.astype(np.int64)), gE.astype(np.int64), gN.astype(np.int64)
+        gen.get("selecteleb")(M.msh[0], lFa)
+        lBc = rt.new("bctype")
+        lBc.weakdir = False
+        lBc.edrn = np.zeros(int(M.maxnsd), dtype=np.int64)
+        lBc.btype = ((1 << M.btype_neu) | (1 << M.btype_res)) if fname == "outlet" else ((1 << M.btype_dir) | (1 << M.btype_std))
+        (lsPtr,) = gen.get("fsilsini")(lBc, lFa, lsPtr)
+        f = M.lhs.face[lsPtr - 1]
+        ini.update({f"{fname}_lsPtr": lsPtr, f"{fname}_bGrp": f.bgrp, f"{fname}_glob": np.array(f.glob),
+                    f"{fname}_val": np.array(f.val).T.copy(), f"{fname}_gN": gN})
+        print(f"  FSILSINI {fname}: lsPtr={lsPtr} bGrp={f.bgrp} nNo={f.nno} |val|={np.abs(f.val).max():.4e}")
+    np.savez_compressed(os.path.join(HERE, "ref_fsilsini_lattice.npz"), **ini)
 
     # ---- generalised-alpha predictor / initiator / corrector (S/PIC.f) on random states
     rng = np.random.default_rng(17)

@@ -1377,10 +1377,10 @@ class Scope:
             if v.dummy:
                 continue
             if u.kind == "function" and name == u.result:
-                if v.is_array:
+                if v.is_array and not v.alloc and all(hi not in (":", "*") for _, hi in v.dims):
                     L.append(f"{pad1}_result = _rt.alloc({v.kind!r}, ({self._dims(v)},))")
                 else:
-                    L.append(f"{pad1}_result = None")
+                    L.append(f"{pad1}_result = None")       # scalar, or an ALLOCATABLE result the body allocates
                 continue
             L.append(pad1 + self._local_init(v))
         # internal procedures (closures over this frame)

@@ -359,6 +359,39 @@ def fsils_multitask(probs, gnNo, Rs, Vs, cases, face_order):
     return emu.run(task), FM
 
 
+def svfsi_commu_multitask(probs, gnNo, Rs):
+    """COMMU(R) exactly as svFSI does it (S/ALLFUN.f:514-533: U = MKC(U); FSILS_COMMUV; MKCI(U)) on len(probs) emulated
+    MPI tasks, each with its own COMMOD (one translator per task: COMMOD is process-global state in the reference)"""
+    n = len(probs)
+    emu = MpiEmu(n)
+    gens = []
+    for r in range(n):
+        g = svfsi_gen()
+        emu.install(g)
+
+        class Cm:
+            @staticmethod
+            def seq():
+                return False
+        g.M.cm = Cm()
+        for name in ("fsils_lhs_create", "commuv"):
+            g.get(name)
+        gens.append(g)
+
+    def task(r):
+        g, p = gens[r], probs[r]
+        M, rt = g.M, g.rt
+        commu = rt.new("fsils_commutype")
+        commu.foc, commu.masf, commu.master, commu.task, commu.tf, commu.ntasks, commu.comm = True, r == 0, 0, r, r + 1, n, 0
+        M.lhs = rt.new("fsils_lhstype")
+        g.get("fsils_lhs_create")(M.lhs, commu, int(gnNo), int(p.rm.nNo), int(p.colPtr.size), p.rm.ltg.astype(np.int64),
+                                  p.rowPtr.astype(np.int64), p.colPtr.astype(np.int64), 0)
+        U = np.asfortranarray(Rs[r].T.copy())
+        g.get("commuv")(U)
+        return U.T.copy()
+    return emu.run(task)
+
+
 MT_GEN = [None]
 
 
@@ -642,6 +675,10 @@ def main():
                   ("bicgs_rcs", FM.ls_type_bicgs, FM.precond_rcs, dict(relTol=1e-6, absTol=1e-14, maxItr=300), 0.0)]
         res, _ = fsils_multitask(pp, mm.nNo, Rs, Vs, mcases, cm.FACE_ORDER)
         mt = dict(nparts=nparts, dims=np.array(dims), L=2.0, partition=np.array(part))
+        Rc_allfun = svfsi_commu_multitask(pp, mm.nNo, Rs)       # svFSI's own COMMU wrapper around FSILS_COMMUV
+        for r in range(nparts):
+            assert np.array_equal(Rc_allfun[r], res[r]["Rc"]), "COMMUV (ALLFUN) differs from permute + FSILS_COMMUV"
+            mt[f"t{r}_Rc_allfun"] = Rc_allfun[r]
         for r, o in enumerate(res):
             mt.update({f"t{r}_{k}": v for k, v in o.items()})
         for name, lst, prec, kw, res_out in mcases:

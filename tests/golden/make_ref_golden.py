@@ -485,6 +485,16 @@ def main():
         sol[name + "_cnt"] = np.array([cnt[k] for k in sorted(cnt)], dtype=np.float64)
         sol[name + "_kw"] = np.array(repr(dict(ls_type=int(lst), prec=int(prec), res_out=res_out, **kw)))
     sol["cnt_keys"] = np.array(sorted(cnt))
+    # FSILS_LS_CREATE defaults (L/LS.f:69-95) of every solver type: relTol, absTol, mItr, sD of RI / GM / CG
+    for tname in ("ns", "gmres", "cg", "bicgs"):
+        ls = fg.rt.new("fsils_lstype")
+        for sub in ("ri", "gm", "cg"):          # poison what FSILS_LS_CREATE does not set, so that it shows
+            o = getattr(ls, sub)
+            o.reltol = o.abstol = float("nan"); o.mitr = o.sd = -1
+        fg.get("fsils_ls_create")(ls, int(getattr(FM, "ls_type_" + tname)))
+        sol["lsdef_" + tname] = np.array([[getattr(ls, sub).reltol, getattr(ls, sub).abstol, getattr(ls, sub).mitr,
+                                           getattr(ls, sub).sd] for sub in ("ri", "gm", "cg")], dtype=np.float64)
+        sol["lstype_" + tname] = int(getattr(FM, "ls_type_" + tname))
     np.savez_compressed(os.path.join(HERE, "ref_fsils_lattice.npz"), **sol)
 
     # ---- LHSA (S/LHSA.f:40-264): the block-CSR pattern of the mesh the element loop just ran on

@@ -40,8 +40,9 @@ def svfsi_gen():
     for f in ("CONSTS.f", "TYPEMOD.f", "UTIL.f", "MOD.f", "ALLFUN.f", "NN.f", "FS.f", "FLUID.f", "HEATS.f", "LHSA.f",
               "EQASSEM.f", "PIC.f", "SETBC.f", "BAFINI.f"):
         lib.add_file(os.path.join(S, f))
-    for f in ("LHS.f", "BC.f", "INCOMMU.f"):                 # FSILSINI calls FSILS_BC_CREATE on COMMOD's lhs
-        lib.add_file(os.path.join(LS, f))
+    for f in sorted(os.listdir(LS)):                         # FSILSINI / LSSOLVE call into svFSILS on COMMOD's lhs
+        if f.endswith(".f"):
+            lib.add_file(os.path.join(LS, f))
 
     def dgesv(n, nrhs, a, lda, ipiv, b, ldb, info):
         """LAPACK DGESV (the reference links LAPACK): A <- LU, B <- solution, INFO handed back"""
@@ -52,7 +53,7 @@ def svfsi_gen():
         ipiv[:n] = piv + 1
         return (int(inf),)
 
-    gen = rx.CodeGen(lib, externals={"dgesv": dgesv})
+    gen = rx.CodeGen(lib, externals={"dgesv": dgesv, "fsils_cput": lambda: 0.0})
     gen.ext_outs["dgesv"] = [7]
 
     class Cm:                        # svFSI's communicator object (CMMOD, type-bound procedures), one task
@@ -571,6 +572,94 @@ def main():
                     f"{fname}_val": np.array(f.val).T.copy(), f"{fname}_gN": gN})
         print(f"  FSILSINI {fname}: lsPtr={lsPtr} bGrp={f.bgrp} nNo={f.nno} |val|={np.abs(f.val).max():.4e}")
     np.savez_compressed(os.path.join(HERE, "ref_fsilsini_lattice.npz"), **ini)
+
+    # ---- the Newton / time loop of S/MAIN.f:111-206 composed from the reference's own routines: two time steps of three
+    # Newton iterations on the pipe (steady parabolic Dirichlet inlet along the normal, no-slip wall, resistance outlet
+    # coupled through res = gam dt r).  The loop below restates MAIN.f's ORDER of calls and its three bookkeeping lines
+    # (R = 0 / Val = 0 of LSALLOC, incL / res of :186-192, Ao = An / Yo = Yn of :277-279); everything else is executed
+    # from source: PICP, SETBCDIR(L), PICI, CONSTRUCT_FLUID, SETBCNEUL, FSILS_SOLVE (LSSOLVE's call), PICC.
+    ga = cm.GA
+    nN = p.rm.nNo
+    rngl = np.random.default_rng(21)
+    Ao = 0.05 * rngl.standard_normal((nN, 4)); Ao[:, 3] = 0.0
+    Yo = p.Yg.copy()
+    resist = 60.0
+    gin, gw = p.faces["inlet"]["gN"], p.faces["wall"]["gN"]
+    xin = p.rm.x[gin - 1]
+    gx_in = np.clip(1.0 - (xin[:, 0] ** 2 + xin[:, 1] ** 2) / (np.abs(p.rm.x[:, :2]).max() ** 2), 0.0, None)
+    gout, fIENo, gEo = cm.local_face(m, p.rm, "outlet")
+    # state of COMMOD for the loop (the element-loop call below also (re)creates eq, msh, x, rowPtr, ...)
+    element_loop(gen, p.rm.x, p.rm.IEN, p.rowPtr, p.colPtr, p.Ag, p.Yg, cm.RHO, cm.MU, cm.F, cm.DT, ga["af"], ga["am"], ga["gam"])
+    eq = M.eq[0]
+    faces_l, bcs_l = [], []
+    for k, (fname, g, gxv) in enumerate((("inlet", -12.0, gx_in), ("wall", 0.0, np.ones(gw.size))), start=1):
+        gNf = p.faces[fname]["gN"]
+        fa = rt.new("facetype")
+        fa.nno, fa.gn = int(gNf.size), gNf.astype(np.int64)
+        fa.nv = np.asfortranarray(np.tile(np.array([[0.0], [0.0], [-1.0]]), (1, gNf.size)))
+        bc = rt.new("bctype")
+        bc.btype = (1 << M.btype_dir) | (1 << M.btype_std)
+        bc.weakdir, bc.ifa, bc.im, bc.g, bc.gx = False, k, 1, g, np.array(gxv, dtype=np.float64)
+        bc.edrn = np.zeros(int(M.maxnsd), dtype=np.int64)
+        faces_l.append(fa); bcs_l.append(bc)
+    lFo = rt.new("facetype")
+    lFo.im, lFo.enon, lFo.nel, lFo.nno = 1, 3, int(fIENo.shape[0]), int(gout.size)
+    lFo.ien, lFo.ge, lFo.gn = np.asfortranarray(fIENo.T.astype(np.int64)), gEo.astype(np.int64), gout.astype(np.int64)
+    gen.get("selecteleb")(M.msh[0], lFo)
+    bco = rt.new("bctype")
+    bco.btype = (1 << M.btype_neu) | (1 << M.btype_res)
+    bco.r, bco.g, bco.flwp, bco.gx, bco.ifa, bco.im = resist, 0.0, False, np.ones(gout.size), 3, 1
+    faces_l.append(lFo); bcs_l.append(bco)
+    M.msh[0].fa = rx.FList(faces_l)
+    eq.bc, eq.nbc = rx.FList(bcs_l), 3
+    eq.s, eq.e, eq.dof, eq.phys, eq.coupled = 1, 4, 4, M.phys_fluid, False
+    eq.gam, eq.beta, eq.am, eq.af = float(ga["gam"]), float(ga["beta"]), float(ga["am"]), float(ga["af"])
+    eq.tol, eq.abstol, eq.minitr, eq.maxitr = 1e-30, 1e-30, 1, 3
+    eq.dmn[0].prop[M.backflow_stab - 1] = 0.2
+    M.psteq, M.ibflag, M.eccpld, M.dflag, M.ssteq, M.cmminit, M.neq, M.ceq = False, False, False, False, False, False, 1, 1
+    # COMMOD's lhs with its three faces (FSILS_LHS_CREATE + FSILSINI), the equation's linear solver (FSILS_LS_CREATE)
+    commu = rt.new("fsils_commutype")
+    commu.foc, commu.masf, commu.master, commu.task, commu.tf, commu.ntasks, commu.comm = True, True, 0, 0, 1, 1, 0
+    M.lhs = rt.new("fsils_lhstype")
+    gen.get("fsils_lhs_create")(M.lhs, commu, nN, nN, int(p.colPtr.size), np.arange(1, nN + 1, dtype=np.int64),
+                                p.rowPtr.astype(np.int64), p.colPtr.astype(np.int64), 3)
+    lsPtr = 0
+    for bc, fa in zip(bcs_l[:2], faces_l[:2]):
+        fa.im, fa.enon, fa.nel = 1, 3, 0
+    for bc, fa in zip(bcs_l, faces_l):
+        (lsPtr,) = gen.get("fsilsini")(bc, fa, lsPtr)
+    gen.get("fsils_ls_create")(eq.fsils, int(M.ls_type_gmres), 1e-5, 1e-14, 10, 80)
+    F = lambda a: np.asfortranarray(a.T.copy())
+    M.ao, M.yo, M.do = F(Ao), F(Yo), np.zeros((4, nN), order="F")
+    M.an, M.yn, M.dn = np.zeros_like(M.ao), np.zeros_like(M.ao), np.zeros_like(M.ao)
+    M.nfacesls = 3
+    lp = dict(Ao=Ao, Yo=Yo, resist=resist, gx_in=gx_in, inlet_g=-12.0, relTol=1e-5, absTol=1e-14, maxItr=10, dimKry=80)
+    norms, fluxes = [], []
+    for ts in range(2):
+        eq.itr, eq.ok, eq.inorm = 0, False, 0.0                                   # S/MAIN.f:99-100
+        gen.get("picp")()
+        gen.get("setbcdir")(M.an, M.yn, M.dn)
+        for it in range(3):
+            Ag, Yg, Dg = (np.full((4, nN), np.nan, order="F") for _ in range(3))
+            gen.get("pici")(Ag, Yg, Dg)
+            M.r = np.zeros((4, nN), order="F")                                    # LSALLOC, S/LS.f:44-51
+            M.val = np.zeros((16, p.colPtr.size), order="F")
+            gen.get("construct_fluid")(M.msh[0], Ag, Yg)
+            fluxes.append(float(gen.get("integv")(lFo, np.asfortranarray(M.yn[:3, :]))))
+            gen.get("setbcneul")(bco, lFo, Yg, Dg)
+            incL = np.zeros(3, dtype=np.int64); resv = np.zeros(3)
+            for bc in bcs_l:                                                      # S/MAIN.f:186-192
+                if bc.lsptr != 0:
+                    resv[bc.lsptr - 1] = eq.gam * M.dt * bc.r
+                    incL[bc.lsptr - 1] = 1
+            gen.get("fsils_solve")(M.lhs, eq.fsils, 4, M.r, M.val, int(M.precond_fsils), incL, resv)   # LSSOLVE, S/LS.f:92
+            norms.append((eq.fsils.ri.inorm, eq.fsils.ri.itr))
+            gen.get("picc")()
+        M.ao, M.yo = M.an.copy(order="F"), M.yn.copy(order="F")                   # S/MAIN.f:277-279
+    lp.update(norms=np.array(norms), fluxes=np.array(fluxes), An=M.an.T.copy(), Yn=M.yn.T.copy())
+    print(f"  time loop: iNorm/itr per Newton iteration = {[(float(f'{a:.4e}'), int(b)) for a, b in norms]}")
+    np.savez_compressed(os.path.join(HERE, "ref_timeloop_lattice.npz"), **lp)
+    eq.nbc = 0
 
     # ---- generalised-alpha predictor / initiator / corrector (S/PIC.f) on random states
     rng = np.random.default_rng(17)

@@ -269,3 +269,68 @@ def test_reference_routines_with_known_answers():
     assert abs(g.get("norms")(u, v) - float(u @ v)) <= 1e-14
     V = np.asfortranarray(rng.standard_normal((3, 2)))
     assert np.allclose(g.get("cross")(V), np.cross(V[:, 0], V[:, 1]), rtol=1e-14, atol=1e-15)
+
+
+def test_do_while_cycle_array_intrinsics_and_odd_spellings(tmp_path):
+    src = (
+        "      SUBROUTINE S(a, n, tot, mx, dp, cnt, bits)\n"
+        "      INTEGER, INTENT(IN) :: n\n"
+        "      REAL(KIND=8), INTENT(IN) :: a(3,n)\n"
+        "      REAL(KIND=8), INTENT(OUT) :: tot, mx, dp\n"
+        "      INTEGER, INTENT(OUT) :: cnt, bits\n"
+        "      REAL(KIND=8) Do(3)\n"
+        "      INTEGER i\n"
+        "      Do = 0D0\n"
+        "      i = 0\n"
+        "      cnt = 0\n"
+        "      DO WHILE (i .LT. n)\n"
+        "         i = i + 1\n"
+        "         IF (MOD(i,2).EQ.0 .OR . a(1,i).LT.0D0) CYCLE\n"
+        "         Do = Do + a(:,i)\n"
+        "         cnt = cnt + 1\n"
+        "      END DO\n"
+        "      tot = SUM(Do)\n"
+        "      mx = MAXVAL(ABS(a))\n"
+        "      dp = DOT_PRODUCT(a(:,1), a(:,n))\n"
+        "      bits = 0\n"
+        "      bits = IBSET(bits, 3)\n"
+        "      IF (BTEST(bits,3) .AND. .NOT.BTEST(bits,2)) bits = bits + 100\n"
+        "      END SUBROUTINE S\n")
+    a = np.asfortranarray(np.array([[1.0, 2.0, 3.0], [9.0, 9.0, 9.0], [-1.0, 5.0, 5.0], [4.0, 4.0, 4.0], [0.5, 0.25, -8.0]]).T)
+    tot, mx, dp, cnt, bits = _gen(tmp_path, src).get("s")(a, 5, 0.0, 0.0, 0.0, 0, 0)
+    assert cnt == 2 and tot == (1 + 2 + 3) + (0.5 + 0.25 - 8.0)        # columns 1 and 5 (3 is negative, 2 and 4 are even)
+    assert mx == 9.0 and dp == 1 * 0.5 + 2 * 0.25 + 3 * (-8.0) and bits == 108
+
+
+def test_generic_interfaces_resolve_by_rank_and_type(tmp_path):
+    src = (
+        "      MODULE M\n"
+        "      INTERFACE TWICE\n"
+        "         MODULE PROCEDURE TWICES, TWICEV, TWICEI\n"
+        "      END INTERFACE TWICE\n"
+        "      CONTAINS\n"
+        "      FUNCTION TWICES(x)\n"
+        "      REAL(KIND=8), INTENT(IN) :: x\n"
+        "      REAL(KIND=8) TWICES\n"
+        "      TWICES = 2D0*x\n"
+        "      END FUNCTION TWICES\n"
+        "      FUNCTION TWICEV(x)\n"
+        "      REAL(KIND=8), INTENT(IN) :: x(:)\n"
+        "      REAL(KIND=8) TWICEV\n"
+        "      TWICEV = 2D0*SUM(x)\n"
+        "      END FUNCTION TWICEV\n"
+        "      FUNCTION TWICEI(i)\n"
+        "      INTEGER, INTENT(IN) :: i\n"
+        "      REAL(KIND=8) TWICEI\n"
+        "      TWICEI = -2D0*i\n"
+        "      END FUNCTION TWICEI\n"
+        "      END MODULE M\n"
+        "      SUBROUTINE S(v, r1, r2, r3)\n"
+        "      REAL(KIND=8), INTENT(IN) :: v(3)\n"
+        "      REAL(KIND=8), INTENT(OUT) :: r1, r2, r3\n"
+        "      r1 = TWICE(v(2))\n"
+        "      r2 = TWICE(v)\n"
+        "      r3 = TWICE(7)\n"
+        "      END SUBROUTINE S\n")
+    r1, r2, r3 = _gen(tmp_path, src).get("s")(np.array([1.0, 2.0, 4.0]), 0.0, 0.0, 0.0)
+    assert (r1, r2, r3) == (4.0, 14.0, -14.0)

@@ -401,6 +401,7 @@ class Runtime:
     def __init__(self, types):
         self.types = types
         self.evaltext = None       # set by CodeGen: evaluates a constant expression given as Fortran text
+        self.files = {}            # unit -> {record number: bytes} of direct-access unformatted WRITEs
 
     # -- allocation
     def alloc(self, kind, dims):
@@ -671,6 +672,24 @@ class Runtime:
     @staticmethod
     def f_pow(a, b):
         return a ** b
+
+    def write_rec(self, unit, rec, items):
+        """WRITE(unit, REC=rec) list  on a direct-access unformatted file: the items' storage in list order
+        (default INTEGER / LOGICAL 4 bytes, REAL(KIND=8) 8 bytes, arrays in column-major element order), kept in
+        memory as self.files[unit][rec]"""
+        out = b""
+        for it in items:
+            if isinstance(it, (bool, np.bool_)):
+                out += np.int32(1 if it else 0).tobytes()
+            elif isinstance(it, (int, np.integer)):
+                out += np.int32(it).tobytes()
+            elif isinstance(it, float):
+                out += np.float64(it).tobytes()
+            else:
+                a = np.asarray(it)
+                a = a.astype("<i4") if a.dtype.kind in "iub" else a.astype("<f8")
+                out += a.reshape(-1, order="F").tobytes()
+        self.files.setdefault(int(unit), {})[int(rec)] = out
 
     @staticmethod
     def do_final(lo, hi, st):
@@ -1629,6 +1648,16 @@ class Scope:
 
     def simple(self, st, L, pad):
         t = st.text
+        m = re.match(r"^write\s*\(\s*(\w+)\s*,\s*rec\s*=\s*(.+?)\)\s*(.+)$", t)
+        if m:       # direct-access unformatted record
+            items = ", ".join(self.expr(parse_expr(x)) for x in _split_top(m.group(3)))
+            L.append(f"{pad}_rt.write_rec({self.expr(parse_expr(m.group(1)))}, {self.expr(parse_expr(m.group(2)))}, ({items},))")
+            return
+        m = re.match(r"^call\s+cm\s*%\s*(\w+)\s*\((.*)\)$", t)
+        if m and self.lookup("cm")[0] == "global":      # type-bound procedure of svFSI's communicator object
+            args = ", ".join(self.expr(parse_expr(x)) for x in _split_top(m.group(2))) if m.group(2).strip() else ""
+            L.append(f"{pad}_m.cm.{m.group(1)}({args})")
+            return
         if t in ("continue",) or re.match(r"^(print|write|read|open|close|flush|rewind|inquire)\b", t):
             L.append(f"{pad}pass")
             return

@@ -38,7 +38,7 @@ def svfsi_gen():
     for h in ("FSILS_TYPEDEF.h", "FSILS_STRUCT.h"):          # eqType carries an FSILS_lsType
         lib.add_include(os.path.join(LS, h))
     for f in ("CONSTS.f", "TYPEMOD.f", "UTIL.f", "MOD.f", "ALLFUN.f", "NN.f", "FS.f", "FLUID.f", "HEATS.f", "LHSA.f",
-              "EQASSEM.f", "PIC.f", "SETBC.f", "BAFINI.f"):
+              "EQASSEM.f", "PIC.f", "SETBC.f", "BAFINI.f", "OUTPUT.f"):
         lib.add_file(os.path.join(S, f))
     for f in sorted(os.listdir(LS)):                         # FSILSINI / LSSOLVE call into svFSILS on COMMOD's lhs
         if f.endswith(".f"):
@@ -53,7 +53,8 @@ def svfsi_gen():
         ipiv[:n] = piv + 1
         return (int(inf),)
 
-    gen = rx.CodeGen(lib, externals={"dgesv": dgesv, "fsils_cput": lambda: 0.0})
+    gen = rx.CodeGen(lib, externals={"dgesv": dgesv, "fsils_cput": lambda: 0.0, "cput": lambda: 1.5,
+                                     "str": lambda *a: str(a[0])})      # (number -> text, only ever used in messages / file names)
     gen.ext_outs["dgesv"] = [7]
 
     class Cm:                        # svFSI's communicator object (CMMOD, type-bound procedures), one task
@@ -64,6 +65,18 @@ def svfsi_gen():
         @staticmethod
         def reduce(v, *a):
             return v
+
+        @staticmethod
+        def mas():
+            return True
+
+        @staticmethod
+        def tf():
+            return 1
+
+        @staticmethod
+        def bcast(*a):
+            return None
     gen.M.cm = Cm()
     gen.M.ikind, gen.M.rkind = 4, 8     # kind numbers (only ever passed as KIND= arguments)
     for n in ("mpint", "mpreal", "mplog", "mpchar", "mpi_sum", "mpi_max", "mpi_min", "stdout"):
@@ -699,6 +712,23 @@ def main():
     M.eq[0].nbc = 0
     print(f"  SETBCDIR: {int((pc['dir_A1'] != pc['dir_A0']).any(axis=1).sum())} nodes overwritten")
     np.savez_compressed(os.path.join(HERE, "ref_pic.npz"), **pc)
+
+    # ---- restart record: WRITERESTART (S/OUTPUT.f:132-232), fluid case (no displacement, no IB, no CEP)
+    nX = 2
+    M.stamp = np.array([1, 1, 1, nN, nX, 4, 0], dtype=np.int64)        # INITIALIZE.f:152
+    M.cts, M.time, M.stfilename, M.stfilerepl, M.cepeq = 37, 0.185, "stFile", True, False
+    M.recln = 4 * (1 + 7) + 8 * (2 + 1 + nX + 2 * 4 * nN)              # INITIALIZE.f:163
+    cplr = rt.new("cplbctype"); cplr.xn = np.array([333.25, -12.5]); M.cplbc = cplr
+    M.eq[0].inorm = 6.963e3
+    rs_Yn, rs_An = rngl.standard_normal((nN, 4)), rngl.standard_normal((nN, 4))
+    M.yn, M.an = np.asfortranarray(rs_Yn.T.copy()), np.asfortranarray(rs_An.T.copy())
+    gen.rt.files.clear()
+    gen.get("writerestart")(np.array([0.25, 0.0, 0.0]))
+    rec = gen.rt.files[27][1]
+    print(f"  WRITERESTART: record of {len(rec)} bytes (recLn = {M.recln})")
+    np.savez_compressed(os.path.join(HERE, "ref_restart.npz"), record=np.frombuffer(rec, dtype=np.uint8), recLn=M.recln,
+                        stamp=np.array(M.stamp), cTS=M.cts, time=M.time, timeP=1.5 - 0.25, iNorm=np.array([6.963e3]),
+                        xn=np.array(cplr.xn), Yn=rs_Yn, An=rs_An)
 
     # ---- RCR (Windkessel) outlets: RCR_Integ_X (S/SETBC.f:1292-1372), two faces, three consecutive time steps
     cpl = rt.new("cplbctype")

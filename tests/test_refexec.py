@@ -334,3 +334,21 @@ def test_generic_interfaces_resolve_by_rank_and_type(tmp_path):
         "      END SUBROUTINE S\n")
     r1, r2, r3 = _gen(tmp_path, src).get("s")(np.array([1.0, 2.0, 4.0]), 0.0, 0.0, 0.0)
     assert (r1, r2, r3) == (4.0, 14.0, -14.0)
+
+
+def test_direct_access_write_is_captured_as_bytes(tmp_path):
+    src = (
+        "      SUBROUTINE S(a, n)\n"
+        "      INTEGER, INTENT(IN) :: n\n"
+        "      REAL(KIND=8), INTENT(IN) :: a(2,n)\n"
+        "      LOGICAL flag\n"
+        "      flag = .TRUE.\n"
+        "      OPEN(27, FILE='x.bin', ACCESS='DIRECT', RECL=64)\n"
+        "      WRITE(27, REC=n+1) n, flag, 2.5D0, a\n"
+        "      CLOSE(27)\n"
+        "      END SUBROUTINE S\n")
+    g = _gen(tmp_path, src)
+    a = np.asfortranarray(np.array([[1.0, 3.0], [2.0, 4.0]]))
+    g.get("s")(a, 2)
+    want = np.array([2, 1], dtype="<i4").tobytes() + np.array([2.5, 1.0, 2.0, 3.0, 4.0], dtype="<f8").tobytes()
+    assert g.rt.files[27][3] == want          # list order, column-major array elements, 4-byte INTEGER / LOGICAL
